@@ -1,0 +1,150 @@
+/*
+ * sbx_oracle.h -- CPU restatement of the reference's drainage + interference hot path.
+ *
+ * TEST INFRASTRUCTURE ONLY.  Nothing in the product path (soap_bubble_simulation_b200/,
+ * include/, libsbx.so) may include, link or call this file; only tests/, __graft_entry__.smoke()
+ * and bench.py's cpu_baseline / --impl reference leg use it, and only as the checker / the CPU
+ * baseline.
+ *
+ * PARITY PINNING STATUS: *partially pinned*.  The reference (Rust 2024, wgpu) cannot be compiled
+ * or imported in this image (no cargo/rustc), and its own tests hold NO golden vectors for the
+ * drainage step -- only property tests and two closed-form known answers.  This restatement is
+ * pinned against every one of those (tests/test_oracle_reference_tests.py restates each reference
+ * unit test of drainage.rs:616-720, interference.rs:612-792, interference_lut.rs:165-205) and
+ * against closed-form identities derived from the cited formulas; the drainage numbers themselves
+ * are "parity unpinned" in the sense of the task statement.
+ *
+ * All citations are file:line relative to the reference repository root.
+ * Build: gcc -O2 -ffp-contract=off -fno-fast-math (Rust never contracts FMAs; glibc libm is what
+ * Rust's f64::sin/cos/powf lower to on Linux).
+ */
+#ifndef SBX_ORACLE_H
+#define SBX_ORACLE_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ------------------------------------------------------------------ drainage (f64) */
+
+#define ORC_MAX_FRONTS 8 /* src/physics/drainage.rs:474 */
+
+typedef struct {
+    double phi_center, extent, width, velocity; /* src/physics/drainage.rs:23-33 */
+} orc_tfe_front;
+
+typedef struct orc_drainage orc_drainage;
+
+/* DrainageSimulator::new (src/physics/drainage.rs:263-288) with the config fields it reads
+ * passed explicitly; num_theta = resolution, num_phi = 2*resolution in the reference, but any
+ * shape is accepted here. */
+orc_drainage *orc_drainage_create(int num_theta, int num_phi, double h0_m, double density,
+                                  double gravity, double viscosity, double diffusion,
+                                  double critical_thickness_m, double radius_m);
+void orc_drainage_destroy(orc_drainage *s);
+
+/* DrainageSimulator::step (src/physics/drainage.rs:298-392).  nthreads > 1 runs the interior
+ * row loop with OpenMP over theta rows (bit-identical results: rows only read `scratch`). */
+void orc_drainage_step(orc_drainage *s, double dt);
+void orc_drainage_set_threads(orc_drainage *s, int nthreads);
+
+double *orc_drainage_data(orc_drainage *s); /* ThicknessField::data_mut, row-major [theta][phi] */
+int orc_drainage_num_theta(const orc_drainage *s);
+int orc_drainage_num_phi(const orc_drainage *s);
+double orc_drainage_delta_theta(const orc_drainage *s);
+double orc_drainage_delta_phi(const orc_drainage *s);
+double orc_drainage_get_thickness(const orc_drainage *s, double theta, double phi); /* :516-552 */
+double orc_drainage_min(const orc_drainage *s);                                     /* :180-185 */
+double orc_drainage_max(const orc_drainage *s);                                     /* :188-193 */
+int orc_drainage_has_critical(const orc_drainage *s);                               /* :565-567 */
+double orc_drainage_critical(const orc_drainage *s);                                /* :570-572 */
+double orc_drainage_time(const orc_drainage *s);                                    /* :560-562 */
+void orc_drainage_reset(orc_drainage *s, double h0_m);                              /* :575-583 */
+void orc_drainage_set_marginal_regeneration(orc_drainage *s, int enabled);          /* :588-593 */
+int orc_drainage_marginal_regeneration(const orc_drainage *s);                      /* :596-598 */
+void orc_drainage_set_tfe_ratio(orc_drainage *s, double ratio);                     /* :601-603 */
+double orc_drainage_tfe_ratio(const orc_drainage *s);                               /* :606-608 */
+int orc_drainage_active_tfe_count(const orc_drainage *s);                           /* :611-613 */
+int orc_drainage_fronts(const orc_drainage *s, orc_tfe_front *out);                 /* returns count */
+double orc_drainage_next_spawn(const orc_drainage *s);
+
+/* ------------------------------------------------------------------ WGSL drainage (f32) */
+
+/* Mirror of DrainageParams (src/render/gpu_drainage.rs:10-44; src/render/shaders/drainage.wgsl:14-31). */
+typedef struct {
+    float dt, gravity, viscosity, density, diffusion_coeff, bubble_radius, critical_thickness;
+    uint32_t grid_width, grid_height, marangoni_enabled;
+    float gamma_air, gamma_reduction, surfactant_diffusion, marangoni_coeff;
+    uint32_t _padding1, _padding2;
+} orc_wgsl_params;
+
+void orc_wgsl_params_default(orc_wgsl_params *p); /* src/render/gpu_drainage.rs:46-68 */
+
+/* One dispatch of drainage.wgsl::drainage_step (src/render/shaders/drainage.wgsl:72-202) over
+ * the whole grid; in/out must not alias. */
+void orc_wgsl_step(const orc_wgsl_params *p, const float *h_in, const float *c_in, float *h_out,
+                   float *c_out);
+
+/* ------------------------------------------------------------------ interference (f64) */
+
+typedef struct {
+    double n_film, n_medium, wavelengths_nm[3]; /* src/physics/interference.rs:127-134 */
+} orc_interference;
+
+void orc_interference_new(orc_interference *c, double n_film); /* :141-151 */
+double orc_transmission_angle_cos(const orc_interference *c, double cos_i);            /* :197-211 */
+double orc_optical_path_difference(const orc_interference *c, double d_nm, double cos_t,
+                                   double wavelength_nm);                              /* :226-238 */
+double orc_phase_difference(double opd_nm, double wavelength_nm);                      /* :248-254 */
+void orc_fresnel_reflection(const orc_interference *c, double cos_i, double out_s_p_avg[3]); /* :266-298 */
+double orc_reflected_intensity(const orc_interference *c, double d_nm, double cos_i,
+                               double wavelength_nm);                                  /* :312-353 */
+void orc_interference_color(const orc_interference *c, double d_nm, double cos_i, double rgb[3]);        /* :380-400 */
+void orc_interference_color_linear(const orc_interference *c, double d_nm, double cos_i, double rgb[3]); /* :413-426 */
+void orc_rgb_to_u8(const double rgb[3], uint8_t out[3]);                               /* :73-79 */
+/* generate_color_lookup_table (:461-477): out = num_samples x 3 doubles */
+void orc_color_lut_1d(const orc_interference *c, double min_nm, double max_nm, int num_samples,
+                      double cos_theta, double *out);
+/* generate_2d_color_lookup_table (:491-512): out[thickness_idx][angle_idx][3] */
+void orc_color_lut_2d(const orc_interference *c, double min_nm, double max_nm, int thickness_samples,
+                      int angle_samples, double *out);
+/* batch: rgb[i] = color(d_nm[i], cos_i[i]); gamma != 0 -> :380-400 else :413-426 */
+void orc_interference_batch(const orc_interference *c, const double *d_nm, const double *cos_i,
+                            size_t n, int gamma, double *rgb);
+
+/* wall.wgsl:165-207 variant: Schlick Fresnel + transmitted Airy at 650/532/450 nm (f32) */
+void orc_schlick_wall_rgb(float d_nm, float cos_i, float n_film, float rgb[3]);
+
+/* ------------------------------------------------------------------ interference LUT (f32) */
+
+#define ORC_LUT_THICKNESS_SAMPLES 256   /* src/render/interference_lut.rs:9  */
+#define ORC_LUT_ANGLE_SAMPLES 64        /* src/render/interference_lut.rs:10 */
+#define ORC_LUT_MAX_THICKNESS_NM 2000.f /* src/render/interference_lut.rs:13 */
+
+void orc_thin_film_interference(float d_nm, float cos_theta, float n_film, float intensity,
+                                float rgb[3]);                             /* :45-93 */
+void orc_generate_interference_lut(float n_film, float intensity, uint8_t *out_rgba); /* :18-41 */
+/* generalisation used by the spectral sweep (BASELINE config 5): same algorithm, n_lambda
+ * wavelengths normalised by n_lambda, T x A texels over [0,max_nm] x [0,1]. */
+void orc_generate_lut_spectral(float n_film, float intensity, const float *wavelengths_nm,
+                               int n_lambda, int T, int A, float max_nm, uint8_t *out_rgba);
+float orc_snells_law(float cos_i, float n_film);                               /* :96-100 */
+float orc_fresnel_unpolarized(float cos_i, float cos_t, float n1, float n2);   /* :103-120 */
+
+/* bubble.wgsl:425-439 consumer semantics: bilinear, clamp-to-edge, texel-centre addressing of an
+ * RGBA8-unorm T x A LUT at uv = (d/max_nm, cos), times intensity, clamped to [0,1]. */
+void orc_lut_shade(const uint8_t *lut_rgba, int T, int A, float max_nm, float d_nm, float cos_theta,
+                   float intensity, float rgb[3]);
+
+/* view cosine for cell (theta,phi) of a sphere of radius R seen from camera position cam:
+ * n = (sin th cos ph, cos th, sin th sin ph) (src/physics/geometry.rs:184-186), world = R n,
+ * cos = |dot(normalize(cam - world), n)| (src/render/shaders/bubble.wgsl:487-494). */
+double orc_view_cos(double theta, double phi, double radius, const double cam[3]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif
