@@ -1,0 +1,1285 @@
+// sbx_api.cu -- the C ABI of libsbx.so (include/sbx.h): handles, host-side state machines
+// (time, TFE fronts, ping-pong), coefficient tables, and kernel sequencing.  All arithmetic on the
+// thickness field happens in the kernels of sbx_kernels.cu; there is no CPU fallback.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "sbx_comm.h"
+#include "sbx_launch.h"
+
+#ifndef M_PI
+#define M_PI 3.14159265358979323846
+#endif
+#ifndef M_PI_2
+#define M_PI_2 1.57079632679489661923
+#endif
+
+using namespace sbx;
+
+// ------------------------------------------------------------------ errors
+static thread_local std::string g_err;
+
+static int32_t fail(int32_t code, const char *fmt, ...)
+{
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_err = buf;
+    return code;
+}
+
+#define CU(expr)                                                                                   \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(e__ == cudaErrorMemoryAllocation ? SBX_ERR_NOMEM : SBX_ERR_CUDA,           \
+                        "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), __FILE__, __LINE__); \
+    } while (0)
+
+#define CHECK_H(h)                                             \
+    if (!(h)) return fail(SBX_ERR_INVALID, "null handle");     \
+    CU(cudaSetDevice((h)->device))
+
+extern "C" const char *sbx_last_error(void) { return g_err.c_str(); }
+
+extern "C" int32_t sbx_version(int32_t *major, int32_t *minor)
+{
+    if (major) *major = SBX_VERSION_MAJOR;
+    if (minor) *minor = SBX_VERSION_MINOR;
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_device_count(int32_t *count)
+{
+    int n = 0;
+    CU(cudaGetDeviceCount(&n));
+    if (count) *count = n;
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_host_alloc(size_t bytes, void **out)
+{
+    if (!out) return fail(SBX_ERR_INVALID, "out is null");
+    CU(cudaHostAlloc(out, bytes, cudaHostAllocDefault));
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_host_free(void *p)
+{
+    CU(cudaFreeHost(p));
+    return SBX_OK;
+}
+
+// ------------------------------------------------------------------ handle
+struct sbx_drainage {
+    sbx_drainage_cfg cfg{};
+    int device = 0;
+    int num_theta = 0, num_phi = 0, batch = 1;
+    int row_begin = 0, row_end = 0, rows_local = 0;
+    bool f64 = false, strict = false, wgsl = false;
+    size_t esz = 4;
+    long long bubble_stride = 0;  // elements
+    long long total_elems = 0;
+
+    cudaStream_t own_stream = nullptr, stream = nullptr;
+    void *buf[2] = {nullptr, nullptr};   // thickness ping-pong
+    float *conc[2] = {nullptr, nullptr}; // WGSL concentration ping-pong
+    int cur = 0;
+
+    void *coefS = nullptr;      // T x 4 per global row
+    float2 *rowSC = nullptr;
+    double4 *coefX = nullptr;
+    float *rowW = nullptr;      // WGSL per-row float4
+    void *bub = nullptr;        // BubbleParam<T>[batch]
+    double *pole_partial = nullptr;
+    int pole_slots_cap = 0;
+    double *mm_part = nullptr;  // minmax partials
+    double *mm_host = nullptr;  // pinned
+    double *scalar_dev = nullptr;
+    double *scalar_host = nullptr;  // pinned
+    static constexpr int kMinmaxBlocks = 592;
+
+    // physics (the Rust struct's fields, drainage.rs:219-235)
+    double density, gravity, viscosity, diffusion, critical, radius;
+    std::vector<double> b_h0, b_radius, b_href;  // per bubble
+    double h_ref = 0.0;
+    double *href_dev = nullptr;  // per-bubble storage offsets (f64) for the conversion kernels
+    bool href_zero = true;
+    double coefA = 0.0;
+    bool tables_dirty = true;
+    sbx_drainage_params wp{};  // WGSL params
+
+    // time + TFE state machine (drainage.rs:237-255)
+    double time = 0.0;
+    std::vector<sbx_tfe_front> fronts;
+    double tfe_ratio = 0.85;
+    bool tfe_enabled = true;
+    double next_spawn = 0.5, spawn_interval = 2.0;
+
+    // colour stage
+    void *rgb_buf = nullptr;
+    size_t rgb_bytes = 0;
+    int rgb_format = -1;
+    float *colA = nullptr;
+    double cam_cached[3] = {NAN, NAN, NAN};
+    cudaArray_t lut_array = nullptr;
+    cudaTextureObject_t lut_tex = 0;
+    float lut_n = -1.f;
+    float lut_max_nm = 2000.f;
+    bool lut_user = false;
+
+    sbx_comm *comm = nullptr;
+    int band_rows = 0;
+    int64_t launches = 0;
+};
+
+template <typename T>
+static T *tbuf(sbx_drainage *h, int i) { return reinterpret_cast<T *>(h->buf[i]); }
+
+static void free_all(sbx_drainage *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    for (int i = 0; i < 2; ++i) {
+        if (h->buf[i]) cudaFree(h->buf[i]);
+        if (h->conc[i]) cudaFree(h->conc[i]);
+    }
+    cudaFree(h->coefS);
+    cudaFree(h->rowSC);
+    cudaFree(h->coefX);
+    cudaFree(h->rowW);
+    cudaFree(h->bub);
+    cudaFree(h->pole_partial);
+    cudaFree(h->mm_part);
+    cudaFree(h->scalar_dev);
+    cudaFree(h->rgb_buf);
+    cudaFree(h->colA);
+    cudaFree(h->href_dev);
+    if (h->mm_host) cudaFreeHost(h->mm_host);
+    if (h->scalar_host) cudaFreeHost(h->scalar_host);
+    if (h->lut_tex) cudaDestroyTextureObject(h->lut_tex);
+    if (h->lut_array) cudaFreeArray(h->lut_array);
+    if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    delete h;
+}
+
+extern "C" int32_t sbx_drainage_cfg_default(sbx_drainage_cfg *c)
+{
+    if (!c) return fail(SBX_ERR_INVALID, "cfg is null");
+    memset(c, 0, sizeof *c);
+    c->num_theta = 128;  // resolution, src/config.rs:313
+    c->num_phi = 256;    // 2 * resolution, src/physics/drainage.rs:265
+    c->batch = 1;
+    c->h0_m = 500.0 * 1e-9;               // film_thickness_nm * 1e-9, config.rs:30,369-371
+    c->density = 1000.0;                  // config.rs:61
+    c->gravity = 9.81;                    // config.rs:96
+    c->viscosity = 0.001;                 // config.rs:59
+    c->diffusion = 1e-9;                  // config.rs:62
+    c->critical_thickness_m = 10.0 * 1e-9;  // config.rs:31, drainage.rs:278
+    c->radius_m = 0.05 / 2.0;             // config.rs:29,356-358
+    c->semantics = SBX_SEM_CPU;
+    c->precision = SBX_PREC_F32;
+    c->h_ref_m = 0.0;
+    c->tfe_enabled = 1;  // drainage.rs:284
+    c->tfe_ratio = 0.85; // drainage.rs:283
+    sbx_drainage_params &p = c->wgsl;  // gpu_drainage.rs:46-68
+    p.dt = 0.001f; p.gravity = 9.81f; p.viscosity = 0.001f; p.density = 1000.0f;
+    p.diffusion_coeff = 1e-9f; p.bubble_radius = 0.025f; p.critical_thickness = 30e-9f;
+    p.grid_width = 128; p.grid_height = 64; p.marangoni_enabled = 0;
+    p.gamma_air = 0.072f; p.gamma_reduction = 0.045f; p.surfactant_diffusion = 1e-9f;
+    p.marangoni_coeff = 0.01f;
+    return SBX_OK;
+}
+
+// ------------------------------------------------------------------ coefficient tables
+template <typename T>
+static int32_t upload_bubbles(sbx_drainage *h)
+{
+    std::vector<BubbleParam<T>> bp((size_t)h->batch);
+    for (int b = 0; b < h->batch; ++b) {
+        const double rb = h->b_radius[b];
+        bp[b].diff_scale = (T)((h->radius / rb) * (h->radius / rb));
+        bp[b].h_ref = (T)h->b_href[b];
+        bp[b].radius = (float)rb;
+        bp[b].pad = 0.f;
+    }
+    CU(cudaMemcpyAsync(h->bub, bp.data(), bp.size() * sizeof(BubbleParam<T>), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return SBX_OK;
+}
+
+template <typename T>
+static int32_t upload_tables_t(sbx_drainage *h)
+{
+    const int N = h->num_theta;
+    const double dth = M_PI / (double)(N - 1);           // drainage.rs:123
+    const double dph = 2.0 * M_PI / (double)h->num_phi;  // drainage.rs:124
+    const double coef = h->density * h->gravity / (3.0 * h->viscosity);  // drainage.rs:305
+    const double r2 = h->radius * h->radius;
+    std::vector<T> cs((size_t)N * 4, T(0));
+    std::vector<float2> sc((size_t)N);
+    std::vector<double4> cx((size_t)N);
+    for (int g = 0; g < N; ++g) {
+        const double theta = (double)g * dth;  // theta_at, drainage.rs:149-151
+        const double s = sin(theta), c = cos(theta);
+        const double s_safe = fabs(s) < 1e-10 ? copysign(1e-10, s) : s;  // drainage.rs:320-324
+        sc[g] = make_float2((float)s, (float)c);
+        cx[g] = make_double4(s, c / s_safe, s_safe * s_safe, 0.0);
+        if (g > 0 && g < N - 1) {
+            cs[4 * (size_t)g + 0] = (T)(coef * s);
+            cs[4 * (size_t)g + 1] = (T)(h->diffusion * (c / s_safe) / (r2 * 2.0 * dth));
+            cs[4 * (size_t)g + 2] = (T)(h->diffusion / (r2 * dph * dph * s_safe * s_safe));
+        }
+    }
+    h->coefA = h->diffusion / (r2 * dth * dth);
+    CU(cudaMemcpyAsync(h->coefS, cs.data(), cs.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->rowSC, sc.data(), sc.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->coefX, cx.data(), cx.size() * sizeof(double4), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));  // host vectors go out of scope
+    return upload_bubbles<T>(h);
+}
+
+static int32_t upload_tables_wgsl(sbx_drainage *h)
+{
+    // per-row constants evaluated in f32 exactly as the shader does (drainage.wgsl:92-101)
+    const int N = h->num_theta;
+    const float PI_F = 3.14159265358979323846f;
+    const float dth = PI_F / (float)(N - 1);
+    std::vector<float4> rw((size_t)N);
+    std::vector<float2> sc((size_t)N);
+    for (int g = 0; g < N; ++g) {
+        const float theta = (float)g * dth;
+        const float s = sinf(theta), c = cosf(theta);
+        const float sgn = s > 0.f ? 1.f : (s < 0.f ? -1.f : 0.f);
+        const float s_safe = fabsf(s) < 0.0001f ? sgn * 0.0001f : s;
+        rw[g] = (g > 0 && g < N - 1) ? make_float4(s, c / s_safe, 1.0f / (s_safe * s_safe), 1.0f / s_safe)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+        const double td = (double)g * (M_PI / (double)(N - 1));
+        sc[g] = make_float2((float)sin(td), (float)cos(td));
+    }
+    CU(cudaMemcpyAsync(h->rowW, rw.data(), rw.size() * sizeof(float4), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->rowSC, sc.data(), sc.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return upload_bubbles<float>(h);
+}
+
+static int32_t ensure_tables(sbx_drainage *h)
+{
+    if (!h->tables_dirty) return SBX_OK;
+    int32_t rc = h->wgsl ? upload_tables_wgsl(h) : (h->f64 ? upload_tables_t<double>(h) : upload_tables_t<float>(h));
+    if (rc == SBX_OK) h->tables_dirty = false;
+    return rc;
+}
+
+// ------------------------------------------------------------------ create / destroy
+template <typename T>
+static int32_t fill_initial(sbx_drainage *h)
+{
+    // uniform start per bubble (ThicknessField::new, drainage.rs:121-122), ghost rows included
+    for (int b = 0; b < h->batch; ++b) {
+        const T v = (T)(h->b_h0[b] - h->b_href[b]);
+        for (int i = 0; i < 2; ++i)
+            CU(launch_fill<T>(tbuf<T>(h, i) + (long long)b * h->bubble_stride, h->bubble_stride, v, h->stream));
+    }
+    h->launches += 2 * h->batch;
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_create(const sbx_drainage_cfg *cfg, int32_t device, sbx_drainage **out)
+{
+    if (!cfg || !out) return fail(SBX_ERR_INVALID, "cfg/out is null");
+    *out = nullptr;
+    if (cfg->num_theta < 3) return fail(SBX_ERR_INVALID, "num_theta must be >= 3 (got %d)", cfg->num_theta);
+    if (cfg->num_phi < 2) return fail(SBX_ERR_INVALID, "num_phi must be >= 2 (got %d)", cfg->num_phi);
+    if (cfg->batch < 1 || cfg->batch > 65535) return fail(SBX_ERR_INVALID, "batch must be in [1,65535] (got %d)", cfg->batch);
+    if (cfg->semantics != SBX_SEM_CPU && cfg->semantics != SBX_SEM_WGSL) return fail(SBX_ERR_INVALID, "bad semantics %d", cfg->semantics);
+    if (cfg->precision < SBX_PREC_F32 || cfg->precision > SBX_PREC_F64_STRICT) return fail(SBX_ERR_INVALID, "bad precision %d", cfg->precision);
+    if (cfg->semantics == SBX_SEM_WGSL && cfg->precision != SBX_PREC_F32)
+        return fail(SBX_ERR_INVALID, "SBX_SEM_WGSL is an f32 path (drainage.wgsl); precision must be SBX_PREC_F32");
+    if (!(cfg->radius_m > 0.0) || !(cfg->viscosity > 0.0)) return fail(SBX_ERR_INVALID, "radius and viscosity must be > 0");
+    int rb = cfg->row_begin, re = cfg->row_end;
+    if (rb == 0 && re == 0) re = cfg->num_theta;
+    if (rb < 0 || re > cfg->num_theta || re - rb < 1) return fail(SBX_ERR_INVALID, "bad row range [%d,%d)", rb, re);
+    if ((rb == 0 && re < 2 && cfg->num_theta > 2) || (re == cfg->num_theta && re - rb < 2))
+        return fail(SBX_ERR_INVALID, "a band holding a pole row must also hold the ring next to it");
+    if (rb == 1 || re == cfg->num_theta - 1) return fail(SBX_ERR_INVALID, "a pole row may not be split from its ring");
+    if (cfg->precision == SBX_PREC_F64_STRICT && cfg->batch_radius_m)
+        return fail(SBX_ERR_UNSUPPORTED, "strict mode does not take per-bubble radii");
+
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(SBX_ERR_CUDA, "no usable CUDA device (%s); libsbx has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(SBX_ERR_INVALID, "device %d out of range (have %d)", device, ndev);
+    CU(cudaSetDevice(device));
+
+    sbx_drainage *h = new sbx_drainage();
+    h->cfg = *cfg;
+    h->cfg.batch_h0_m = nullptr;
+    h->cfg.batch_radius_m = nullptr;
+    h->device = device;
+    h->num_theta = cfg->num_theta;
+    h->num_phi = cfg->num_phi;
+    h->batch = cfg->batch;
+    h->row_begin = rb;
+    h->row_end = re;
+    h->rows_local = re - rb;
+    h->wgsl = cfg->semantics == SBX_SEM_WGSL;
+    h->f64 = cfg->precision != SBX_PREC_F32;
+    h->strict = cfg->precision == SBX_PREC_F64_STRICT;
+    h->esz = h->f64 ? 8 : 4;
+    h->bubble_stride = (long long)(h->rows_local + 2) * h->num_phi;
+    h->total_elems = h->bubble_stride * h->batch;
+    h->density = cfg->density; h->gravity = cfg->gravity; h->viscosity = cfg->viscosity;
+    h->diffusion = cfg->diffusion; h->critical = cfg->critical_thickness_m; h->radius = cfg->radius_m;
+    h->h_ref = h->f64 ? 0.0 : cfg->h_ref_m;
+    h->tfe_enabled = cfg->tfe_enabled != 0;
+    h->tfe_ratio = cfg->tfe_ratio;
+    h->wp = cfg->wgsl;
+    h->wp.grid_width = (uint32_t)cfg->num_phi;
+    h->wp.grid_height = (uint32_t)cfg->num_theta;
+    h->b_h0.assign((size_t)h->batch, cfg->h0_m);
+    h->b_radius.assign((size_t)h->batch, h->wgsl ? (double)h->wp.bubble_radius : cfg->radius_m);
+    if (cfg->batch_h0_m) for (int b = 0; b < h->batch; ++b) h->b_h0[b] = cfg->batch_h0_m[b];
+    if (cfg->batch_radius_m) for (int b = 0; b < h->batch; ++b) h->b_radius[b] = cfg->batch_radius_m[b];
+    // F32 storage offset: one value for the handle, or (with per-bubble h0 and a non-zero h_ref_m) each
+    // bubble's own initial thickness
+    h->b_href.assign((size_t)h->batch, h->h_ref);
+    if (!h->f64 && cfg->batch_h0_m && cfg->h_ref_m != 0.0) h->b_href = h->b_h0;
+    h->href_zero = std::all_of(h->b_href.begin(), h->b_href.end(), [](double v) { return v == 0.0; });
+    if (const char *s = getenv("SBX_BAND_ROWS")) h->band_rows = atoi(s);
+
+#define CU_H(expr)                                                                     \
+    do {                                                                               \
+        cudaError_t e__ = (expr);                                                      \
+        if (e__ != cudaSuccess) {                                                      \
+            int32_t rc__ = fail(e__ == cudaErrorMemoryAllocation ? SBX_ERR_NOMEM : SBX_ERR_CUDA, \
+                                "%s failed: %s", #expr, cudaGetErrorString(e__));      \
+            free_all(h);                                                               \
+            return rc__;                                                               \
+        }                                                                              \
+    } while (0)
+
+    CU_H(cudaStreamCreateWithFlags(&h->own_stream, cudaStreamNonBlocking));
+    h->stream = h->own_stream;
+    const size_t bytes = (size_t)h->total_elems * h->esz;
+    for (int i = 0; i < 2; ++i) CU_H(cudaMalloc(&h->buf[i], bytes));
+    if (h->wgsl)
+        for (int i = 0; i < 2; ++i) CU_H(cudaMalloc(&h->conc[i], (size_t)h->total_elems * 4));
+    const int N = h->num_theta;
+    CU_H(cudaMalloc(&h->coefS, (size_t)N * 4 * h->esz));
+    CU_H(cudaMalloc(&h->rowSC, (size_t)N * sizeof(float2)));
+    CU_H(cudaMalloc(&h->coefX, (size_t)N * sizeof(double4)));
+    CU_H(cudaMalloc(&h->rowW, (size_t)N * sizeof(float4)));
+    CU_H(cudaMalloc(&h->bub, (size_t)h->batch * (h->f64 ? sizeof(BubbleParam<double>) : sizeof(BubbleParam<float>))));
+    h->pole_slots_cap = h->num_phi / 32 + 2;
+    CU_H(cudaMalloc(&h->pole_partial, (size_t)h->batch * 2 * h->pole_slots_cap * sizeof(double)));
+    CU_H(cudaMemsetAsync(h->pole_partial, 0, (size_t)h->batch * 2 * h->pole_slots_cap * sizeof(double), h->stream));
+    CU_H(cudaMalloc(&h->mm_part, 2 * sbx_drainage::kMinmaxBlocks * sizeof(double)));
+    CU_H(cudaHostAlloc(&h->mm_host, 2 * sbx_drainage::kMinmaxBlocks * sizeof(double), cudaHostAllocDefault));
+    CU_H(cudaMalloc(&h->scalar_dev, 8 * sizeof(double)));
+    CU_H(cudaHostAlloc(&h->scalar_host, 8 * sizeof(double), cudaHostAllocDefault));
+    CU_H(cudaMalloc(&h->colA, (size_t)h->num_phi * sizeof(float)));
+    CU_H(cudaMalloc(&h->href_dev, (size_t)h->batch * sizeof(double)));
+    CU_H(cudaMemcpy(h->href_dev, h->b_href.data(), (size_t)h->batch * sizeof(double), cudaMemcpyHostToDevice));
+#undef CU_H
+
+    int32_t rc = h->f64 ? fill_initial<double>(h) : fill_initial<float>(h);
+    if (rc == SBX_OK && h->wgsl) {
+        for (int i = 0; i < 2 && rc == SBX_OK; ++i) {  // initial concentration 0.5, gpu_drainage.rs:130-131
+            cudaError_t ce = launch_fill<float>(h->conc[i], h->total_elems, 0.5f, h->stream);
+            if (ce != cudaSuccess) rc = fail(SBX_ERR_CUDA, "fill failed: %s", cudaGetErrorString(ce));
+            h->launches++;
+        }
+    }
+    if (rc == SBX_OK) rc = ensure_tables(h);
+    if (rc != SBX_OK) {
+        free_all(h);
+        return rc;
+    }
+    *out = h;
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_destroy(sbx_drainage *h)
+{
+    if (!h) return SBX_OK;
+    cudaSetDevice(h->device);
+    cudaStreamSynchronize(h->stream);
+    free_all(h);
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_set_stream(sbx_drainage *h, void *cuda_stream)
+{
+    CHECK_H(h);
+    CU(cudaStreamSynchronize(h->stream));
+    h->stream = cuda_stream ? reinterpret_cast<cudaStream_t>(cuda_stream) : h->own_stream;
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_sync(sbx_drainage *h)
+{
+    CHECK_H(h);
+    CU(cudaStreamSynchronize(h->stream));
+    return SBX_OK;
+}
+
+// ------------------------------------------------------------------ upload / download
+template <typename TD, typename TS>
+static int32_t upload_conv(sbx_drainage *h, TD *dst, const TS *host)
+{
+    const size_t row_bytes_src = (size_t)h->rows_local * h->num_phi * sizeof(TS);
+    if (sizeof(TD) == sizeof(TS) && h->href_zero) {  // same type: strided copy straight into place
+        CU(cudaMemcpy2DAsync(dst + h->num_phi, (size_t)h->bubble_stride * sizeof(TD), host, row_bytes_src,
+                             row_bytes_src, (size_t)h->batch, cudaMemcpyHostToDevice, h->stream));
+        return SBX_OK;
+    }
+    TS *stage = nullptr;
+    CU(cudaMalloc(&stage, (size_t)h->total_elems * sizeof(TS)));
+    cudaError_t e = cudaMemcpy2DAsync(stage + h->num_phi, (size_t)h->bubble_stride * sizeof(TS), host, row_bytes_src,
+                                      row_bytes_src, (size_t)h->batch, cudaMemcpyHostToDevice, h->stream);
+    if (e == cudaSuccess) e = launch_convert_in<TD, TS>(dst, stage, h->total_elems, h->bubble_stride, h->href_zero ? nullptr : h->href_dev, h->stream);
+    h->launches++;
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(stage);
+    if (e != cudaSuccess) return fail(SBX_ERR_CUDA, "upload failed: %s", cudaGetErrorString(e));
+    return SBX_OK;
+}
+
+template <typename TH, typename TS>
+static int32_t download_conv(sbx_drainage *h, TH *host, const TS *src)
+{
+    const size_t row_bytes_dst = (size_t)h->rows_local * h->num_phi * sizeof(TH);
+    if (sizeof(TH) == sizeof(TS) && h->href_zero) {
+        CU(cudaMemcpy2DAsync(host, row_bytes_dst, src + h->num_phi, (size_t)h->bubble_stride * sizeof(TS),
+                             row_bytes_dst, (size_t)h->batch, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        return SBX_OK;
+    }
+    TH *stage = nullptr;
+    CU(cudaMalloc(&stage, (size_t)h->total_elems * sizeof(TH)));
+    cudaError_t e = launch_convert_out<TH, TS>(stage, src, h->total_elems, h->bubble_stride, h->href_zero ? nullptr : h->href_dev, h->stream);
+    h->launches++;
+    if (e == cudaSuccess)
+        e = cudaMemcpy2DAsync(host, row_bytes_dst, stage + h->num_phi, (size_t)h->bubble_stride * sizeof(TH),
+                              row_bytes_dst, (size_t)h->batch, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(stage);
+    if (e != cudaSuccess) return fail(SBX_ERR_CUDA, "download failed: %s", cudaGetErrorString(e));
+    return SBX_OK;
+}
+
+static int32_t halo_exchange(sbx_drainage *h);
+
+extern "C" int32_t sbx_drainage_upload(sbx_drainage *h, const void *host, int32_t dtype)
+{
+    CHECK_H(h);
+    if (!host) return fail(SBX_ERR_INVALID, "host is null");
+    if (dtype != SBX_F32 && dtype != SBX_F64) return fail(SBX_ERR_INVALID, "bad dtype %d", dtype);
+    int32_t rc;
+    if (h->f64) {
+        rc = dtype == SBX_F64 ? upload_conv<double, double>(h, tbuf<double>(h, h->cur), (const double *)host)
+                              : upload_conv<double, float>(h, tbuf<double>(h, h->cur), (const float *)host);
+    } else {
+        rc = dtype == SBX_F64 ? upload_conv<float, double>(h, tbuf<float>(h, h->cur), (const double *)host)
+                              : upload_conv<float, float>(h, tbuf<float>(h, h->cur), (const float *)host);
+    }
+    if (rc != SBX_OK) return rc;
+    if (h->wgsl)  // frozen pole rows live in both ping-pong buffers (drainage.wgsl:85-89)
+        CU(cudaMemcpyAsync(h->buf[1 - h->cur], h->buf[h->cur], (size_t)h->total_elems * h->esz, cudaMemcpyDeviceToDevice, h->stream));
+    return halo_exchange(h);
+}
+
+extern "C" int32_t sbx_drainage_download(sbx_drainage *h, void *host, int32_t dtype)
+{
+    CHECK_H(h);
+    if (!host) return fail(SBX_ERR_INVALID, "host is null");
+    if (dtype != SBX_F32 && dtype != SBX_F64) return fail(SBX_ERR_INVALID, "bad dtype %d", dtype);
+    if (h->f64)
+        return dtype == SBX_F64 ? download_conv<double, double>(h, (double *)host, tbuf<double>(h, h->cur))
+                                : download_conv<float, double>(h, (float *)host, tbuf<double>(h, h->cur));
+    return dtype == SBX_F64 ? download_conv<double, float>(h, (double *)host, tbuf<float>(h, h->cur))
+                            : download_conv<float, float>(h, (float *)host, tbuf<float>(h, h->cur));
+}
+
+extern "C" int32_t sbx_drainage_upload_concentration(sbx_drainage *h, const float *host)
+{
+    CHECK_H(h);
+    if (!h->wgsl) return fail(SBX_ERR_INVALID, "concentration exists only with SBX_SEM_WGSL");
+    if (!host) return fail(SBX_ERR_INVALID, "host is null");
+    const size_t rb = (size_t)h->rows_local * h->num_phi * 4;
+    CU(cudaMemcpy2DAsync(h->conc[h->cur] + h->num_phi, (size_t)h->bubble_stride * 4, host, rb, rb, (size_t)h->batch,
+                         cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->conc[1 - h->cur], h->conc[h->cur], (size_t)h->total_elems * 4, cudaMemcpyDeviceToDevice, h->stream));
+    return halo_exchange(h);
+}
+
+extern "C" int32_t sbx_drainage_download_concentration(sbx_drainage *h, float *host)
+{
+    CHECK_H(h);
+    if (!h->wgsl) return fail(SBX_ERR_INVALID, "concentration exists only with SBX_SEM_WGSL");
+    if (!host) return fail(SBX_ERR_INVALID, "host is null");
+    const size_t rb = (size_t)h->rows_local * h->num_phi * 4;
+    CU(cudaMemcpy2DAsync(host, rb, h->conc[h->cur] + h->num_phi, (size_t)h->bubble_stride * 4, rb, (size_t)h->batch,
+                         cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return SBX_OK;
+}
+
+// ------------------------------------------------------------------ TFE state machine (host, f64)
+// update_marginal_regeneration without the field pass (drainage.rs:395-411) ...
+static void tfe_advance(sbx_drainage *h, double dt)
+{
+    h->next_spawn -= dt;
+    if (h->next_spawn <= 0.0) {
+        const double t = h->time;  // current_time before this step's increment
+        sbx_tfe_front f;           // spawn_tfe_front, drainage.rs:464-477
+        f.phi_center = fabs(sin(t * 7.89 + 1.23)) * 2.0 * M_PI;
+        f.width = 0.3 + fabs(sin(t * 3.21)) * 0.4;
+        f.velocity = 0.05 + fabs(cos(t * 5.67)) * 0.05;
+        f.extent = 0.0;
+        h->fronts.push_back(f);
+        if (h->fronts.size() > (size_t)kMaxFronts) h->fronts.erase(h->fronts.begin());
+        const double random_factor = 0.5 + fabs(sin(h->time * 12.345));
+        h->next_spawn = h->spawn_interval * random_factor;
+    }
+    for (auto &f : h->fronts) {  // TfeFront::advance, drainage.rs:47-49
+        const double e = f.extent + f.velocity * dt;
+        f.extent = e < M_PI_2 ? e : M_PI_2;
+    }
+    h->fronts.erase(std::remove_if(h->fronts.begin(), h->fronts.end(),
+                                   [](const sbx_tfe_front &f) { return !(f.extent < M_PI_2 * 0.95); }),
+                    h->fronts.end());
+}
+
+// largest [lo,hi] within [a_est-2,b_est+2] ∩ [lo_bound,hi_bound] on which P holds at both ends;
+// P is true on one contiguous run, and the estimates are within a cell of its ends.
+template <typename Pred>
+static void exact_interval(Pred P, long a_est, long b_est, long lo_bound, long hi_bound, int &lo, int &hi)
+{
+    long a = std::max(a_est - 2, lo_bound), a_stop = std::min(std::max(a_est, b_est) + 2, hi_bound);
+    while (a <= a_stop && !P(a)) ++a;
+    long b = std::min(b_est + 2, hi_bound), b_stop = std::max(std::min(a_est, b_est) - 2, lo_bound);
+    while (b >= b_stop && !P(b)) --b;
+    if (a > a_stop || b < b_stop || a > b) { lo = 1; hi = 0; return; }
+    lo = (int)a;
+    hi = (int)b;
+}
+
+// ... and the cells its field pass touches (drainage.rs:419-460, TfeFront::contains :55-71), as exact
+// integer intervals.
+static void tfe_table(const sbx_drainage *h, FrontTable &ft)
+{
+    memset(&ft, 0, sizeof ft);
+    ft.row_min = 1; ft.row_max = 0;
+    if (h->fronts.empty()) return;
+    const int NT = h->num_theta, NP = h->num_phi;
+    const double dth = M_PI / (double)(NT - 1), dph = 2.0 * M_PI / (double)NP;
+    size_t min_idx = (size_t)NT, max_idx = 0;
+    for (const auto &f : h->fronts) {  // drainage.rs:428-434
+        const double lo = M_PI_2 - f.extent, hi = M_PI_2 + f.extent;
+        const double flo = floor(lo / dth), fhi = ceil(hi / dth);
+        size_t a = flo <= 0.0 ? 0 : (size_t)flo, b = fhi <= 0.0 ? 0 : (size_t)fhi;
+        b = std::min(b, (size_t)(NT - 1));
+        min_idx = std::min(min_idx, a);
+        max_idx = std::max(max_idx, b);
+    }
+    min_idx = std::min(min_idx, (size_t)(NT - 1));
+    ft.row_min = (int)min_idx;
+    ft.row_max = (int)max_idx;
+    ft.count = (int)h->fronts.size();
+    for (int k = 0; k < ft.count; ++k) {
+        const sbx_tfe_front &f = h->fronts[k];
+        FrontCells &c = ft.f[k];
+        auto Prow = [&](long i) { const double th = (double)i * dth; return !(fabs(th - M_PI_2) > f.extent); };
+        exact_interval(Prow, (long)ceil((M_PI_2 - f.extent) / dth), (long)floor((M_PI_2 + f.extent) / dth),
+                       (long)min_idx, (long)max_idx, c.row_lo, c.row_hi);
+        const double hw = f.width / 2.0;
+        auto Pdir = [&](long j) { const double d = fabs((double)j * dph - f.phi_center); return !(d > M_PI) && d < hw; };
+        auto Pwrap = [&](long j) { const double d = fabs((double)j * dph - f.phi_center); return d > M_PI && (2.0 * M_PI - d) < hw; };
+        exact_interval(Pdir, (long)ceil((f.phi_center - hw) / dph), (long)floor((f.phi_center + hw) / dph), 0, NP - 1,
+                       c.c0_lo, c.c0_hi);
+        c.c1_lo = 1; c.c1_hi = 0;
+        if (f.phi_center - hw < 0.0)
+            exact_interval(Pwrap, (long)ceil((f.phi_center + 2.0 * M_PI - hw) / dph), NP - 1, 0, NP - 1, c.c1_lo, c.c1_hi);
+        else if (f.phi_center + hw > 2.0 * M_PI)
+            exact_interval(Pwrap, 0, (long)floor((f.phi_center - 2.0 * M_PI + hw) / dph), 0, NP - 1, c.c1_lo, c.c1_hi);
+    }
+}
+
+// ------------------------------------------------------------------ colour stage set-up
+static int32_t ensure_lut(sbx_drainage *h, float n_film);
+
+static int32_t prepare_rgb(sbx_drainage *h, const sbx_view *v, RgbArgs &r)
+{
+    memset(&r, 0, sizeof r);
+    if (!v || v->mode == SBX_RGB_NONE) { r.mode = SBX_RGB_NONE; return SBX_OK; }
+    if (v->mode < SBX_RGB_NONE || v->mode > SBX_RGB_SCHLICK_WALL) return fail(SBX_ERR_INVALID, "bad rgb mode %d", v->mode);
+    if (v->format != SBX_OUT_RGBA8 && v->format != SBX_OUT_RGB_F32) return fail(SBX_ERR_INVALID, "bad rgb format %d", v->format);
+    if (!(v->n_film > 0.f)) return fail(SBX_ERR_INVALID, "n_film must be > 0");
+    const size_t cells = (size_t)h->batch * h->rows_local * h->num_phi;
+    const size_t need = cells * (v->format == SBX_OUT_RGBA8 ? 4 : 12);
+    if (h->rgb_bytes < need) {
+        if (h->rgb_buf) { CU(cudaStreamSynchronize(h->stream)); CU(cudaFree(h->rgb_buf)); h->rgb_buf = nullptr; h->rgb_bytes = 0; }
+        CU(cudaMalloc(&h->rgb_buf, need));
+        h->rgb_bytes = need;
+    }
+    h->rgb_format = v->format;
+    if (!(v->cam_pos[0] == h->cam_cached[0] && v->cam_pos[1] == h->cam_cached[1] && v->cam_pos[2] == h->cam_cached[2])) {
+        CU(launch_col_view(h->colA, h->num_phi, v->cam_pos[0], v->cam_pos[2], h->stream));
+        h->launches++;
+        memcpy(h->cam_cached, v->cam_pos, sizeof h->cam_cached);
+    }
+    if (v->mode == SBX_RGB_LUT) {
+        int32_t rc = ensure_lut(h, v->n_film);
+        if (rc != SBX_OK) return rc;
+    }
+    r.mode = v->mode;
+    r.format = v->format;
+    r.out = h->rgb_buf;
+    r.colA = h->colA;
+    r.cam_y = (float)v->cam_pos[1];
+    r.cam2 = (float)(v->cam_pos[0] * v->cam_pos[0] + v->cam_pos[1] * v->cam_pos[1] + v->cam_pos[2] * v->cam_pos[2]);
+    r.n_film = v->n_film;
+    r.inv_n2 = (float)(1.0 / ((double)v->n_film * (double)v->n_film));
+    r.intensity = v->intensity;
+    r.inv_max_nm = 1.0f / h->lut_max_nm;
+    r.lut = h->lut_tex;
+    r.inv_wl[0] = (float)(1.0 / 650.0);  // interference.rs:26-30
+    r.inv_wl[1] = (float)(1.0 / 532.0);
+    r.inv_wl[2] = (float)(1.0 / 450.0);
+    return SBX_OK;
+}
+
+static int32_t install_lut(sbx_drainage *h, const uint8_t *dev_or_host, bool on_device, int T, int A, float max_nm)
+{
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->lut_tex) { CU(cudaDestroyTextureObject(h->lut_tex)); h->lut_tex = 0; }
+    if (h->lut_array) { CU(cudaFreeArray(h->lut_array)); h->lut_array = nullptr; }
+    cudaChannelFormatDesc ch = cudaCreateChannelDesc<uchar4>();
+    CU(cudaMallocArray(&h->lut_array, &ch, (size_t)T, (size_t)A));
+    CU(cudaMemcpy2DToArrayAsync(h->lut_array, 0, 0, dev_or_host, (size_t)T * 4, (size_t)T * 4, (size_t)A,
+                                on_device ? cudaMemcpyDeviceToDevice : cudaMemcpyHostToDevice, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    cudaResourceDesc rd{};
+    rd.resType = cudaResourceTypeArray;
+    rd.res.array.array = h->lut_array;
+    cudaTextureDesc td{};  // sampler at pipeline.rs:350-359: clamp-to-edge, linear, Rgba8Unorm
+    td.addressMode[0] = cudaAddressModeClamp;
+    td.addressMode[1] = cudaAddressModeClamp;
+    td.filterMode = cudaFilterModeLinear;
+    td.readMode = cudaReadModeNormalizedFloat;
+    td.normalizedCoords = 1;
+    CU(cudaCreateTextureObject(&h->lut_tex, &rd, &td, nullptr));
+    h->lut_max_nm = max_nm;
+    return SBX_OK;
+}
+
+static const float kLutWl7[7] = {400.f, 450.f, 500.f, 550.f, 600.f, 650.f, 700.f};  // interference_lut.rs:52
+
+static int32_t build_lut_device(float n, float intensity, const float *wl, int nl, int T, int A, float max_nm,
+                                uint8_t **dev_out, cudaStream_t st)
+{
+    float *wl_dev = nullptr;
+    uint8_t *out = nullptr;
+    CU(cudaMalloc(&wl_dev, (size_t)nl * 4));
+    cudaError_t e = cudaMalloc(&out, (size_t)T * A * 4);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(wl_dev, wl, (size_t)nl * 4, cudaMemcpyHostToDevice, st);
+    if (e == cudaSuccess) e = launch_lut_build(out, T, A, max_nm, n, intensity, wl_dev, nl, st);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+    cudaFree(wl_dev);
+    if (e != cudaSuccess) {
+        cudaFree(out);
+        return fail(SBX_ERR_CUDA, "LUT build failed: %s", cudaGetErrorString(e));
+    }
+    *dev_out = out;
+    return SBX_OK;
+}
+
+static int32_t ensure_lut(sbx_drainage *h, float n_film)
+{
+    if (h->lut_tex && (h->lut_user || h->lut_n == n_film)) return SBX_OK;
+    // generate_interference_lut(refractive_index, 1.0): intensity is applied at shading time
+    // (pipeline.rs:312-315, bubble.wgsl:435-436)
+    uint8_t *dev = nullptr;
+    int32_t rc = build_lut_device(n_film, 1.0f, kLutWl7, 7, 256, 64, 2000.f, &dev, h->stream);
+    if (rc != SBX_OK) return rc;
+    h->launches++;
+    rc = install_lut(h, dev, true, 256, 64, 2000.f);
+    cudaFree(dev);
+    if (rc == SBX_OK) { h->lut_n = n_film; h->lut_user = false; }
+    return rc;
+}
+
+extern "C" int32_t sbx_drainage_set_lut(sbx_drainage *h, const uint8_t *rgba, int32_t T, int32_t A, float max_nm)
+{
+    CHECK_H(h);
+    if (!rgba || T < 2 || A < 2 || !(max_nm > 0.f)) return fail(SBX_ERR_INVALID, "bad LUT arguments");
+    int32_t rc = install_lut(h, rgba, false, T, A, max_nm);
+    if (rc == SBX_OK) h->lut_user = true;
+    return rc;
+}
+
+// ------------------------------------------------------------------ stepping
+static void interior_range(const sbx_drainage *h, int &l_first, int &l_last)
+{
+    const int g_first = std::max(1, h->row_begin), g_last = std::min(h->num_theta - 2, h->row_end - 1);
+    l_first = g_first - h->row_begin + 1;
+    l_last = g_last - h->row_begin + 1;
+}
+
+template <typename T>
+static void fill_step_args(sbx_drainage *h, StepArgs<T> &a, double dt, const RgbArgs &rgb)
+{
+    memset(&a, 0, sizeof a);
+    a.in = tbuf<T>(h, h->cur);
+    a.out = tbuf<T>(h, 1 - h->cur);
+    a.coefS = reinterpret_cast<const T *>(h->coefS);
+    a.rowSC = h->rowSC;
+    a.coefX = h->coefX;
+    a.bub = reinterpret_cast<const BubbleParam<T> *>(h->bub);
+    a.pole_partial = h->pole_partial;
+    a.num_phi = h->num_phi;
+    a.num_theta = h->num_theta;
+    a.row_begin = h->row_begin;
+    interior_range(h, a.l_first, a.l_last);
+    a.bubble_stride = h->bubble_stride;
+    a.rgb_bubble_stride = (long long)h->rows_local * h->num_phi;
+    a.dt = (T)dt;
+    a.crit = (T)h->critical;
+    a.coefA = (T)h->coefA;
+    const double reduction_rate = (1.0 - h->tfe_ratio) * 0.5;  // drainage.rs:453
+    a.tfe_rdt = (T)(reduction_rate * dt);
+    const double dth = M_PI / (double)(h->num_theta - 1), dph = 2.0 * M_PI / (double)h->num_phi;
+    a.s_drain_coef = h->density * h->gravity / (3.0 * h->viscosity);
+    a.s_dth2 = dth * dth;
+    a.s_two_dth = 2.0 * dth;
+    a.s_dph2 = dph * dph;
+    a.s_r2 = h->radius * h->radius;
+    a.s_D = h->diffusion;
+    a.s_dt = dt;
+    a.s_crit = h->critical;
+    a.s_tfe_factor = 1.0 - reduction_rate * dt;  // drainage.rs:454
+    a.rgb = rgb;
+}
+
+template <typename T>
+static int32_t step_cpu_sem(sbx_drainage *h, double dt, const RgbArgs &rgb)
+{
+    FrontTable ft;
+    memset(&ft, 0, sizeof ft);
+    ft.row_min = 1; ft.row_max = 0;
+    if (h->tfe_enabled) {  // drainage.rs:387-389
+        tfe_advance(h, dt);
+        tfe_table(h, ft);
+    }
+    StepArgs<T> a;
+    fill_step_args<T>(h, a, dt, rgb);
+    const bool has_top = h->row_begin == 0, has_bottom = h->row_end == h->num_theta;
+    int n = 0;
+    if (h->strict) {
+        // the reference's pass order: interior, poles, TFE (drainage.rs:314-389); colour afterwards
+        RgbArgs none;
+        memset(&none, 0, sizeof none);
+        a.rgb = none;
+        CU(launch_step<T>(a, h->batch, false, true, has_top, has_bottom, h->band_rows, h->stream, &n));
+        CU(launch_tfe_pass<T>(tbuf<T>(h, 1 - h->cur), h->bubble_stride, h->num_phi, h->row_begin, h->rows_local,
+                              h->batch, ft, a.s_tfe_factor, h->stream, &n));
+        h->cur = 1 - h->cur;
+        if (rgb.mode != SBX_RGB_NONE) {
+            StepArgs<T> s;
+            fill_step_args<T>(h, s, dt, rgb);
+            s.l_first = 1;
+            s.l_last = h->rows_local;
+            CU(launch_shade<T>(s, h->batch, h->band_rows, h->stream, &n));
+        }
+    } else {
+        a.fronts = ft;
+        CU(launch_step<T>(a, h->batch, ft.count > 0, false, has_top, has_bottom, h->band_rows, h->stream, &n));
+        h->cur = 1 - h->cur;
+    }
+    h->launches += n;
+    h->time += dt;  // drainage.rs:391
+    return halo_exchange(h);
+}
+
+static int32_t step_wgsl_sem(sbx_drainage *h, double dt, const RgbArgs &rgb)
+{
+    WgslArgs a;
+    memset(&a, 0, sizeof a);
+    a.h_in = tbuf<float>(h, h->cur);
+    a.h_out = tbuf<float>(h, 1 - h->cur);
+    a.c_in = h->conc[h->cur];
+    a.c_out = h->conc[1 - h->cur];
+    a.rowW = h->rowW;
+    a.rowSC = h->rowSC;
+    a.num_phi = h->num_phi;
+    a.num_theta = h->num_theta;
+    a.row_begin = h->row_begin;
+    a.rows_local = h->rows_local;
+    interior_range(h, a.l_first, a.l_last);
+    a.bubble_stride = h->bubble_stride;
+    a.rgb_bubble_stride = (long long)h->rows_local * h->num_phi;
+    a.p = h->wp;
+    const float PI_F = 3.14159265358979323846f;
+    a.delta_theta = PI_F / (float)(h->wp.grid_height - 1u);  // drainage.wgsl:92
+    a.delta_phi = 2.0f * PI_F / (float)h->wp.grid_width;     // drainage.wgsl:93
+    a.radius_view = h->wp.bubble_radius;
+    a.rgb = rgb;
+    int n = 0;
+    CU(launch_wgsl(a, h->batch, h->band_rows, h->stream, &n));
+    if (rgb.mode != SBX_RGB_NONE && (h->row_begin == 0 || h->row_end == h->num_theta)) {
+        // frozen pole rows still need their colour: shade them from the (unchanged) pole values
+        StepArgs<float> s;
+        fill_step_args<float>(h, s, dt, rgb);
+        s.in = tbuf<float>(h, 1 - h->cur);
+        if (h->row_begin == 0) { s.l_first = 1; s.l_last = 1; CU(launch_shade<float>(s, h->batch, 1, h->stream, &n)); }
+        if (h->row_end == h->num_theta) { s.l_first = h->rows_local; s.l_last = h->rows_local; CU(launch_shade<float>(s, h->batch, 1, h->stream, &n)); }
+    }
+    h->cur = 1 - h->cur;
+    h->launches += n;
+    h->time += dt;  // gpu_drainage.rs:368
+    return halo_exchange(h);
+}
+
+static int32_t do_steps(sbx_drainage *h, double dt, int32_t nsteps, const sbx_view *view)
+{
+    if (nsteps < 0) return fail(SBX_ERR_INVALID, "nsteps < 0");
+    int32_t rc = ensure_tables(h);
+    if (rc != SBX_OK) return rc;
+    RgbArgs rgb;
+    rc = prepare_rgb(h, view, rgb);
+    if (rc != SBX_OK) return rc;
+    for (int s = 0; s < nsteps; ++s) {
+        rc = h->wgsl ? step_wgsl_sem(h, dt, rgb) : (h->f64 ? step_cpu_sem<double>(h, dt, rgb) : step_cpu_sem<float>(h, dt, rgb));
+        if (rc != SBX_OK) return rc;
+    }
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_step(sbx_drainage *h, double dt, int32_t nsteps)
+{
+    CHECK_H(h);
+    return do_steps(h, dt, nsteps, nullptr);
+}
+
+extern "C" int32_t sbx_drainage_step_fused(sbx_drainage *h, double dt, int32_t nsteps, const sbx_view *view)
+{
+    CHECK_H(h);
+    if (!view) return fail(SBX_ERR_INVALID, "view is null");
+    return do_steps(h, dt, nsteps, view);
+}
+
+extern "C" int32_t sbx_drainage_shade(sbx_drainage *h, const sbx_view *view)
+{
+    CHECK_H(h);
+    if (!view || view->mode == SBX_RGB_NONE) return fail(SBX_ERR_INVALID, "view is null or mode is NONE");
+    int32_t rc = ensure_tables(h);
+    if (rc != SBX_OK) return rc;
+    RgbArgs rgb;
+    rc = prepare_rgb(h, view, rgb);
+    if (rc != SBX_OK) return rc;
+    int n = 0;
+    if (h->f64) {
+        StepArgs<double> s;
+        fill_step_args<double>(h, s, 0.0, rgb);
+        s.l_first = 1; s.l_last = h->rows_local;
+        CU(launch_shade<double>(s, h->batch, h->band_rows, h->stream, &n));
+    } else {
+        StepArgs<float> s;
+        fill_step_args<float>(h, s, 0.0, rgb);
+        s.l_first = 1; s.l_last = h->rows_local;
+        if (h->wgsl) {
+            // WGSL handles carry radius in params, h_ref = 0; BubbleParam was filled from them at create
+        }
+        CU(launch_shade<float>(s, h->batch, h->band_rows, h->stream, &n));
+    }
+    h->launches += n;
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_download_rgb(sbx_drainage *h, void *host)
+{
+    CHECK_H(h);
+    if (!host) return fail(SBX_ERR_INVALID, "host is null");
+    if (!h->rgb_buf || h->rgb_format < 0) return fail(SBX_ERR_INVALID, "no colour frame has been produced yet");
+    const size_t cells = (size_t)h->batch * h->rows_local * h->num_phi;
+    CU(cudaMemcpyAsync(host, h->rgb_buf, cells * (h->rgb_format == SBX_OUT_RGBA8 ? 4 : 12), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_step_host(sbx_drainage *h, double dt, int32_t nsteps, const sbx_view *view,
+                                          const void *host_in, int32_t in_dtype, void *host_out_h, int32_t out_dtype,
+                                          void *host_out_rgb)
+{
+    CHECK_H(h);
+    int32_t rc = SBX_OK;
+    if (host_in) rc = sbx_drainage_upload(h, host_in, in_dtype);
+    if (rc != SBX_OK) return rc;
+    rc = do_steps(h, dt, nsteps, view);
+    if (rc != SBX_OK) return rc;
+    if (host_out_rgb) {
+        if (!view || view->mode == SBX_RGB_NONE) return fail(SBX_ERR_INVALID, "host_out_rgb needs a colour view");
+        const size_t cells = (size_t)h->batch * h->rows_local * h->num_phi;
+        CU(cudaMemcpyAsync(host_out_rgb, h->rgb_buf, cells * (h->rgb_format == SBX_OUT_RGBA8 ? 4 : 12), cudaMemcpyDeviceToHost, h->stream));
+    }
+    if (host_out_h) return sbx_drainage_download(h, host_out_h, out_dtype);
+    CU(cudaStreamSynchronize(h->stream));
+    return SBX_OK;
+}
+
+// ------------------------------------------------------------------ queries
+extern "C" int32_t sbx_drainage_get_thickness(sbx_drainage *h, int32_t bubble, double theta, double phi, double *out)
+{
+    CHECK_H(h);
+    if (!out) return fail(SBX_ERR_INVALID, "out is null");
+    if (bubble < 0 || bubble >= h->batch) return fail(SBX_ERR_INVALID, "bubble %d out of range", bubble);
+    // index arithmetic of get_thickness (drainage.rs:516-540); the blend itself runs on the device
+    const int NT = h->num_theta, NP = h->num_phi;
+    const double dth = M_PI / (double)(NT - 1), dph = 2.0 * M_PI / (double)NP;
+    const double theta_clamped = theta < 0.0 ? 0.0 : (theta > M_PI ? M_PI : theta);
+    const double two_pi = 2.0 * M_PI;
+    double phi_n = fmod(phi, two_pi);
+    if (phi_n < 0.0) phi_n += two_pi;
+    const double tc = theta_clamped / dth, pc = phi_n / dph;
+    size_t ti = (size_t)floor(tc);
+    if (ti > (size_t)(NT - 2)) ti = (size_t)(NT - 2);
+    const size_t pj = (size_t)floor(pc) % (size_t)NP;
+    const size_t pj_hi = (pj + 1) % (size_t)NP;
+    const double tf = tc - (double)ti, pf = pc - (double)pj;
+    if ((int)ti < h->row_begin || (int)ti + 1 >= h->row_end)
+        return fail(SBX_ERR_INVALID, "theta rows %zu,%zu are not owned by this band [%d,%d)", ti, ti + 1, h->row_begin, h->row_end);
+    const long long base = (long long)bubble * h->bubble_stride;
+    const long long r0 = base + (long long)((int)ti - h->row_begin + 1) * NP, r1 = r0 + NP;
+    if (h->f64) CU(launch_sample<double>(tbuf<double>(h, h->cur), r0 + pj, r0 + pj_hi, r1 + pj, r1 + pj_hi, tf, pf, 0.0, h->scalar_dev, h->stream));
+    else CU(launch_sample<float>(tbuf<float>(h, h->cur), r0 + pj, r0 + pj_hi, r1 + pj, r1 + pj_hi, tf, pf, h->b_href[bubble], h->scalar_dev, h->stream));
+    h->launches++;
+    CU(cudaMemcpyAsync(h->scalar_host, h->scalar_dev, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    *out = h->scalar_host[0];
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_minmax(sbx_drainage *h, double *min_out, double *max_out)
+{
+    CHECK_H(h);
+    const int nb = sbx_drainage::kMinmaxBlocks;
+    double mn = INFINITY, mx = -INFINITY;
+    for (int b = 0; b < h->batch; ++b) {  // owned rows only (ghost rows are skipped)
+        const long long off = (long long)b * h->bubble_stride + h->num_phi;
+        const long long n = (long long)h->rows_local * h->num_phi;
+        if (h->f64) CU(launch_minmax<double>(tbuf<double>(h, h->cur) + off, n, 0.0, h->mm_part, nb, h->stream));
+        else CU(launch_minmax<float>(tbuf<float>(h, h->cur) + off, n, h->b_href[b], h->mm_part, nb, h->stream));
+        h->launches++;
+        CU(cudaMemcpyAsync(h->mm_host, h->mm_part, 2 * nb * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        for (int i = 0; i < nb; ++i) { mn = fmin(mn, h->mm_host[2 * i]); mx = fmax(mx, h->mm_host[2 * i + 1]); }
+    }
+    if (min_out) *min_out = mn;
+    if (max_out) *max_out = mx;
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_has_critical(sbx_drainage *h, int32_t *out)
+{
+    double mn, mx;
+    int32_t rc = sbx_drainage_minmax(h, &mn, &mx);
+    if (rc != SBX_OK) return rc;
+    if (out) *out = mn < (h->wgsl ? (double)h->wp.critical_thickness : h->critical) ? 1 : 0;  // drainage.rs:565-567
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_critical_thickness(sbx_drainage *h, double *out)
+{
+    if (!h || !out) return fail(SBX_ERR_INVALID, "null argument");
+    *out = h->wgsl ? (double)h->wp.critical_thickness : h->critical;
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_current_time(sbx_drainage *h, double *out)
+{
+    if (!h || !out) return fail(SBX_ERR_INVALID, "null argument");
+    *out = h->time;
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_reset(sbx_drainage *h, double h0_m)
+{
+    CHECK_H(h);
+    std::fill(h->b_h0.begin(), h->b_h0.end(), h0_m);
+    if (!h->f64 && !h->href_zero) {
+        // offset storage follows the new uniform level, so the reset field is exact (delta == 0)
+        h->h_ref = h0_m;
+        std::fill(h->b_href.begin(), h->b_href.end(), h0_m);
+        CU(cudaStreamSynchronize(h->stream));
+        CU(cudaMemcpy(h->href_dev, h->b_href.data(), (size_t)h->batch * sizeof(double), cudaMemcpyHostToDevice));
+        int32_t rcb = upload_bubbles<float>(h);
+        if (rcb != SBX_OK) return rcb;
+    }
+    int32_t rc = h->f64 ? fill_initial<double>(h) : fill_initial<float>(h);
+    if (rc != SBX_OK) return rc;
+    if (h->wgsl)
+        for (int i = 0; i < 2; ++i) { CU(launch_fill<float>(h->conc[i], h->total_elems, 0.5f, h->stream)); h->launches++; }
+    h->cur = 0;
+    h->time = 0.0;
+    h->fronts.clear();
+    h->next_spawn = 0.5;
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_set_marginal_regeneration(sbx_drainage *h, int32_t enabled)
+{
+    if (!h) return fail(SBX_ERR_INVALID, "null handle");
+    h->tfe_enabled = enabled != 0;
+    if (!enabled) h->fronts.clear();
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_marginal_regeneration(sbx_drainage *h, int32_t *out)
+{
+    if (!h || !out) return fail(SBX_ERR_INVALID, "null argument");
+    *out = h->tfe_enabled ? 1 : 0;
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_set_tfe_ratio(sbx_drainage *h, double ratio)
+{
+    if (!h) return fail(SBX_ERR_INVALID, "null handle");
+    h->tfe_ratio = ratio < 0.5 ? 0.5 : (ratio > 0.95 ? 0.95 : ratio);  // clamp(0.5, 0.95)
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_tfe_ratio(sbx_drainage *h, double *out)
+{
+    if (!h || !out) return fail(SBX_ERR_INVALID, "null argument");
+    *out = h->tfe_ratio;
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_active_tfe_count(sbx_drainage *h, int32_t *out)
+{
+    if (!h || !out) return fail(SBX_ERR_INVALID, "null argument");
+    *out = (int32_t)h->fronts.size();
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_fronts(sbx_drainage *h, sbx_tfe_front *out8, int32_t *count)
+{
+    if (!h || !out8 || !count) return fail(SBX_ERR_INVALID, "null argument");
+    *count = (int32_t)h->fronts.size();
+    for (size_t i = 0; i < h->fronts.size(); ++i) out8[i] = h->fronts[i];
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_update_params(sbx_drainage *h, const sbx_drainage_params *p)
+{
+    if (!h || !p) return fail(SBX_ERR_INVALID, "null argument");
+    if (!h->wgsl) return fail(SBX_ERR_INVALID, "update_params applies to SBX_SEM_WGSL handles");
+    if (p->grid_width != (uint32_t)h->num_phi || p->grid_height != (uint32_t)h->num_theta)
+        return fail(SBX_ERR_INVALID, "grid size is fixed at creation (%dx%d)", h->num_phi, h->num_theta);
+    h->wp = *p;
+    std::fill(h->b_radius.begin(), h->b_radius.end(), (double)p->bubble_radius);
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_params_get(sbx_drainage *h, sbx_drainage_params *out)
+{
+    if (!h || !out) return fail(SBX_ERR_INVALID, "null argument");
+    *out = h->wp;
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_set_physics(sbx_drainage *h, double density, double gravity, double viscosity,
+                                            double diffusion, double critical_thickness_m, double radius_m)
+{
+    if (!h) return fail(SBX_ERR_INVALID, "null handle");
+    if (h->wgsl) return fail(SBX_ERR_INVALID, "use sbx_drainage_update_params for SBX_SEM_WGSL handles");
+    if (!(radius_m > 0.0) || !(viscosity > 0.0)) return fail(SBX_ERR_INVALID, "radius and viscosity must be > 0");
+    const double old_r = h->radius;
+    h->density = density; h->gravity = gravity; h->viscosity = viscosity;
+    h->diffusion = diffusion; h->critical = critical_thickness_m; h->radius = radius_m;
+    for (auto &r : h->b_radius) if (r == old_r) r = radius_m;
+    h->tables_dirty = true;
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_device_ptr(sbx_drainage *h, int32_t kind, void **out)
+{
+    if (!h || !out) return fail(SBX_ERR_INVALID, "null argument");
+    switch (kind) {
+    case SBX_PTR_THICKNESS: *out = (char *)h->buf[h->cur] + (size_t)h->num_phi * h->esz; return SBX_OK;
+    case SBX_PTR_CONCENTRATION:
+        if (!h->wgsl) return fail(SBX_ERR_INVALID, "concentration exists only with SBX_SEM_WGSL");
+        *out = h->conc[h->cur] + h->num_phi;
+        return SBX_OK;
+    case SBX_PTR_RGB:
+        if (!h->rgb_buf) return fail(SBX_ERR_INVALID, "no colour frame has been produced yet");
+        *out = h->rgb_buf;
+        return SBX_OK;
+    }
+    return fail(SBX_ERR_INVALID, "bad pointer kind %d", kind);
+}
+
+extern "C" int32_t sbx_drainage_launch_count(sbx_drainage *h, int64_t *out)
+{
+    if (!h || !out) return fail(SBX_ERR_INVALID, "null argument");
+    *out = h->launches;
+    return SBX_OK;
+}
+
+// ------------------------------------------------------------------ LUT / calculator entry points
+static int32_t pick_device(int32_t device)
+{
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev == 0)
+        return fail(SBX_ERR_CUDA, "no usable CUDA device (%s); libsbx has no CPU fallback", cudaGetErrorString(e));
+    if (device < 0 || device >= ndev) return fail(SBX_ERR_INVALID, "device %d out of range (have %d)", device, ndev);
+    CU(cudaSetDevice(device));
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_lut_build_spectral(float n, float intensity, const float *wl, int32_t nl, int32_t T, int32_t A,
+                                          float max_nm, uint8_t *out, int32_t device)
+{
+    if (!wl || !out || nl < 1 || T < 2 || A < 2) return fail(SBX_ERR_INVALID, "bad LUT arguments");
+    int32_t rc = pick_device(device);
+    if (rc != SBX_OK) return rc;
+    uint8_t *dev = nullptr;
+    rc = build_lut_device(n, intensity, wl, nl, T, A, max_nm, &dev, 0);
+    if (rc != SBX_OK) return rc;
+    cudaError_t e = cudaMemcpy(out, dev, (size_t)T * A * 4, cudaMemcpyDeviceToHost);
+    cudaFree(dev);
+    if (e != cudaSuccess) return fail(SBX_ERR_CUDA, "LUT download failed: %s", cudaGetErrorString(e));
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_lut_build(float n, float intensity, uint8_t *out65536, int32_t device)
+{
+    return sbx_lut_build_spectral(n, intensity, kLutWl7, 7, 256, 64, 2000.f, out65536, device);
+}
+
+extern "C" int32_t sbx_interference_eval(double n_film, const double wl[3], const double *d_nm, const double *cos_i,
+                                         size_t n, int32_t gamma, double *rgb_out, int32_t device)
+{
+    if (!wl || !d_nm || !cos_i || !rgb_out) return fail(SBX_ERR_INVALID, "null argument");
+    int32_t rc = pick_device(device);
+    if (rc != SBX_OK) return rc;
+    if (n == 0) return SBX_OK;
+    double *dd = nullptr, *dc = nullptr, *dr = nullptr;
+    CU(cudaMalloc(&dd, n * 8));
+    cudaError_t e = cudaMalloc(&dc, n * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&dr, n * 24);
+    if (e == cudaSuccess) e = cudaMemcpy(dd, d_nm, n * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dc, cos_i, n * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_interference_eval(n_film, wl, dd, dc, n, gamma, dr, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(rgb_out, dr, n * 24, cudaMemcpyDeviceToHost);
+    cudaFree(dd); cudaFree(dc); cudaFree(dr);
+    if (e != cudaSuccess) return fail(SBX_ERR_CUDA, "interference eval failed: %s", cudaGetErrorString(e));
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_interference_terms(double n_film, const double *d_nm, const double *cos_i, size_t n, double wl,
+                                          double *out_cos_t, double *out_fresnel, double *out_intensity, int32_t device)
+{
+    if (!d_nm || !cos_i) return fail(SBX_ERR_INVALID, "null argument");
+    int32_t rc = pick_device(device);
+    if (rc != SBX_OK) return rc;
+    if (n == 0) return SBX_OK;
+    double *dd = nullptr, *dc = nullptr, *o1 = nullptr, *o2 = nullptr, *o3 = nullptr;
+    cudaError_t e = cudaMalloc(&dd, n * 8);
+    if (e == cudaSuccess) e = cudaMalloc(&dc, n * 8);
+    if (e == cudaSuccess && out_cos_t) e = cudaMalloc(&o1, n * 8);
+    if (e == cudaSuccess && out_fresnel) e = cudaMalloc(&o2, n * 24);
+    if (e == cudaSuccess && out_intensity) e = cudaMalloc(&o3, n * 8);
+    if (e == cudaSuccess) e = cudaMemcpy(dd, d_nm, n * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dc, cos_i, n * 8, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_interference_terms(n_film, dd, dc, n, wl, o1, o2, o3, 0);
+    if (e == cudaSuccess && o1) e = cudaMemcpy(out_cos_t, o1, n * 8, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && o2) e = cudaMemcpy(out_fresnel, o2, n * 24, cudaMemcpyDeviceToHost);
+    if (e == cudaSuccess && o3) e = cudaMemcpy(out_intensity, o3, n * 8, cudaMemcpyDeviceToHost);
+    cudaFree(dd); cudaFree(dc); cudaFree(o1); cudaFree(o2); cudaFree(o3);
+    if (e != cudaSuccess) return fail(SBX_ERR_CUDA, "interference terms failed: %s", cudaGetErrorString(e));
+    return SBX_OK;
+}
+
+// ------------------------------------------------------------------ multi-GPU glue
+static int32_t halo_exchange(sbx_drainage *h)
+{
+    if (!h->comm) return SBX_OK;
+    const char *err = nullptr;
+    // my first owned row -> upper neighbour's bottom ghost; my last owned row -> lower neighbour's top ghost
+    const size_t row_bytes = (size_t)h->num_phi * h->esz;
+    for (int b = 0; b < h->batch; ++b) {
+        char *base = (char *)h->buf[h->cur] + (size_t)b * h->bubble_stride * h->esz;
+        int rc = sbx_comm_halo(h->comm, base + row_bytes, base, base + (size_t)h->rows_local * row_bytes,
+                               base + (size_t)(h->rows_local + 1) * row_bytes, row_bytes, h->stream, &err);
+        if (rc != 0) return fail(SBX_ERR_COMM, "halo exchange failed: %s", err ? err : "?");
+        if (h->wgsl) {
+            char *cb = (char *)h->conc[h->cur] + (size_t)b * h->bubble_stride * 4;
+            const size_t rbc = (size_t)h->num_phi * 4;
+            rc = sbx_comm_halo(h->comm, cb + rbc, cb, cb + (size_t)h->rows_local * rbc, cb + (size_t)(h->rows_local + 1) * rbc,
+                               rbc, h->stream, &err);
+            if (rc != 0) return fail(SBX_ERR_COMM, "halo exchange failed: %s", err ? err : "?");
+        }
+    }
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_comm_unique_id(uint8_t out128[128])
+{
+    const char *err = nullptr;
+    if (sbx_comm_unique_id_impl(out128, &err) != 0) return fail(SBX_ERR_COMM, "%s", err ? err : "nccl unique id failed");
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_comm_init(const uint8_t id128[128], int32_t nranks, int32_t rank, int32_t device, sbx_comm **out)
+{
+    if (!id128 || !out) return fail(SBX_ERR_INVALID, "null argument");
+    int32_t rc = pick_device(device);
+    if (rc != SBX_OK) return rc;
+    const char *err = nullptr;
+    if (sbx_comm_init_impl(id128, nranks, rank, device, out, &err) != 0) return fail(SBX_ERR_COMM, "%s", err ? err : "nccl init failed");
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_comm_destroy(sbx_comm *c)
+{
+    sbx_comm_destroy_impl(c);
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_attach_comm(sbx_drainage *h, sbx_comm *c)
+{
+    CHECK_H(h);
+    h->comm = c;
+    return halo_exchange(h);
+}
+
+extern "C" int32_t sbx_drainage_minmax_global(sbx_drainage *h, double *min_out, double *max_out)
+{
+    double mn, mx;
+    int32_t rc = sbx_drainage_minmax(h, &mn, &mx);
+    if (rc != SBX_OK) return rc;
+    if (h->comm) {
+        const char *err = nullptr;
+        double v[2] = {-mn, mx};  // one max-allreduce for both
+        if (sbx_comm_allreduce_max2(h->comm, v, h->scalar_dev, h->stream, &err) != 0)
+            return fail(SBX_ERR_COMM, "allreduce failed: %s", err ? err : "?");
+        mn = -v[0];
+        mx = v[1];
+    }
+    if (min_out) *min_out = mn;
+    if (max_out) *max_out = mx;
+    return SBX_OK;
+}

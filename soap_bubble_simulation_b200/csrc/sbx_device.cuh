@@ -1,0 +1,254 @@
+// sbx_device.cuh -- device-side building blocks: vector loads, the per-cell drainage update in its
+// fast and strict forms, TFE membership, and the colour stage.
+#pragma once
+
+#include "sbx_internal.cuh"
+
+namespace sbx {
+
+// ------------------------------------------------------------------ 16-byte vectors
+template <typename T, int VEC>
+struct Vec {
+    T v[VEC];
+};
+
+template <typename T, int VEC>
+__device__ __forceinline__ Vec<T, VEC> ldv(const T *p)
+{
+    Vec<T, VEC> r;
+    if constexpr (VEC == 1) {
+        r.v[0] = __ldg(p);
+    } else if constexpr (sizeof(T) == 4) {
+        static_assert(VEC == 4, "float vectors are 4 wide");
+        float4 q = __ldg(reinterpret_cast<const float4 *>(p));
+        r.v[0] = q.x; r.v[1] = q.y; r.v[2] = q.z; r.v[3] = q.w;
+    } else {
+        static_assert(VEC == 2, "double vectors are 2 wide");
+        double2 q = __ldg(reinterpret_cast<const double2 *>(p));
+        r.v[0] = q.x; r.v[1] = q.y;
+    }
+    return r;
+}
+
+template <typename T, int VEC>
+__device__ __forceinline__ void stv(T *p, const Vec<T, VEC> &r)
+{
+    if constexpr (VEC == 1) {
+        *p = r.v[0];
+    } else if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<float4 *>(p) = make_float4(r.v[0], r.v[1], r.v[2], r.v[3]);
+    } else {
+        *reinterpret_cast<double2 *>(p) = make_double2(r.v[0], r.v[1]);
+    }
+}
+
+// ------------------------------------------------------------------ drainage update, fast form
+// dh/dt = -(rho g/3 eta) h^3 sin(theta) + D/R^2 [ d2h/dth2 + cot(theta) dh/dth + d2h/dph2 / sin^2 ]
+// (src/physics/drainage.rs:347-372) with the divisions folded into per-row coefficients
+//   G = (rho g / 3 eta) sin(theta),  A = D/(R^2 dth^2),  B = D cot(theta)/(R^2 2 dth),
+//   E = D/(R^2 dph^2 sin^2(theta)).
+// `h` is the stored value (h_abs - h_ref).  Differences are taken neighbour-minus-centre so that they
+// are exact in the storage type (Sterbenz) and sub-ulp increments are not lost before the final add.
+template <typename T>
+__device__ __forceinline__ T cell_update(T h, T up, T dn, T lf, T rt, T G, T A, T B, T E, T dscale,
+                                         T href, T dt, T crit)
+{
+    const T habs = h + href;
+    const T dN = dn - h, dS = up - h;
+    const T dE = rt - h, dW = lf - h;
+    const T t1 = dN + dS, t2 = dN - dS, t3 = dE + dW;
+    T diff = A * t1;
+    diff = fma(B, t2, diff);
+    diff = fma(E, t3, diff);
+    const T rate = fma(diff, dscale, -G * (habs * habs * habs));
+    T hn = fma(dt, rate, h);
+    hn = hn > -href ? hn : -href;            // max(h_abs, 0), drainage.rs:378
+    return habs < crit ? h : hn;             // below-critical cells keep their value, drainage.rs:331-333
+}
+
+// strict form: the reference's operation order with IEEE round-to-nearest ops that nvcc never
+// contracts into FMAs (drainage.rs:347-379).
+struct StrictRow {
+    double sin_theta, cot, sin2;
+};
+
+__device__ __forceinline__ double cell_update_strict(double hc, double h_tm, double h_tp, double h_pm,
+                                                     double h_pp, const StrictRow &r, double coef,
+                                                     double dth2, double two_dth, double dph2, double r2,
+                                                     double D, double dt, double crit)
+{
+    if (hc < crit) return hc;
+    const double cubed = __dmul_rn(__dmul_rn(hc, hc), hc);
+    const double drainage_term = __dmul_rn(__dmul_rn(-coef, cubed), r.sin_theta);
+    const double two_h = __dmul_rn(2.0, hc);
+    const double d2t = __ddiv_rn(__dadd_rn(__dsub_rn(h_tp, two_h), h_tm), dth2);
+    const double dht = __ddiv_rn(__dsub_rn(h_tp, h_tm), two_dth);
+    const double d2p = __ddiv_rn(__dadd_rn(__dsub_rn(h_pp, two_h), h_pm), dph2);
+    const double lap =
+        __ddiv_rn(__dadd_rn(__dadd_rn(d2t, __dmul_rn(r.cot, dht)), __ddiv_rn(d2p, r.sin2)), r2);
+    const double dh_dt = __dadd_rn(drainage_term, __dmul_rn(D, lap));
+    const double nh = __dadd_rn(hc, __dmul_rn(dt, dh_dt));
+    return nh > 0.0 ? nh : 0.0;
+}
+
+// ------------------------------------------------------------------ TFE membership (integer)
+__device__ __forceinline__ unsigned front_row_mask(const FrontTable &ft, int grow)
+{
+    unsigned m = 0;
+    if (grow < ft.row_min || grow > ft.row_max) return 0;
+#pragma unroll
+    for (int k = 0; k < kMaxFronts; ++k)
+        if (k < ft.count && grow >= ft.f[k].row_lo && grow <= ft.f[k].row_hi) m |= 1u << k;
+    return m;
+}
+
+__device__ __forceinline__ bool front_hit(const FrontTable &ft, unsigned rowmask, int col)
+{
+    bool hit = false;
+#pragma unroll
+    for (int k = 0; k < kMaxFronts; ++k) {
+        if (rowmask & (1u << k)) {
+            const FrontCells &f = ft.f[k];
+            hit |= (col >= f.c0_lo && col <= f.c0_hi) || (col >= f.c1_lo && col <= f.c1_hi);
+        }
+    }
+    return hit;
+}
+
+// ------------------------------------------------------------------ colour stage (f32)
+__device__ __forceinline__ float clamp01(float x) { return fminf(fmaxf(x, 0.f), 1.f); }
+
+// cos(theta_i) = |n.(c - R n)| / |c - R n| with n.c = sin(th) A_j + cos(th) c_y
+__device__ __forceinline__ float view_cos(float sin_th, float cos_th_cy, float colA, float R, float cam2)
+{
+    const float nc = fmaf(sin_th, colA, cos_th_cy);
+    const float len2 = fmaf(-2.f * R, nc, cam2 + R * R);
+    return fabsf(nc - R) * rsqrtf(len2);
+}
+
+// approximate SFU ops (1-2 ulp), one MUFU each
+__device__ __forceinline__ float rcp_approx(float x)
+{
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float sqrt_approx(float x)
+{
+    float r;
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float ex2_approx(float x)
+{
+    float r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float lg2_approx(float x)
+{
+    float r;
+    asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// sin(pi x) for |x| <= 0.5 from the Taylor series of sin(pi x)/x in x^2 up to x^10 (truncation error
+// < 6e-8 at |x| = 0.5, relative accuracy kept near 0).  The fringes' zeros need *relative* accuracy:
+// the 1/2.2 gamma turns an absolute 1e-8 intensity error into 2e-4 of colour.
+__device__ __forceinline__ float sinpi_half(float x)
+{
+    const float x2 = x * x;
+    float p = -7.3704310e-3f;             // -pi^11/11!
+    p = fmaf(p, x2, 8.2145887e-2f);       //  pi^9/9!
+    p = fmaf(p, x2, -5.9926453e-1f);      // -pi^7/7!
+    p = fmaf(p, x2, 2.5501640f);          //  pi^5/5!
+    p = fmaf(p, x2, -5.1677128f);         // -pi^3/3!
+    p = fmaf(p, x2, 3.1415927f);          //  pi
+    return p * x;
+}
+
+// InterferenceCalculator::calculate_interference_color[_linear] (src/physics/interference.rs:380-426)
+// in f32: Snell (197-211), exact Fresnel average (266-298), OPD with lambda/2 (226-238), multi-bounce
+// Airy (344-352) rewritten with 1-cos(phi) = 2 sin^2(phi/2) and phase reduced in cycles.
+__device__ __forceinline__ void rgb_exact3(float d_nm, float ci, const RgbArgs &a, bool gamma, float rgb[3])
+{
+    ci = fminf(fmaxf(ci, -1.f), 1.f);
+    const float s2 = (1.f - ci * ci) * a.inv_n2;
+    const float ct = sqrt_approx(fmaxf(1.f - s2, 0.f));
+    const float n = a.n_film;
+    const float a1 = ci, b1 = n * ct, c1 = n * ci, d1 = ct;
+    const float ds = a1 + b1, dp = c1 + d1;
+    const float inv = rcp_approx(ds * dp);
+    const float rs = (a1 - b1) * dp * inv;
+    const float rp = (c1 - d1) * ds * inv;
+    const float R = 0.5f * (rs * rs + rp * rp);
+    const float omr = 1.f - R;
+    const float opd2 = 2.f * n * d_nm * ct;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float cyc = fmaf(opd2, a.inv_wl[k], 0.5f);
+        const float f = cyc - rintf(cyc);
+        const float s = sinpi_half(f);
+        const float num = 4.f * R * s * s;
+        const float den = fmaf(omr, omr, num);
+        float I = den < 1e-30f ? R : num * rcp_approx(den);  // |den| < eps -> R, interference.rs:348-350
+        I = d_nm <= 0.f ? 0.f : clamp01(I);
+        if (gamma) I = ex2_approx(lg2_approx(I) * (1.0f / 2.2f));  // powf(1/2.2); lg2(0) = -inf -> 0
+        rgb[k] = clamp01(I);
+    }
+}
+
+// wall.wgsl:165-207
+__device__ __forceinline__ void rgb_schlick_wall(float d_nm, float ci, const RgbArgs &a, float rgb[3])
+{
+    const float n = a.n_film;
+    const float s2 = (1.f - ci * ci) * a.inv_n2;
+    const float ct = s2 > 1.f ? 0.f : sqrt_approx(1.f - s2);
+    const float opd2 = 2.f * n * d_nm * ct;
+    const float q = (1.f - n) / (1.f + n);
+    const float r0 = q * q;
+    const float m = 1.f - ci, m2 = m * m;
+    const float R = r0 + (1.f - r0) * (m2 * m2 * m);
+    const float omr = 1.f - R;
+    const float F = 4.f * R * rcp_approx(omr * omr);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float cyc = fmaf(opd2, a.inv_wl[k], 0.5f);  // delta/2pi = opd/lambda + 1/2
+        const float f = cyc - rintf(cyc);
+        const float s = sinpi_half(f);
+        rgb[k] = rcp_approx(fmaf(F, s * s, 1.f));
+    }
+}
+
+// bubble.wgsl:425-439 through the texture unit: linear filter, clamp-to-edge, normalised coordinates,
+// unorm8 -> float (sampler at pipeline.rs:350-359, texture format Rgba8Unorm at pipeline.rs:325)
+__device__ __forceinline__ void rgb_lut(float d_nm, float ci, const RgbArgs &a, float rgb[3])
+{
+    const float u = clamp01(d_nm * a.inv_max_nm);
+    const float v = clamp01(ci);
+    const float4 t = tex2D<float4>(a.lut, u, v);
+    rgb[0] = clamp01(t.x * a.intensity);
+    rgb[1] = clamp01(t.y * a.intensity);
+    rgb[2] = clamp01(t.z * a.intensity);
+}
+
+template <int MODE>
+__device__ __forceinline__ void rgb_eval(float d_nm, float ci, const RgbArgs &a, float rgb[3])
+{
+    if constexpr (MODE == SBX_RGB_LUT) rgb_lut(d_nm, ci, a, rgb);
+    else if constexpr (MODE == SBX_RGB_EXACT3) rgb_exact3(d_nm, ci, a, true, rgb);
+    else if constexpr (MODE == SBX_RGB_EXACT3_LINEAR) rgb_exact3(d_nm, ci, a, false, rgb);
+    else if constexpr (MODE == SBX_RGB_SCHLICK_WALL) rgb_schlick_wall(d_nm, ci, a, rgb);
+}
+
+// RgbColor::to_u8_tuple (interference.rs:73-79): round(255 x), alpha 255
+__device__ __forceinline__ uint32_t pack_rgba8(const float rgb[3])
+{
+    // f64::round is half-away-from-zero; inputs are in [0,1] so floor(255 x + 0.5) matches it
+    const uint32_t r = __float2uint_rz(fmaf(rgb[0], 255.f, 0.5f));
+    const uint32_t g = __float2uint_rz(fmaf(rgb[1], 255.f, 0.5f));
+    const uint32_t b = __float2uint_rz(fmaf(rgb[2], 255.f, 0.5f));
+    return r | (g << 8) | (b << 16) | 0xff000000u;
+}
+
+}  // namespace sbx

@@ -1,0 +1,92 @@
+// sbx_internal.cuh -- shared device/host structures of libsbx (not part of the public ABI).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sbx.h"
+
+namespace sbx {
+
+constexpr int kMaxFronts = 8;  // src/physics/drainage.rs:474
+
+// Integer description of the cells one TFE front covers this step.  Membership is decided on the
+// host with the reference's exact f64 predicate (TfeFront::contains, drainage.rs:55-71) and handed to
+// the kernels as closed global-row / column intervals, so the device test is pure integer compares.
+struct FrontCells {
+    int row_lo, row_hi;  // global theta rows, inclusive; row_lo > row_hi = empty
+    int c0_lo, c0_hi;    // direct phi interval, inclusive (empty if lo > hi)
+    int c1_lo, c1_hi;    // wrapped part of the interval (touches column 0 or num_phi-1)
+};
+
+struct FrontTable {
+    int count;
+    int row_min, row_max;  // union row range the reference iterates (drainage.rs:425-440)
+    FrontCells f[kMaxFronts];
+};
+
+// per-bubble constants (foam batches may vary radius and reference thickness per bubble)
+template <typename T>
+struct BubbleParam {
+    T diff_scale;  // (radius_ref / radius_b)^2 applied to the diffusion terms
+    T h_ref;       // F32 storage offset (0 for f64)
+    float radius;  // for the view cosine
+    float pad;
+};
+
+// colour-stage arguments
+struct RgbArgs {
+    int mode;    // sbx_rgb_mode
+    int format;  // sbx_rgb_format
+    void *out;   // RGBA8 (uint32 per cell) or 3 floats per cell, same [bubble][row][phi] order as the
+                 // owned rows (no ghost rows)
+    const float *colA;  // per column: cos(phi)*cam_x + sin(phi)*cam_z
+    float cam_y, cam2;  // cam_y, |cam|^2
+    float n_film, inv_n2;
+    float intensity;
+    float inv_max_nm;  // 1 / LUT max thickness
+    cudaTextureObject_t lut;
+    float inv_wl[3];  // 1/650, 1/532, 1/450
+};
+
+// arguments of one drainage step (CPU semantics)
+template <typename T>
+struct StepArgs {
+    const T *in;   // local buffer incl. ghost row at local row 0
+    T *out;
+    const T *coefS;          // per global row: {G, B, E, 0} (see host: build_row_tables)
+    const float2 *rowSC;     // per global row: {sin theta, cos theta}
+    const double4 *coefX;    // strict mode per global row: {sin theta, cos/sin_safe, sin_safe^2, 0}
+    const BubbleParam<T> *bub;
+    double *pole_partial;    // [batch][2][pole_slots]
+    int pole_slots;
+    int num_phi, num_theta;  // global grid
+    int row_begin;           // global row of local row 1
+    int l_first, l_last;     // local rows to update, inclusive (global poles excluded)
+    int band_rows;           // rows marched by one block
+    long long bubble_stride; // elements per bubble in in/out: (rows_local + 2) * num_phi
+    long long rgb_bubble_stride;  // cells per bubble in rgb out: rows_local * num_phi
+    T dt, crit, coefA;       // coefA = D / (R^2 dtheta^2)
+    T tfe_rdt;               // (1 - ratio) * 0.5 * dt
+    // strict-mode scalars, computed on the host exactly as the reference does (drainage.rs:305,353-369)
+    double s_drain_coef, s_dth2, s_two_dth, s_dph2, s_r2, s_D, s_dt, s_crit, s_tfe_factor;
+    FrontTable fronts;
+    RgbArgs rgb;
+};
+
+// arguments of one WGSL-semantics dispatch
+struct WgslArgs {
+    const float *h_in, *c_in;
+    float *h_out, *c_out;
+    const float *rowW;  // per global row float4: {sin, cos/sin_safe, 1/sin_safe^2, 1/sin_safe}
+    const float2 *rowSC;
+    int num_phi, num_theta, row_begin, l_first, l_last, band_rows;
+    int rows_local;
+    long long bubble_stride, rgb_bubble_stride;
+    sbx_drainage_params p;
+    float delta_theta, delta_phi;
+    float radius_view;
+    RgbArgs rgb;
+};
+
+}  // namespace sbx

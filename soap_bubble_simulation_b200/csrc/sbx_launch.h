@@ -1,0 +1,43 @@
+// sbx_launch.h -- host-callable launchers implemented in sbx_kernels.cu (internal).
+#pragma once
+
+#include "sbx_internal.cuh"
+
+namespace sbx {
+
+// one drainage step in CPU semantics: marching stencil (+ fused colour) then the pole rows.
+// `launches` is incremented once per kernel launched.
+template <typename T>
+cudaError_t launch_step(StepArgs<T> a, int batch, bool tfe, bool strict, bool has_top, bool has_bottom,
+                        int band_rows_req, cudaStream_t st, int *launches);
+
+template <typename T>
+cudaError_t launch_tfe_pass(T *buf, long long bubble_stride, int num_phi, int row_begin, int rows_local,
+                            int batch, const FrontTable &ft, double factor, cudaStream_t st, int *launches);
+
+template <typename T>
+cudaError_t launch_shade(StepArgs<T> a, int batch, int band_rows_req, cudaStream_t st, int *launches);
+
+cudaError_t launch_wgsl(WgslArgs a, int batch, int band_rows_req, cudaStream_t st, int *launches);
+
+template <typename TD, typename TS>
+cudaError_t launch_convert_in(TD *dst, const TS *src, long long n, long long bubble_stride, const double *href, cudaStream_t st);
+template <typename TD, typename TS>
+cudaError_t launch_convert_out(TD *dst, const TS *src, long long n, long long bubble_stride, const double *href, cudaStream_t st);
+template <typename T>
+cudaError_t launch_fill(T *dst, long long n, T v, cudaStream_t st);
+template <typename T>
+cudaError_t launch_minmax(const T *buf, long long n, double h_ref, double *part, int nblocks, cudaStream_t st);
+template <typename T>
+cudaError_t launch_sample(const T *buf, long long i00, long long i01, long long i10, long long i11, double tf,
+                          double pf, double h_ref, double *out, cudaStream_t st);
+
+cudaError_t launch_lut_build(uint8_t *out, int T, int A, float max_nm, float n_film, float intensity,
+                             const float *wl_dev, int n_lambda, cudaStream_t st);
+cudaError_t launch_interference_eval(double n_film, const double wl[3], const double *d_nm, const double *cos_i,
+                                     size_t n, int gamma, double *rgb, cudaStream_t st);
+cudaError_t launch_interference_terms(double n_film, const double *d_nm, const double *cos_i, size_t n, double wl,
+                                      double *out_cos_t, double *out_fresnel, double *out_intensity, cudaStream_t st);
+cudaError_t launch_col_view(float *colA, int num_phi, double cam_x, double cam_z, cudaStream_t st);
+
+}  // namespace sbx

@@ -1,0 +1,347 @@
+"""DrainageSimulator / ThicknessField -- host-side mirror of src/physics/drainage.rs over libsbx.
+
+Same names, argument meaning and error behaviour as the Rust API (drainage.rs:96-204, 212-614); the
+thickness field lives in HBM and every step runs the hand-written sm_100a kernels behind the C ABI
+(include/sbx.h).  ``thickness_field()`` returns a host view that is refreshed from the device on
+demand, which is what a Rust shim returning ``&ThicknessField`` has to do as well.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+from dataclasses import dataclass, field as _field
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib as L
+from .config import SimulationConfig
+
+
+@dataclass
+class View:
+    """Camera + optics of the colour stage (sbx_view).  Defaults: Camera::new (src/render/camera.rs:49-68:
+    distance 0.2, yaw 0, pitch 0.3), refractive index 1.33, interference_intensity 4.0 (pipeline.rs:75)."""
+    cam_pos: Sequence[float] = _field(default_factory=lambda: camera_position(0.2, 0.0, 0.3))
+    n_film: float = 1.33
+    intensity: float = 4.0
+    mode: int = L.RGB_LUT
+    format: int = L.OUT_RGBA8
+
+    def to_c(self) -> L.ViewC:
+        v = L.ViewC()
+        for k in range(3):
+            v.cam_pos[k] = float(self.cam_pos[k])
+        v.n_film, v.intensity, v.mode, v.format = self.n_film, self.intensity, self.mode, self.format
+        return v
+
+
+def camera_position(distance: float, yaw: float, pitch: float):
+    """Camera::position (src/render/camera.rs:63-68) for target = origin; f32 like the reference."""
+    d, y, p = np.float32(distance), np.float32(yaw), np.float32(pitch)
+    return (float(d * np.cos(p) * np.sin(y)), float(d * np.sin(p)), float(d * np.cos(p) * np.cos(y)))
+
+
+class ThicknessField:
+    """ThicknessField (drainage.rs:96-204).  Standalone it is a plain host container; obtained from
+    ``DrainageSimulator.thickness_field()`` it is a view of the device field (reductions run on the GPU,
+    ``data()`` downloads, ``set``/``data_mut`` edits are uploaded before the next step)."""
+
+    def __init__(self, num_theta: int, num_phi: int, initial_thickness: float, _sim=None):
+        self._num_theta, self._num_phi = int(num_theta), int(num_phi)
+        self._delta_theta = math.pi / (num_theta - 1)   # drainage.rs:123
+        self._delta_phi = 2.0 * math.pi / num_phi       # drainage.rs:124
+        self._sim = _sim
+        self._host: Optional[np.ndarray] = None
+        self._dirty = False
+        if _sim is None:
+            self._host = np.full((num_theta, num_phi), initial_thickness, dtype=np.float64)
+
+    # -- synchronisation with the device (attached fields only)
+    def _refresh(self) -> np.ndarray:
+        if self._sim is not None and (self._host is None or self._sim._host_stale) and not self._dirty:
+            self._host = self._sim.download(np.float64)[0]
+            self._sim._host_stale = False
+        return self._host
+
+    def _flush(self) -> None:
+        if self._sim is not None and self._dirty:
+            self._sim.upload(self._host)
+            self._dirty = False
+
+    def get(self, theta_index: int, phi_index: int) -> float:  # drainage.rs:137-139
+        return float(self._refresh()[theta_index, phi_index])
+
+    def set(self, theta_index: int, phi_index: int, value: float) -> None:  # drainage.rs:143-145
+        self._refresh()[theta_index, phi_index] = value
+        self._dirty = self._sim is not None
+
+    def theta_at(self, theta_index: int) -> float:  # drainage.rs:149-151
+        return theta_index * self._delta_theta
+
+    def phi_at(self, phi_index: int) -> float:  # drainage.rs:155-157
+        return phi_index * self._delta_phi
+
+    def num_theta(self) -> int:
+        return self._num_theta
+
+    def num_phi(self) -> int:
+        return self._num_phi
+
+    def delta_theta(self) -> float:
+        return self._delta_theta
+
+    def delta_phi(self) -> float:
+        return self._delta_phi
+
+    def min_thickness(self) -> float:  # drainage.rs:180-185
+        if self._sim is not None:
+            self._flush()
+            return self._sim.minmax()[0]
+        return float(self._host.min())
+
+    def max_thickness(self) -> float:  # drainage.rs:188-193
+        if self._sim is not None:
+            self._flush()
+            return self._sim.minmax()[1]
+        return float(self._host.max())
+
+    def data(self) -> np.ndarray:  # drainage.rs:196-198 (row-major [theta][phi], metres)
+        return self._refresh()
+
+    def data_mut(self) -> np.ndarray:  # drainage.rs:201-203
+        a = self._refresh()
+        self._dirty = self._sim is not None
+        return a
+
+
+class _DeviceField:
+    """Shared handle plumbing for the two simulator mirrors."""
+
+    def __init__(self, cfg: L.DrainageCfgC, device: int, keep=()):
+        self._keep = keep  # keeps numpy arrays behind cfg pointers alive during create
+        self._h = C.c_void_p()
+        L.check(L.lib().sbx_drainage_create(C.byref(cfg), device, C.byref(self._h)))
+        self.num_theta, self.num_phi, self.batch = cfg.num_theta, cfg.num_phi, cfg.batch
+        rb, re = cfg.row_begin, cfg.row_end
+        if rb == 0 and re == 0:
+            re = cfg.num_theta
+        self.row_begin, self.row_end = rb, re
+        self.rows_local = re - rb
+        self.device = device
+        self._host_stale = True
+        self._view_c = None
+
+    def close(self) -> None:
+        if getattr(self, "_h", None) is not None and self._h:
+            L.lib().sbx_drainage_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- field I/O (shape (batch, rows_local, num_phi))
+    def _shape(self):
+        return (self.batch, self.rows_local, self.num_phi)
+
+    def upload(self, field: np.ndarray) -> None:
+        a = np.ascontiguousarray(field)
+        if a.dtype not in (np.float32, np.float64):
+            a = a.astype(np.float64)
+        if a.size != self.batch * self.rows_local * self.num_phi:
+            raise ValueError(f"field has {a.size} cells, expected {self._shape()}")
+        L.check(L.lib().sbx_drainage_upload(self._h, a.ctypes.data, L.F64 if a.dtype == np.float64 else L.F32))
+        self._host_stale = True
+
+    def download(self, dtype=np.float64) -> np.ndarray:
+        out = np.empty(self._shape(), dtype=dtype)
+        L.check(L.lib().sbx_drainage_download(self._h, out.ctypes.data, L.F64 if out.dtype == np.float64 else L.F32))
+        return out
+
+    def download_rgb(self, fmt: int = L.OUT_RGBA8) -> np.ndarray:
+        if fmt == L.OUT_RGBA8:
+            out = np.empty(self._shape() + (4,), dtype=np.uint8)
+        else:
+            out = np.empty(self._shape() + (3,), dtype=np.float32)
+        L.check(L.lib().sbx_drainage_download_rgb(self._h, out.ctypes.data))
+        return out
+
+    def minmax(self):
+        mn, mx = C.c_double(), C.c_double()
+        L.check(L.lib().sbx_drainage_minmax(self._h, C.byref(mn), C.byref(mx)))
+        return mn.value, mx.value
+
+    def sync(self) -> None:
+        L.check(L.lib().sbx_drainage_sync(self._h))
+
+    def set_stream(self, cuda_stream: int) -> None:
+        L.check(L.lib().sbx_drainage_set_stream(self._h, C.c_void_p(cuda_stream)))
+
+    def device_ptr(self, kind: int) -> int:
+        p = C.c_void_p()
+        L.check(L.lib().sbx_drainage_device_ptr(self._h, kind, C.byref(p)))
+        return p.value
+
+    def launch_count(self) -> int:
+        n = C.c_int64()
+        L.check(L.lib().sbx_drainage_launch_count(self._h, C.byref(n)))
+        return n.value
+
+    def set_lut(self, lut_rgba: np.ndarray, max_nm: float = 2000.0) -> None:
+        a = np.ascontiguousarray(lut_rgba, dtype=np.uint8)
+        A, T = a.shape[0], a.shape[1]
+        L.check(L.lib().sbx_drainage_set_lut(self._h, a.ctypes.data, T, A, max_nm))
+
+    def shade(self, view: View) -> None:
+        vc = view.to_c()
+        L.check(L.lib().sbx_drainage_shade(self._h, C.byref(vc)))
+
+    def step_fused(self, dt: float, view: View, nsteps: int = 1) -> None:
+        vc = view.to_c()
+        L.check(L.lib().sbx_drainage_step_fused(self._h, dt, nsteps, C.byref(vc)))
+        self._host_stale = True
+
+    def step_host(self, dt: float, nsteps: int, view: Optional[View], host_in: Optional[np.ndarray],
+                  host_out_h: Optional[np.ndarray], host_out_rgb: Optional[np.ndarray]) -> None:
+        """Host-buffer round trip (sbx_drainage_step_host): upload, nsteps fused steps, download."""
+        vc = view.to_c() if view is not None else None
+
+        def dt_of(a):
+            return L.F64 if a is not None and a.dtype == np.float64 else L.F32
+
+        L.check(L.lib().sbx_drainage_step_host(
+            self._h, dt, nsteps, C.byref(vc) if vc is not None else None,
+            host_in.ctypes.data if host_in is not None else None, dt_of(host_in),
+            host_out_h.ctypes.data if host_out_h is not None else None, dt_of(host_out_h),
+            host_out_rgb.ctypes.data if host_out_rgb is not None else None))
+        self._host_stale = True
+
+    def attach_comm(self, comm) -> None:
+        L.check(L.lib().sbx_drainage_attach_comm(self._h, comm._c))
+        self._comm = comm
+
+    def minmax_global(self):
+        mn, mx = C.c_double(), C.c_double()
+        L.check(L.lib().sbx_drainage_minmax_global(self._h, C.byref(mn), C.byref(mx)))
+        return mn.value, mx.value
+
+
+class DrainageSimulator(_DeviceField):
+    """DrainageSimulator (drainage.rs:212-614).
+
+    ``precision``: ``PREC_F32`` (4 B/cell; the field is stored relative to ``h_ref`` -- by default the
+    initial uniform thickness -- so that the sub-ulp increments of the default configuration are kept),
+    ``PREC_F64`` or ``PREC_F64_STRICT`` (bit-identical to the f64 CPU path).
+    """
+
+    def __init__(self, config: Optional[SimulationConfig] = None, *, precision: int = L.PREC_F32,
+                 device: int = 0, h_ref: Optional[float] = None, num_theta: Optional[int] = None,
+                 num_phi: Optional[int] = None, batch: int = 1, batch_h0_m=None, batch_radius_m=None,
+                 row_begin: int = 0, row_end: int = 0):
+        config = config or SimulationConfig.default()
+        self.config = config
+        cfg = L.DrainageCfgC()
+        L.check(L.lib().sbx_drainage_cfg_default(C.byref(cfg)))
+        cfg.num_theta = int(num_theta if num_theta is not None else config.resolution)      # drainage.rs:264
+        cfg.num_phi = int(num_phi if num_phi is not None else config.resolution * 2)        # drainage.rs:265
+        cfg.batch = batch
+        cfg.h0_m = config.film_thickness_meters()                                            # drainage.rs:266
+        cfg.density = config.fluid.density
+        cfg.gravity = config.environment.gravity
+        cfg.viscosity = config.fluid.viscosity
+        cfg.diffusion = config.fluid.surfactant_diffusion
+        cfg.critical_thickness_m = config.bubble.critical_thickness_nm * 1e-9               # drainage.rs:278
+        cfg.radius_m = config.bubble_radius()
+        cfg.semantics = L.SEM_CPU
+        cfg.precision = precision
+        cfg.h_ref_m = cfg.h0_m if h_ref is None else h_ref
+        cfg.row_begin, cfg.row_end = row_begin, row_end
+        keep = []
+        if batch_h0_m is not None:
+            a = np.ascontiguousarray(batch_h0_m, dtype=np.float64)
+            cfg.batch_h0_m = a.ctypes.data_as(C.POINTER(C.c_double))
+            keep.append(a)
+        if batch_radius_m is not None:
+            a = np.ascontiguousarray(batch_radius_m, dtype=np.float64)
+            cfg.batch_radius_m = a.ctypes.data_as(C.POINTER(C.c_double))
+            keep.append(a)
+        super().__init__(cfg, device, keep)
+        self.precision = precision
+        self._field = ThicknessField(cfg.num_theta, cfg.num_phi, cfg.h0_m, _sim=self)
+
+    @classmethod
+    def new(cls, config: SimulationConfig, **kw) -> "DrainageSimulator":  # drainage.rs:263
+        return cls(config, **kw)
+
+    def step(self, dt: float, nsteps: int = 1) -> None:  # drainage.rs:298-392
+        self._field._flush()
+        L.check(L.lib().sbx_drainage_step(self._h, dt, nsteps))
+        self._host_stale = True
+
+    def step_fused(self, dt: float, view: View, nsteps: int = 1) -> None:
+        self._field._flush()
+        super().step_fused(dt, view, nsteps)
+
+    def get_thickness(self, theta: float, phi: float, bubble: int = 0) -> float:  # drainage.rs:516-552
+        self._field._flush()
+        out = C.c_double()
+        L.check(L.lib().sbx_drainage_get_thickness(self._h, bubble, theta, phi, C.byref(out)))
+        return out.value
+
+    def thickness_field(self) -> ThicknessField:  # drainage.rs:555-557
+        return self._field
+
+    def current_time(self) -> float:  # drainage.rs:560-562
+        out = C.c_double()
+        L.check(L.lib().sbx_drainage_current_time(self._h, C.byref(out)))
+        return out.value
+
+    def has_critical_region(self) -> bool:  # drainage.rs:565-567
+        self._field._flush()
+        out = C.c_int32()
+        L.check(L.lib().sbx_drainage_has_critical(self._h, C.byref(out)))
+        return bool(out.value)
+
+    def critical_thickness(self) -> float:  # drainage.rs:570-572
+        out = C.c_double()
+        L.check(L.lib().sbx_drainage_critical_thickness(self._h, C.byref(out)))
+        return out.value
+
+    def reset(self, initial_thickness: float) -> None:  # drainage.rs:575-583
+        L.check(L.lib().sbx_drainage_reset(self._h, initial_thickness))
+        self._field._dirty = False
+        self._host_stale = True
+
+    def set_marginal_regeneration(self, enabled: bool) -> None:  # drainage.rs:588-593
+        L.check(L.lib().sbx_drainage_set_marginal_regeneration(self._h, int(bool(enabled))))
+
+    def marginal_regeneration_enabled(self) -> bool:  # drainage.rs:596-598
+        out = C.c_int32()
+        L.check(L.lib().sbx_drainage_marginal_regeneration(self._h, C.byref(out)))
+        return bool(out.value)
+
+    def set_tfe_thickness_ratio(self, ratio: float) -> None:  # drainage.rs:601-603
+        L.check(L.lib().sbx_drainage_set_tfe_ratio(self._h, ratio))
+
+    def tfe_thickness_ratio(self) -> float:  # drainage.rs:606-608
+        out = C.c_double()
+        L.check(L.lib().sbx_drainage_tfe_ratio(self._h, C.byref(out)))
+        return out.value
+
+    def active_tfe_count(self) -> int:  # drainage.rs:611-613
+        out = C.c_int32()
+        L.check(L.lib().sbx_drainage_active_tfe_count(self._h, C.byref(out)))
+        return out.value
+
+    def fronts(self):
+        buf = (L.TfeFrontC * 8)()
+        n = C.c_int32()
+        L.check(L.lib().sbx_drainage_fronts(self._h, buf, C.byref(n)))
+        return [(buf[k].phi_center, buf[k].extent, buf[k].width, buf[k].velocity) for k in range(n.value)]
+
+    def set_physics(self, density, gravity, viscosity, diffusion, critical_thickness_m, radius_m) -> None:
+        L.check(L.lib().sbx_drainage_set_physics(self._h, density, gravity, viscosity, diffusion,
+                                                 critical_thickness_m, radius_m))
