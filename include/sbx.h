@@ -127,7 +127,7 @@ typedef struct {
  * n = (sin th cos ph, cos th, sin th sin ph) (src/physics/geometry.rs:184-186, bubble.wgsl:487-494). */
 typedef struct {
     double cam_pos[3]; /* Camera::position(), src/render/camera.rs:63-68 */
-    float n_film;      /* bubble.refractive_index */
+    double n_film;     /* bubble.refractive_index (f64 like InterferenceCalculator; the LUT path rounds it to f32) */
     float intensity;   /* bubble.interference_intensity (4.0 default, pipeline.rs:75); LUT mode only */
     int32_t mode;      /* sbx_rgb_mode */
     int32_t format;    /* sbx_rgb_format */

@@ -684,3 +684,52 @@ double orc_view_cos(double theta, double phi, double radius, const double cam[3]
     double d = (v[0] * n[0] + v[1] * n[1] + v[2] * n[2]) / len;
     return fabs(d);
 }
+
+void orc_shade_field(const double *h, int num_theta, int num_phi, int row0, int num_rows, double radius,
+                     const double cam[3], double n_film, const uint8_t *lut, int T, int A, float max_nm,
+                     float intensity, int mode, uint8_t *out, int nthreads)
+{
+    orc_interference ic;
+    orc_interference_new(&ic, n_film);
+    const double dth = M_PI / (double)(num_theta - 1), dph = 2.0 * M_PI / (double)num_phi;
+    if (nthreads < 1) nthreads = 1;
+    /* per-column trig hoisted out of the cell loop; the values (and so the results) are those of
+     * orc_view_cos evaluated per cell */
+    double *sp = (double *)malloc((size_t)num_phi * sizeof(double));
+    double *cp = (double *)malloc((size_t)num_phi * sizeof(double));
+    for (int j = 0; j < num_phi; ++j) {
+        sp[j] = sin((double)j * dph);
+        cp[j] = cos((double)j * dph);
+    }
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+    for (int r = 0; r < num_rows; ++r) {
+        const double theta = (double)(row0 + r) * dth;
+        const double st = sin(theta), ct = cos(theta);
+        for (int j = 0; j < num_phi; ++j) {
+            const size_t idx = (size_t)r * (size_t)num_phi + (size_t)j;
+            const double n[3] = {st * cp[j], ct, st * sp[j]};
+            const double v[3] = {cam[0] - radius * n[0], cam[1] - radius * n[1], cam[2] - radius * n[2]};
+            const double len = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+            const double c = fabs((v[0] * n[0] + v[1] * n[1] + v[2] * n[2]) / len);
+            const double d_nm = h[idx] * 1e9;
+            double rgb[3];
+            if (mode == 1) {
+                float f[3];
+                orc_lut_shade(lut, T, A, max_nm, (float)d_nm, (float)c, intensity, f);
+                rgb[0] = f[0]; rgb[1] = f[1]; rgb[2] = f[2];
+            } else if (mode == 2) {
+                orc_interference_color(&ic, d_nm, c, rgb);
+            } else {
+                orc_interference_color_linear(&ic, d_nm, c, rgb);
+            }
+            uint8_t px[3];
+            orc_rgb_to_u8(rgb, px);
+            out[4 * idx + 0] = px[0];
+            out[4 * idx + 1] = px[1];
+            out[4 * idx + 2] = px[2];
+            out[4 * idx + 3] = 255;
+        }
+    }
+    free(sp);
+    free(cp);
+}

@@ -144,6 +144,14 @@ void orc_lut_shade(const uint8_t *lut_rgba, int T, int A, float max_nm, float d_
  * cos = |dot(normalize(cam - world), n)| (src/render/shaders/bubble.wgsl:487-494). */
 double orc_view_cos(double theta, double phi, double radius, const double cam[3]);
 
+/* Colour frame of a whole thickness field (row-major [theta][phi], metres), the CPU counterpart of the
+ * fused colour stage: per cell view cosine as orc_view_cos, then mode 1 = orc_lut_shade (bubble.wgsl:425-439)
+ * or mode 2/3 = orc_interference_color / _linear (interference.rs:380-426); RGBA8 via round(255 x), A=255
+ * (interference.rs:73-79).  row0/num_rows select a band of the global grid; OpenMP over rows. */
+void orc_shade_field(const double *h, int num_theta, int num_phi, int row0, int num_rows, double radius,
+                     const double cam[3], double n_film, const uint8_t *lut_rgba, int T, int A, float max_nm,
+                     float intensity, int mode, uint8_t *out_rgba, int nthreads);
+
 #ifdef __cplusplus
 }
 #endif

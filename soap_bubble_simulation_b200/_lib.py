@@ -52,7 +52,7 @@ class DrainageCfgC(C.Structure):
 
 
 class ViewC(C.Structure):
-    _fields_ = [("cam_pos", C.c_double * 3), ("n_film", C.c_float), ("intensity", C.c_float),
+    _fields_ = [("cam_pos", C.c_double * 3), ("n_film", C.c_double), ("intensity", C.c_float),
                 ("mode", C.c_int32), ("format", C.c_int32)]
 
 

@@ -95,6 +95,8 @@ struct sbx_drainage {
     int cur = 0;
 
     void *coefS = nullptr;      // T x 4 per global row
+    float *coefF = nullptr;     // f32 fast path: float4 per global row
+    bool use_tma = true;        // SBX_NO_TMA=1 forces the direct-load kernel (A/B measurements)
     float2 *rowSC = nullptr;
     double4 *coefX = nullptr;
     float *rowW = nullptr;      // WGSL per-row float4
@@ -153,6 +155,7 @@ static void free_all(sbx_drainage *h)
         if (h->conc[i]) cudaFree(h->conc[i]);
     }
     cudaFree(h->coefS);
+    cudaFree(h->coefF);
     cudaFree(h->rowSC);
     cudaFree(h->coefX);
     cudaFree(h->rowW);
@@ -225,6 +228,7 @@ static int32_t upload_tables_t(sbx_drainage *h)
     const double coef = h->density * h->gravity / (3.0 * h->viscosity);  // drainage.rs:305
     const double r2 = h->radius * h->radius;
     std::vector<T> cs((size_t)N * 4, T(0));
+    std::vector<float> cf((size_t)N * 4, 0.f);
     std::vector<float2> sc((size_t)N);
     std::vector<double4> cx((size_t)N);
     for (int g = 0; g < N; ++g) {
@@ -237,10 +241,17 @@ static int32_t upload_tables_t(sbx_drainage *h)
             cs[4 * (size_t)g + 0] = (T)(coef * s);
             cs[4 * (size_t)g + 1] = (T)(h->diffusion * (c / s_safe) / (r2 * 2.0 * dth));
             cs[4 * (size_t)g + 2] = (T)(h->diffusion / (r2 * dph * dph * s_safe * s_safe));
+            const double A = h->diffusion / (r2 * dth * dth);
+            const double B = h->diffusion * (c / s_safe) / (r2 * 2.0 * dth);
+            cf[4 * (size_t)g + 0] = (float)(A + B);
+            cf[4 * (size_t)g + 1] = (float)(A - B);
+            cf[4 * (size_t)g + 2] = (float)(h->diffusion / (r2 * dph * dph * s_safe * s_safe));
+            cf[4 * (size_t)g + 3] = (float)(coef * s);
         }
     }
     h->coefA = h->diffusion / (r2 * dth * dth);
     CU(cudaMemcpyAsync(h->coefS, cs.data(), cs.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->coefF, cf.data(), cf.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->rowSC, sc.data(), sc.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->coefX, cx.data(), cx.size() * sizeof(double4), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));  // host vectors go out of scope
@@ -356,6 +367,7 @@ extern "C" int32_t sbx_drainage_create(const sbx_drainage_cfg *cfg, int32_t devi
     if (!h->f64 && cfg->batch_h0_m && cfg->h_ref_m != 0.0) h->b_href = h->b_h0;
     h->href_zero = std::all_of(h->b_href.begin(), h->b_href.end(), [](double v) { return v == 0.0; });
     if (const char *s = getenv("SBX_BAND_ROWS")) h->band_rows = atoi(s);
+    if (const char *s = getenv("SBX_NO_TMA")) h->use_tma = atoi(s) == 0;
 
 #define CU_H(expr)                                                                     \
     do {                                                                               \
@@ -376,6 +388,7 @@ extern "C" int32_t sbx_drainage_create(const sbx_drainage_cfg *cfg, int32_t devi
         for (int i = 0; i < 2; ++i) CU_H(cudaMalloc(&h->conc[i], (size_t)h->total_elems * 4));
     const int N = h->num_theta;
     CU_H(cudaMalloc(&h->coefS, (size_t)N * 4 * h->esz));
+    CU_H(cudaMalloc(&h->coefF, (size_t)N * 4 * sizeof(float)));
     CU_H(cudaMalloc(&h->rowSC, (size_t)N * sizeof(float2)));
     CU_H(cudaMalloc(&h->coefX, (size_t)N * sizeof(double4)));
     CU_H(cudaMalloc(&h->rowW, (size_t)N * sizeof(float4)));
@@ -625,7 +638,7 @@ static int32_t prepare_rgb(sbx_drainage *h, const sbx_view *v, RgbArgs &r)
     if (!v || v->mode == SBX_RGB_NONE) { r.mode = SBX_RGB_NONE; return SBX_OK; }
     if (v->mode < SBX_RGB_NONE || v->mode > SBX_RGB_SCHLICK_WALL) return fail(SBX_ERR_INVALID, "bad rgb mode %d", v->mode);
     if (v->format != SBX_OUT_RGBA8 && v->format != SBX_OUT_RGB_F32) return fail(SBX_ERR_INVALID, "bad rgb format %d", v->format);
-    if (!(v->n_film > 0.f)) return fail(SBX_ERR_INVALID, "n_film must be > 0");
+    if (!(v->n_film > 0.0)) return fail(SBX_ERR_INVALID, "n_film must be > 0");
     const size_t cells = (size_t)h->batch * h->rows_local * h->num_phi;
     const size_t need = cells * (v->format == SBX_OUT_RGBA8 ? 4 : 12);
     if (h->rgb_bytes < need) {
@@ -640,7 +653,7 @@ static int32_t prepare_rgb(sbx_drainage *h, const sbx_view *v, RgbArgs &r)
         memcpy(h->cam_cached, v->cam_pos, sizeof h->cam_cached);
     }
     if (v->mode == SBX_RGB_LUT) {
-        int32_t rc = ensure_lut(h, v->n_film);
+        int32_t rc = ensure_lut(h, (float)v->n_film);
         if (rc != SBX_OK) return rc;
     }
     r.mode = v->mode;
@@ -649,14 +662,15 @@ static int32_t prepare_rgb(sbx_drainage *h, const sbx_view *v, RgbArgs &r)
     r.colA = h->colA;
     r.cam_y = (float)v->cam_pos[1];
     r.cam2 = (float)(v->cam_pos[0] * v->cam_pos[0] + v->cam_pos[1] * v->cam_pos[1] + v->cam_pos[2] * v->cam_pos[2]);
-    r.n_film = v->n_film;
-    r.inv_n2 = (float)(1.0 / ((double)v->n_film * (double)v->n_film));
+    r.n_film = (float)v->n_film;
+    r.inv_n2 = (float)(1.0 / (v->n_film * v->n_film));
     r.intensity = v->intensity;
     r.inv_max_nm = 1.0f / h->lut_max_nm;
+    r.nm_over_max = 1e9f / h->lut_max_nm;
     r.lut = h->lut_tex;
-    r.inv_wl[0] = (float)(1.0 / 650.0);  // interference.rs:26-30
-    r.inv_wl[1] = (float)(1.0 / 532.0);
-    r.inv_wl[2] = (float)(1.0 / 450.0);
+    r.inv_n2_d = 1.0 / (v->n_film * v->n_film);
+    const double wl[3] = {650.0, 532.0, 450.0};  // interference.rs:26-30
+    for (int k = 0; k < 3; ++k) r.two_n_over_wl[k] = 2.0 * v->n_film / wl[k];
     return SBX_OK;
 }
 
@@ -744,6 +758,7 @@ static void fill_step_args(sbx_drainage *h, StepArgs<T> &a, double dt, const Rgb
     a.in = tbuf<T>(h, h->cur);
     a.out = tbuf<T>(h, 1 - h->cur);
     a.coefS = reinterpret_cast<const T *>(h->coefS);
+    a.coefF = h->coefF;
     a.rowSC = h->rowSC;
     a.coefX = h->coefX;
     a.bub = reinterpret_cast<const BubbleParam<T> *>(h->bub);
@@ -791,7 +806,7 @@ static int32_t step_cpu_sem(sbx_drainage *h, double dt, const RgbArgs &rgb)
         RgbArgs none;
         memset(&none, 0, sizeof none);
         a.rgb = none;
-        CU(launch_step<T>(a, h->batch, false, true, has_top, has_bottom, h->band_rows, h->stream, &n));
+        CU(launch_step<T>(a, h->batch, false, true, has_top, has_bottom, h->band_rows, false, h->stream, &n));
         CU(launch_tfe_pass<T>(tbuf<T>(h, 1 - h->cur), h->bubble_stride, h->num_phi, h->row_begin, h->rows_local,
                               h->batch, ft, a.s_tfe_factor, h->stream, &n));
         h->cur = 1 - h->cur;
@@ -804,7 +819,7 @@ static int32_t step_cpu_sem(sbx_drainage *h, double dt, const RgbArgs &rgb)
         }
     } else {
         a.fronts = ft;
-        CU(launch_step<T>(a, h->batch, ft.count > 0, false, has_top, has_bottom, h->band_rows, h->stream, &n));
+        CU(launch_step<T>(a, h->batch, ft.count > 0, false, has_top, has_bottom, h->band_rows, h->use_tma, h->stream, &n));
         h->cur = 1 - h->cur;
     }
     h->launches += n;

@@ -167,44 +167,73 @@ __device__ __forceinline__ float sinpi_half(float x)
     return p * x;
 }
 
-// InterferenceCalculator::calculate_interference_color[_linear] (src/physics/interference.rs:380-426)
-// in f32: Snell (197-211), exact Fresnel average (266-298), OPD with lambda/2 (226-238), multi-bounce
-// Airy (344-352) rewritten with 1-cos(phi) = 2 sin^2(phi/2) and phase reduced in cycles.
-__device__ __forceinline__ void rgb_exact3(float d_nm, float ci, const RgbArgs &a, bool gamma, float rgb[3])
+// Fringe phase in cycles, reduced to [-0.5, 0.5], for the three colour wavelengths:
+//   cyc_k = 2 n d cos(theta_t) / lambda_k          (interference.rs:226-254 without the lambda/2 term)
+// evaluated in f64.  Near grazing incidence R -> 1 and the Airy fringes become needle-sharp (finesse
+// ~ 1/(1-R)): an fp32 phase (relative error 1e-7 on ~10 cycles) would move the colour by > 1e-4 there.
+// cos(theta_t) is an fp32 SFU square root polished by one Newton step in f64.
+struct Phase3 {
+    float y[3];  // distance of the phase from the nearest fringe zero, in cycles: 1/2 - |frac(cyc)|
+    float ct;    // cos(theta_t)
+};
+
+__device__ __forceinline__ Phase3 phase3(double d_nm, float ci, const RgbArgs &a)
 {
-    ci = fminf(fmaxf(ci, -1.f), 1.f);
-    const float s2 = (1.f - ci * ci) * a.inv_n2;
-    const float ct = sqrt_approx(fmaxf(1.f - s2, 0.f));
-    const float n = a.n_film;
-    const float a1 = ci, b1 = n * ct, c1 = n * ci, d1 = ct;
-    const float ds = a1 + b1, dp = c1 + d1;
-    const float inv = rcp_approx(ds * dp);
-    const float rs = (a1 - b1) * dp * inv;
-    const float rp = (c1 - d1) * ds * inv;
-    const float R = 0.5f * (rs * rs + rp * rp);
-    const float omr = 1.f - R;
-    const float opd2 = 2.f * n * d_nm * ct;
+    const double cid = (double)ci;
+    const double x = fma(-(1.0 - cid * cid), a.inv_n2_d, 1.0);  // 1 - sin^2(theta_t), interference.rs:199-210
+    const float ct0 = sqrt_approx(fmaxf((float)x, 1e-30f));
+    const double c0 = (double)ct0;
+    const double ctd = fma(x - c0 * c0, (double)(0.5f * rcp_approx(ct0)), c0);
+    const double base = d_nm * ctd;
+    Phase3 p;
+    p.ct = (float)ctd;
 #pragma unroll
     for (int k = 0; k < 3; ++k) {
-        const float cyc = fmaf(opd2, a.inv_wl[k], 0.5f);
-        const float f = cyc - rintf(cyc);
-        const float s = sinpi_half(f);
-        const float num = 4.f * R * s * s;
-        const float den = fmaf(omr, omr, num);
+        const double cyc = base * a.two_n_over_wl[k];
+        p.y[k] = (float)(0.5 - fabs(cyc - rint(cyc)));  // formed in f64: keeps relative accuracy at the zeros
+    }
+    return p;
+}
+
+// sin^2(pi (cyc + 1/2)) = cos^2(pi fr) = sin^2(pi (1/2 - |fr|)): the lambda/2 reflection shift
+// (interference.rs:235-237) folded in without adding 0.5 to a rounded number
+__device__ __forceinline__ float fringe_sin2(float y)
+{
+    const float s = sinpi_half(y);
+    return s * s;
+}
+
+// InterferenceCalculator::calculate_interference_color[_linear] (src/physics/interference.rs:380-426):
+// Snell (197-211), exact Fresnel average (266-298), OPD with lambda/2 (226-238), multi-bounce Airy
+// (344-352) with 1 - cos(phi) = 2 sin^2(phi/2).  1 - R is formed without cancellation from the
+// transmittances: 1 - r_s^2 = 4 ci n ct / (ci + n ct)^2, 1 - r_p^2 = 4 n ci ct / (n ci + ct)^2.
+__device__ __forceinline__ void rgb_exact3(double d_nm, float ci, const RgbArgs &a, bool gamma, float rgb[3])
+{
+    ci = fminf(fmaxf(ci, -1.f), 1.f);
+    const Phase3 ph = phase3(d_nm, ci, a);
+    const float n = a.n_film, ct = ph.ct;
+    const float ds = fmaf(n, ct, ci), dp = fmaf(n, ci, ct);
+    const float inv = rcp_approx(ds * dp);
+    const float P = 4.f * n * ci * ct;
+    const float omr = 0.5f * P * inv * inv * fmaf(ds, ds, dp * dp);  // 1 - R
+    const float R = 1.f - omr;
+    const float omr2 = omr * omr;
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float num = 4.f * R * fringe_sin2(ph.y[k]);
+        const float den = omr2 + num;
         float I = den < 1e-30f ? R : num * rcp_approx(den);  // |den| < eps -> R, interference.rs:348-350
-        I = d_nm <= 0.f ? 0.f : clamp01(I);
+        I = d_nm <= 0.0 ? 0.f : clamp01(I);                   // interference.rs:319-321
         if (gamma) I = ex2_approx(lg2_approx(I) * (1.0f / 2.2f));  // powf(1/2.2); lg2(0) = -inf -> 0
         rgb[k] = clamp01(I);
     }
 }
 
 // wall.wgsl:165-207
-__device__ __forceinline__ void rgb_schlick_wall(float d_nm, float ci, const RgbArgs &a, float rgb[3])
+__device__ __forceinline__ void rgb_schlick_wall(double d_nm, float ci, const RgbArgs &a, float rgb[3])
 {
+    const Phase3 ph = phase3(d_nm, ci, a);
     const float n = a.n_film;
-    const float s2 = (1.f - ci * ci) * a.inv_n2;
-    const float ct = s2 > 1.f ? 0.f : sqrt_approx(1.f - s2);
-    const float opd2 = 2.f * n * d_nm * ct;
     const float q = (1.f - n) / (1.f + n);
     const float r0 = q * q;
     const float m = 1.f - ci, m2 = m * m;
@@ -212,12 +241,7 @@ __device__ __forceinline__ void rgb_schlick_wall(float d_nm, float ci, const Rgb
     const float omr = 1.f - R;
     const float F = 4.f * R * rcp_approx(omr * omr);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const float cyc = fmaf(opd2, a.inv_wl[k], 0.5f);  // delta/2pi = opd/lambda + 1/2
-        const float f = cyc - rintf(cyc);
-        const float s = sinpi_half(f);
-        rgb[k] = rcp_approx(fmaf(F, s * s, 1.f));
-    }
+    for (int k = 0; k < 3; ++k) rgb[k] = rcp_approx(fmaf(F, fringe_sin2(ph.y[k]), 1.f));
 }
 
 // bubble.wgsl:425-439 through the texture unit: linear filter, clamp-to-edge, normalised coordinates,
@@ -232,8 +256,14 @@ __device__ __forceinline__ void rgb_lut(float d_nm, float ci, const RgbArgs &a, 
     rgb[2] = clamp01(t.z * a.intensity);
 }
 
+// thickness in nm handed to the colour stage: f32 is enough for the LUT fetch, the analytic modes need
+// the f64 phase (see phase3)
+template <int MODE> struct Dnm { using type = double; };
+template <> struct Dnm<SBX_RGB_LUT> { using type = float; };
+template <> struct Dnm<SBX_RGB_NONE> { using type = float; };
+
 template <int MODE>
-__device__ __forceinline__ void rgb_eval(float d_nm, float ci, const RgbArgs &a, float rgb[3])
+__device__ __forceinline__ void rgb_eval(typename Dnm<MODE>::type d_nm, float ci, const RgbArgs &a, float rgb[3])
 {
     if constexpr (MODE == SBX_RGB_LUT) rgb_lut(d_nm, ci, a, rgb);
     else if constexpr (MODE == SBX_RGB_EXACT3) rgb_exact3(d_nm, ci, a, true, rgb);

@@ -45,8 +45,10 @@ struct RgbArgs {
     float n_film, inv_n2;
     float intensity;
     float inv_max_nm;  // 1 / LUT max thickness
+    float nm_over_max; // 1e9 / LUT max thickness: metres -> LUT u coordinate
     cudaTextureObject_t lut;
-    float inv_wl[3];  // 1/650, 1/532, 1/450
+    double inv_n2_d;          // 1/n^2 in f64 for the phase
+    double two_n_over_wl[3];  // 2 n / lambda_k at 650, 532, 450 nm (interference.rs:26-30)
 };
 
 // arguments of one drainage step (CPU semantics)
@@ -54,7 +56,8 @@ template <typename T>
 struct StepArgs {
     const T *in;   // local buffer incl. ghost row at local row 0
     T *out;
-    const T *coefS;          // per global row: {G, B, E, 0} (see host: build_row_tables)
+    const T *coefS;          // per global row: {G, B, E, 0} (see host: upload_tables_t)
+    const float *coefF;      // f32 fast path, per global row: {A+B, A-B, E, G}
     const float2 *rowSC;     // per global row: {sin theta, cos theta}
     const double4 *coefX;    // strict mode per global row: {sin theta, cos/sin_safe, sin_safe^2, 0}
     const BubbleParam<T> *bub;

@@ -20,7 +20,7 @@ namespace sbx {
 
 // ------------------------------------------------------------------ colour output helpers
 template <int MODE, int VEC>
-__device__ __forceinline__ void emit_rgb(const float *d_nm, const float *ci, const RgbArgs &rgb,
+__device__ __forceinline__ void emit_rgb(const typename Dnm<MODE>::type *d_nm, const float *ci, const RgbArgs &rgb,
                                          long long cell0)
 {
     if constexpr (MODE != SBX_RGB_NONE) {
@@ -175,10 +175,12 @@ __global__ void __launch_bounds__(256) k_march(const StepArgs<T> a)
             if constexpr (MODE != SBX_RGB_NONE) {
                 const float2 sc = __ldg(a.rowSC + grow);
                 const float ccy = sc.y * a.rgb.cam_y;
-                float d_nm[VEC], ci[VEC];
+                using DN = typename Dnm<MODE>::type;
+                DN d_nm[VEC];
+                float ci[VEC];
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) {
-                    d_nm[k] = (float)((nw.v[k] + href) * T(1e9));
+                    d_nm[k] = ((DN)nw.v[k] + (DN)href) * (DN)1e9;
                     ci[k] = view_cos(sc.x, ccy, colA[k], Rv, a.rgb.cam2);
                 }
                 emit_rgb<MODE, VEC>(d_nm, ci, a.rgb,
@@ -195,11 +197,13 @@ __global__ void __launch_bounds__(256) k_march(const StepArgs<T> a)
 // ------------------------------------------------------------------ poles
 // thickness[0][*] = mean(updated ring 1), thickness[N-1][*] = mean(updated ring N-2)
 // (src/physics/drainage.rs:480-503), then the TFE reduction if a front's row range reaches the pole
-// row (drainage.rs:437-460), then the pole rows' colour.  grid = (2, batch); which = blockIdx.x.
+// row (drainage.rs:437-460), then the pole rows' colour.  grid = (2 * blocks_per_pole, batch); every
+// block re-derives the (tiny) mean itself and writes a 1024-column slice of the row.
 template <typename T, int MODE, bool STRICT>
-__global__ void __launch_bounds__(256) k_poles(const StepArgs<T> a, int has_top, int has_bottom)
+__global__ void __launch_bounds__(256) k_poles(const StepArgs<T> a, int has_top, int has_bottom, int blocks_per_pole)
 {
-    const int which = blockIdx.x;  // 0 top, 1 bottom
+    const int which = blockIdx.x / blocks_per_pole;  // 0 top, 1 bottom
+    const int col0 = (blockIdx.x % blocks_per_pole) * 1024;
     if ((which == 0 && !has_top) || (which == 1 && !has_bottom)) return;
     const int b = blockIdx.y;
     const int N = a.num_phi;
@@ -230,7 +234,7 @@ __global__ void __launch_bounds__(256) k_poles(const StepArgs<T> a, int has_top,
     const float ccy = sc.y * a.rgb.cam_y;
     unsigned rm = 0;
     if (a.fronts.count > 0) rm = front_row_mask(a.fronts, grow);
-    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    for (int j = col0 + threadIdx.x; j < min(N, col0 + 1024); j += blockDim.x) {
         T w = v;
         if (rm && front_hit(a.fronts, rm, j)) {
             if constexpr (STRICT) w = (T)__dmul_rn((double)w, a.s_tfe_factor);
@@ -238,7 +242,8 @@ __global__ void __launch_bounds__(256) k_poles(const StepArgs<T> a, int has_top,
         }
         out[(long long)l * N + j] = w;
         if constexpr (MODE != SBX_RGB_NONE) {
-            float d_nm[1] = {(float)((w + bp.h_ref) * T(1e9))};
+            using DN = typename Dnm<MODE>::type;
+            DN d_nm[1] = {((DN)w + (DN)bp.h_ref) * (DN)1e9};
             float ci[1] = {view_cos(sc.x, ccy, __ldg(a.rgb.colA + j), bp.radius, a.rgb.cam2)};
             emit_rgb<MODE, 1>(d_nm, ci, a.rgb, (long long)b * a.rgb_bubble_stride + (long long)(l - 1) * N + j);
         }
@@ -282,10 +287,12 @@ __global__ void __launch_bounds__(256) k_shade(const StepArgs<T> a)
         const Vec<T, VEC> h = ldv<T, VEC>(in + (long long)l * N + j0);
         const float2 sc = __ldg(a.rowSC + grow);
         const float ccy = sc.y * a.rgb.cam_y;
-        float d_nm[VEC], ci[VEC];
+        using DN = typename Dnm<MODE>::type;
+        DN d_nm[VEC];
+        float ci[VEC];
 #pragma unroll
         for (int k = 0; k < VEC; ++k) {
-            d_nm[k] = (float)((h.v[k] + bp.h_ref) * T(1e9));
+            d_nm[k] = ((DN)h.v[k] + (DN)bp.h_ref) * (DN)1e9;
             ci[k] = view_cos(sc.x, ccy, colA[k], bp.radius, a.rgb.cam2);
         }
         emit_rgb<MODE, VEC>(d_nm, ci, a.rgb, (long long)b * a.rgb_bubble_stride + (long long)(l - 1) * N + j0);
@@ -404,10 +411,12 @@ __global__ void __launch_bounds__(256) k_wgsl(const WgslArgs a)
             if constexpr (MODE != SBX_RGB_NONE) {
                 const float2 sc = __ldg(a.rowSC + grow);
                 const float ccy = sc.y * a.rgb.cam_y;
-                float d_nm[VEC], ci[VEC];
+                using DN = typename Dnm<MODE>::type;
+                DN d_nm[VEC];
+                float ci[VEC];
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) {
-                    d_nm[k] = hn.v[k] * 1e9f;
+                    d_nm[k] = (DN)hn.v[k] * (DN)1e9;
                     ci[k] = view_cos(sc.x, ccy, colA[k], a.radius_view, a.rgb.cam2);
                 }
                 emit_rgb<MODE, VEC>(d_nm, ci, a.rgb,
@@ -682,7 +691,7 @@ static void march_geometry(int num_phi, int vec, int rows, int batch, int band_r
 
 template <typename T>
 cudaError_t launch_step(StepArgs<T> a, int batch, bool tfe, bool strict, bool has_top, bool has_bottom,
-                        int band_rows_req, cudaStream_t st, int *launches)
+                        int band_rows_req, bool use_tma, cudaStream_t st, int *launches)
 {
     constexpr int VECW = 16 / (int)sizeof(T);
     const bool vec_ok = (a.num_phi % VECW) == 0;
@@ -695,16 +704,27 @@ cudaError_t launch_step(StepArgs<T> a, int batch, bool tfe, bool strict, bool ha
     a.pole_slots = (int)grid.x;
     cudaError_t e = cudaSuccess;
     if (rows > 0) {
-        e = vec_ok ? launch_march_vec<T, VECW>(a, tfe, strict, grid, block, st)
-                   : launch_march_vec<T, 1>(a, tfe, strict, grid, block, st);
+        bool done = false;
+        if constexpr (sizeof(T) == 4) {
+            if (!strict && use_tma && march_tma_supported(a)) {
+                int slots = 0;
+                e = launch_march_tma(a, batch, tfe, band_rows_req, st, &slots);
+                a.pole_slots = slots;
+                done = true;
+            }
+        }
+        if (!done)
+            e = vec_ok ? launch_march_vec<T, VECW>(a, tfe, strict, grid, block, st)
+                       : launch_march_vec<T, 1>(a, tfe, strict, grid, block, st);
         if (e != cudaSuccess) return e;
         ++*launches;
     }
     if (has_top || has_bottom) {
-        const dim3 pg(2, (unsigned)batch);
+        const int bpp = (a.num_phi + 1023) / 1024;
+        const dim3 pg((unsigned)(2 * bpp), (unsigned)batch);
 #define SBX_POLES(MODE)                                                                         \
-    if (strict) { if constexpr (sizeof(T) == 8) k_poles<T, MODE, true><<<pg, 256, 0, st>>>(a, has_top, has_bottom); } \
-    else k_poles<T, MODE, false><<<pg, 256, 0, st>>>(a, has_top, has_bottom)
+    if (strict) { if constexpr (sizeof(T) == 8) k_poles<T, MODE, true><<<pg, 256, 0, st>>>(a, has_top, has_bottom, bpp); } \
+    else k_poles<T, MODE, false><<<pg, 256, 0, st>>>(a, has_top, has_bottom, bpp)
         switch (a.rgb.mode) {
         case SBX_RGB_NONE: SBX_POLES(SBX_RGB_NONE); break;
         case SBX_RGB_LUT: SBX_POLES(SBX_RGB_LUT); break;
@@ -721,8 +741,8 @@ cudaError_t launch_step(StepArgs<T> a, int batch, bool tfe, bool strict, bool ha
     return cudaSuccess;
 }
 
-template cudaError_t launch_step<float>(StepArgs<float>, int, bool, bool, bool, bool, int, cudaStream_t, int *);
-template cudaError_t launch_step<double>(StepArgs<double>, int, bool, bool, bool, bool, int, cudaStream_t, int *);
+template cudaError_t launch_step<float>(StepArgs<float>, int, bool, bool, bool, bool, int, bool, cudaStream_t, int *);
+template cudaError_t launch_step<double>(StepArgs<double>, int, bool, bool, bool, bool, int, bool, cudaStream_t, int *);
 
 template <typename T>
 cudaError_t launch_tfe_pass(T *buf, long long bubble_stride, int num_phi, int row_begin, int rows_local,

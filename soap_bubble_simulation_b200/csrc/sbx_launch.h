@@ -9,7 +9,11 @@ namespace sbx {
 // `launches` is incremented once per kernel launched.
 template <typename T>
 cudaError_t launch_step(StepArgs<T> a, int batch, bool tfe, bool strict, bool has_top, bool has_bottom,
-                        int band_rows_req, cudaStream_t st, int *launches);
+                        int band_rows_req, bool use_tma, cudaStream_t st, int *launches);
+
+// f32 fast path (sbx_march_tma.cu): TMA-staged ring, RGBA8 or no colour, num_phi % 4 == 0
+bool march_tma_supported(const StepArgs<float> &a);
+cudaError_t launch_march_tma(StepArgs<float> a, int batch, bool tfe, int band_rows_req, cudaStream_t st, int *pole_slots);
 
 template <typename T>
 cudaError_t launch_tfe_pass(T *buf, long long bubble_stride, int num_phi, int row_begin, int rows_local,

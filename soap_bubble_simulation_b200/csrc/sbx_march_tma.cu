@@ -1,0 +1,329 @@
+// sbx_march_tma.cu -- the f32 fast path of the fused drainage + interference step for sm_100a.
+//
+// Each CTA owns a strip of up to 4*C consecutive phi columns (C = consumer threads) and marches down a
+// band of theta rows.  A dedicated producer warp streams the strip's rows -- main segment plus a 4-float
+// halo on each side, wrapped across the periodic seam when the strip touches column 0 or num_phi-1 --
+// into a shared-memory ring with TMA bulk copies (cp.async.bulk, SASS UBLKCP) that complete on
+// mbarriers; the consumer warps pull each row out of the ring exactly once (one LDS.128 + two LDS.32
+// per thread), keep a three-row window in registers, and write h' and RGBA8 with 16-byte stores.
+// Compared with the direct-load kernel (k_march) this removes every global-load instruction, the warp
+// shuffles and the predicated edge loads from the instruction stream, which is what bounds the fused
+// step (profiles/: k_march is issue-slot bound at 77 instructions per cell).
+#include "sbx_device.cuh"
+#include "sbx_launch.h"
+
+namespace sbx {
+
+namespace {
+
+constexpr int kStages = 4;        // ring depth
+constexpr int kRowsPerStage = 2;  // theta rows per stage
+constexpr int kHalo = 4;          // floats each side (16 B keeps every bulk copy aligned)
+
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}" ::"r"(smem_u32(bar)),
+        "r"(parity)
+        : "memory");
+}
+// TMA bulk copy global -> shared; completion is counted in bytes on an mbarrier
+__device__ __forceinline__ void tma_bulk_g2s(void *dst_smem, const void *src_gmem, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                     smem_u32(dst_smem)),
+                 "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void bar_consumers(int nthreads)
+{
+    asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+
+struct Row {
+    float v[4];
+    float eL, eR;
+};
+
+// RGBA8 from three floats in [0,1]: the low mantissa byte of (255 x + 2^23) is round(255 x); the blue
+// channel's magic constant also plants 0xff in byte 1, which becomes alpha.  Two PRMTs gather the bytes.
+__device__ __forceinline__ uint32_t pack_rgba8_fast(float r, float g, float b)
+{
+    const uint32_t ur = __float_as_uint(fmaf(r, 255.f, 8388608.0f));
+    const uint32_t ug = __float_as_uint(fmaf(g, 255.f, 8388608.0f));
+    const uint32_t ub = __float_as_uint(fmaf(b, 255.f, 8453888.0f));  // 2^23 + 0xff00
+    const uint32_t rg = __byte_perm(ur, ug, 0x0040);                  // bytes: r, g, -, -
+    return __byte_perm(rg, ub, 0x5410);                               // bytes: r, g, b, 0xff
+}
+
+template <int MODE>
+__device__ __forceinline__ uint32_t shade_px(float h, float href, float href_u, float colA, float sin_th, float ccy,
+                                             float R, float camR2, const RgbArgs &rgb)
+{
+    const float nc = fmaf(sin_th, colA, ccy);      // n . cam
+    const float len2 = fmaf(-2.f * R, nc, camR2);  // |cam - R n|^2
+    if constexpr (MODE == SBX_RGB_LUT) {
+        // u = clamp(d_nm / max_nm), v = clamp(cos theta_i): bubble.wgsl:429-433
+        const float u = __saturatef(fmaf(h, rgb.nm_over_max, href_u));
+        const float v = __saturatef(fabsf(nc - R) * rsqrtf(len2));
+        const float4 t = tex2D<float4>(rgb.lut, u, v);
+        return pack_rgba8_fast(__saturatef(t.x * rgb.intensity), __saturatef(t.y * rgb.intensity),
+                               __saturatef(t.z * rgb.intensity));
+    } else {
+        const float ci = fabsf(nc - R) * rsqrtf(len2);
+        const double d_nm = ((double)h + (double)href) * 1e9;
+        float c[3];
+        rgb_eval<MODE>(d_nm, ci, rgb, c);
+        return pack_rgba8(c);
+    }
+}
+
+}  // namespace
+
+template <int MODE, bool TFE>
+__global__ void __launch_bounds__(288) k_march_tma(const StepArgs<float> a)
+{
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ double warp_part[8];
+    const int C = blockDim.x - 32;  // consumer threads
+    const int N = a.num_phi;
+    const int strip_w_max = 4 * C;
+    const int c0 = blockIdx.x * strip_w_max;
+    const int w = min(strip_w_max, N - c0);    // multiple of 4
+    const int rowf = strip_w_max + 2 * kHalo;  // floats per ring row
+    float *ring = reinterpret_cast<float *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStages * kRowsPerStage * rowf * sizeof(float));
+    uint64_t *empty = full + kStages;
+
+    const int b = blockIdx.z;
+    const float *in = a.in + (long long)b * a.bubble_stride;
+    const int l0 = a.l_first + blockIdx.y * a.band_rows;
+    const int l1 = min(l0 + a.band_rows - 1, a.l_last);
+    if (l0 > l1) return;
+    const int rows_load = (l1 - l0 + 1) + 2;  // local rows l0-1 .. l1+1
+    const int nchunks = (rows_load + kRowsPerStage - 1) / kRowsPerStage;
+    const int nwarps_c = C >> 5;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], nwarps_c);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (threadIdx.x >= C) {
+        // ------------------------------------------------------------ producer warp (one lane issues)
+        if (threadIdx.x == C) {
+            const bool wrapL = c0 == 0, wrapR = c0 + w >= N;
+            const uint32_t main_floats = (uint32_t)w + (wrapL ? 0 : kHalo) + (wrapR ? 0 : kHalo);
+            const uint32_t row_bytes = ((uint32_t)w + 2 * kHalo) * 4u;
+            for (int c = 0; c < nchunks; ++c) {
+                const int s = c % kStages;
+                if (c >= kStages) mbar_wait(&empty[s], (uint32_t)(((c / kStages) - 1) & 1));
+                const int r_begin = c * kRowsPerStage;
+                const int r_end = min(r_begin + kRowsPerStage, rows_load);
+                mbar_expect_tx(&full[s], row_bytes * (uint32_t)(r_end - r_begin));
+                for (int r = r_begin; r < r_end; ++r) {
+                    const float *grow_ptr = in + (long long)(l0 - 1 + r) * N;
+                    float *dst = ring + ((size_t)s * kRowsPerStage + (r - r_begin)) * rowf;
+                    // ring row layout: [0,4) left halo | [4, 4+w) main | [4+w, 8+w) right halo
+                    tma_bulk_g2s(dst + (wrapL ? kHalo : 0), grow_ptr + c0 - (wrapL ? 0 : kHalo), main_floats * 4u, &full[s]);
+                    if (wrapL) tma_bulk_g2s(dst, grow_ptr + (N - kHalo), kHalo * 4u, &full[s]);           // seam
+                    if (wrapR) tma_bulk_g2s(dst + kHalo + w, grow_ptr, kHalo * 4u, &full[s]);             // seam
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------------------------------------------------------- consumers
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int jloc = tid * 4;  // column offset inside the strip
+    const bool active = jloc < w;
+    const int jc = c0 + (active ? jloc : 0);
+    const int soff = kHalo + (active ? jloc : 0);  // float offset of this thread's packet in a ring row
+    float *out = a.out + (long long)b * a.bubble_stride;
+    const BubbleParam<float> bp = a.bub[b];
+    const float href = bp.h_ref;
+    const float neg_href = -href;
+    const float dscale = bp.diff_scale;
+    const float dt = a.dt;
+    const float crit = a.crit;
+
+    float colA[4] = {0.f, 0.f, 0.f, 0.f};
+    if constexpr (MODE != SBX_RGB_NONE) {
+        const float4 ca = __ldg(reinterpret_cast<const float4 *>(a.rgb.colA + jc));
+        colA[0] = ca.x; colA[1] = ca.y; colA[2] = ca.z; colA[3] = ca.w;
+    }
+    const float Rv = bp.radius;
+    const float camR2 = a.rgb.cam2 + Rv * Rv;
+    const float href_u = href * a.rgb.nm_over_max;
+
+    int row_in_chunk = 0, stage = 0;
+    uint32_t full_parity = 0;
+
+    auto load_row = [&](Row &r, int rows_loaded_after) {
+        if (row_in_chunk == 0) mbar_wait(&full[stage], full_parity);
+        const float *src = ring + ((size_t)stage * kRowsPerStage + row_in_chunk) * rowf + soff;
+        const float4 q = *reinterpret_cast<const float4 *>(src);
+        r.v[0] = q.x; r.v[1] = q.y; r.v[2] = q.z; r.v[3] = q.w;
+        r.eL = src[-1];
+        r.eR = src[4];
+        if (++row_in_chunk == kRowsPerStage || rows_loaded_after == rows_load) {
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&empty[stage]);  // every lane of this warp has read the stage
+            row_in_chunk = 0;
+            if (++stage == kStages) { stage = 0; full_parity ^= 1u; }
+        }
+    };
+
+    auto compute_row = [&](const Row &up, const Row &cur, const Row &dn, int l) {
+        const int grow = a.row_begin + (l - 1);
+        const float4 cf = __ldg(reinterpret_cast<const float4 *>(a.coefF) + grow);  // {A+B, A-B, E, G}
+        float nw[4];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            const float h = cur.v[k];
+            const float lf = k == 0 ? cur.eL : cur.v[k - 1];
+            const float rt = k == 3 ? cur.eR : cur.v[k + 1];
+            const float habs = h + href;
+            // A (dN + dS) + B (dN - dS) + E (dE + dW) with neighbour-minus-centre differences
+            float diff = cf.x * (dn.v[k] - h);
+            diff = fmaf(cf.y, up.v[k] - h, diff);
+            diff = fmaf(cf.z, (rt - h) + (lf - h), diff);
+            const float g3 = (cf.w * habs) * (habs * habs);
+            const float rate = fmaf(dscale, diff, -g3);
+            float hn = fmaf(dt, rate, h);
+            hn = fmaxf(hn, neg_href);      // max(h_abs, 0), drainage.rs:378
+            nw[k] = habs < crit ? h : hn;  // below-critical cells keep their value, drainage.rs:331-333
+        }
+        if (grow == 1 || grow == a.num_theta - 2) {  // block-uniform: ring sums for the poles (pre-TFE)
+            double s = 0.0;
+            if (active) s = ((double)nw[0] + (double)nw[1]) + ((double)nw[2] + (double)nw[3]);
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
+            if (lane == 0) warp_part[tid >> 5] = s;
+            bar_consumers(C);
+            if (tid == 0) {
+                double t = 0.0;
+                for (int i = 0; i < nwarps_c; ++i) t += warp_part[i];
+                double *pp = a.pole_partial + (long long)b * 2 * a.pole_slots;
+                if (grow == 1) pp[blockIdx.x] = t;
+                if (grow == a.num_theta - 2) pp[a.pole_slots + blockIdx.x] = t;
+            }
+            bar_consumers(C);
+        }
+        if constexpr (TFE) {
+            const unsigned rm = front_row_mask(a.fronts, grow);
+            if (rm) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    if (front_hit(a.fronts, rm, jc + k)) nw[k] = fmaf(-(nw[k] + href), a.tfe_rdt, nw[k]);
+            }
+        }
+        if (active) {
+            *reinterpret_cast<float4 *>(out + (long long)l * N + jc) = make_float4(nw[0], nw[1], nw[2], nw[3]);
+            if constexpr (MODE != SBX_RGB_NONE) {
+                const float2 sc = __ldg(a.rowSC + grow);
+                const float ccy = sc.y * a.rgb.cam_y;
+                uint32_t px[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    px[k] = shade_px<MODE>(nw[k], href, href_u, colA[k], sc.x, ccy, Rv, camR2, a.rgb);
+                uint32_t *o = reinterpret_cast<uint32_t *>(a.rgb.out) + (long long)b * a.rgb_bubble_stride +
+                              (long long)(l - 1) * N + jc;
+                *reinterpret_cast<uint4 *>(o) = make_uint4(px[0], px[1], px[2], px[3]);
+            }
+        }
+    };
+
+    Row r0, r1, r2;
+    int loaded = 0;
+    load_row(r0, ++loaded);
+    load_row(r1, ++loaded);
+    int l = l0;
+    // three sub-steps per trip so that the three-row window rotates by renaming instead of by moves
+    while (true) {
+        load_row(r2, ++loaded);
+        compute_row(r0, r1, r2, l);
+        if (++l > l1) break;
+        load_row(r0, ++loaded);
+        compute_row(r1, r2, r0, l);
+        if (++l > l1) break;
+        load_row(r1, ++loaded);
+        compute_row(r2, r0, r1, l);
+        if (++l > l1) break;
+    }
+}
+
+static size_t march_tma_smem_bytes(int consumers)
+{
+    return (size_t)kStages * kRowsPerStage * (4 * consumers + 2 * kHalo) * sizeof(float) + 2 * kStages * sizeof(uint64_t);
+}
+
+template <bool TFE>
+static cudaError_t launch_tma_mode(const StepArgs<float> &a, dim3 grid, dim3 block, size_t smem, cudaStream_t st)
+{
+    switch (a.rgb.mode) {
+    case SBX_RGB_NONE: k_march_tma<SBX_RGB_NONE, TFE><<<grid, block, smem, st>>>(a); break;
+    case SBX_RGB_LUT: k_march_tma<SBX_RGB_LUT, TFE><<<grid, block, smem, st>>>(a); break;
+    case SBX_RGB_EXACT3: k_march_tma<SBX_RGB_EXACT3, TFE><<<grid, block, smem, st>>>(a); break;
+    case SBX_RGB_EXACT3_LINEAR: k_march_tma<SBX_RGB_EXACT3_LINEAR, TFE><<<grid, block, smem, st>>>(a); break;
+    case SBX_RGB_SCHLICK_WALL: k_march_tma<SBX_RGB_SCHLICK_WALL, TFE><<<grid, block, smem, st>>>(a); break;
+    default: return cudaErrorInvalidValue;
+    }
+    return cudaGetLastError();
+}
+
+// The fast path handles: f32 storage, non-strict, RGBA8 output (or no colour), num_phi % 4 == 0.
+bool march_tma_supported(const StepArgs<float> &a)
+{
+    if (a.num_phi % 4 != 0 || a.num_phi < 128) return false;
+    if (a.rgb.mode != SBX_RGB_NONE && a.rgb.format != SBX_OUT_RGBA8) return false;
+    return true;
+}
+
+cudaError_t launch_march_tma(StepArgs<float> a, int batch, bool tfe, int band_rows_req, cudaStream_t st, int *pole_slots)
+{
+    const int rows = a.l_last - a.l_first + 1;
+    int consumers = 256;
+    while (consumers > 32 && consumers * 2 >= a.num_phi) consumers >>= 1;  // narrow grids: fewer, fuller CTAs
+    const int strip = consumers * 4;
+    const int gx = (a.num_phi + strip - 1) / strip;
+    int band_rows = band_rows_req > 0 ? band_rows_req : 64;
+    if (band_rows > rows) band_rows = rows;
+    const int gy = (rows + band_rows - 1) / band_rows;
+    a.band_rows = band_rows;
+    a.pole_slots = gx;
+    *pole_slots = gx;
+    const dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)batch), block((unsigned)(consumers + 32));
+    const size_t smem = march_tma_smem_bytes(consumers);
+    return tfe ? launch_tma_mode<true>(a, grid, block, smem, st) : launch_tma_mode<false>(a, grid, block, smem, st);
+}
+
+}  // namespace sbx

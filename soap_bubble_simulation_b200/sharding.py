@@ -1,0 +1,65 @@
+"""Latitude-band sharding across the GPUs of one box: one process per GPU, torch.distributed for the
+rendezvous, NCCL send/recv (inside libsbx) for the per-step halo rows.
+
+The sphere is cut into contiguous bands of theta rows; phi stays whole on every rank, so the periodic
+seam never crosses devices.  The pole rows and the rings whose mean they take live on the first and last
+rank.  TFE front state is a deterministic function of time and is replicated, not communicated.
+Independent foam bubbles shard by bubble index with no exchange at all (``bubble_range``).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import List, Tuple
+
+import numpy as np
+
+from . import _lib as L
+
+
+def band_partition(num_theta: int, world_size: int) -> List[Tuple[int, int]]:
+    """Row ranges [begin, end) per rank: as even as possible, every band >= 2 rows so that a pole row is
+    never separated from the ring next to it."""
+    if world_size < 1:
+        raise ValueError("world_size must be >= 1")
+    if num_theta < 2 * world_size or num_theta < 3:
+        raise ValueError(f"{num_theta} theta rows cannot be split into {world_size} bands of >= 2 rows")
+    base, rem = divmod(num_theta, world_size)
+    out, r0 = [], 0
+    for r in range(world_size):
+        n = base + (1 if r < rem else 0)
+        out.append((r0, r0 + n))
+        r0 += n
+    return out
+
+
+def bubble_range(num_bubbles: int, world_size: int, rank: int) -> Tuple[int, int]:
+    """Independent bubbles: contiguous slice of the batch for this rank (no data-path collective)."""
+    base, rem = divmod(num_bubbles, world_size)
+    b0 = rank * base + min(rank, rem)
+    return b0, b0 + base + (1 if rank < rem else 0)
+
+
+class Comm:
+    """sbx_comm: an NCCL communicator owned by libsbx.  The 128-byte unique id is created on rank 0 and
+    handed to the other ranks through torch.distributed (any backend: gloo on CPU hosts, nccl on GPUs)."""
+
+    def __init__(self, rank: int, world_size: int, device: int):
+        import torch
+        import torch.distributed as dist
+
+        self.rank, self.world_size = rank, world_size
+        ident = np.zeros(128, dtype=np.uint8)
+        if rank == 0:
+            L.check(L.lib().sbx_comm_unique_id(ident.ctypes.data))
+        if world_size > 1:
+            box = [ident.tobytes()]
+            dist.broadcast_object_list(box, src=0)
+            ident = np.frombuffer(box[0], dtype=np.uint8).copy()
+        self._c = C.c_void_p()
+        L.check(L.lib().sbx_comm_init(ident.ctypes.data, world_size, rank, device, C.byref(self._c)))
+        del torch
+
+    def close(self) -> None:
+        if self._c:
+            L.lib().sbx_comm_destroy(self._c)
+            self._c = C.c_void_p()

@@ -99,6 +99,7 @@ def lib() -> C.CDLL:
         "orc_fresnel_unpolarized": (f, [f, f, f, f]),
         "orc_lut_shade": (None, [p, i, i, f, f, f, f, C.POINTER(C.c_float)]),
         "orc_view_cos": (d, [d, d, d, dp]),
+        "orc_shade_field": (None, [p, i, i, i, i, d, dp, d, p, i, i, f, f, i, p, i]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -312,3 +313,18 @@ def wgsl_step(p: WgslParams, h: np.ndarray, c: np.ndarray):
     ho, co = np.empty_like(h), np.empty_like(c)
     lib().orc_wgsl_step(C.byref(p), h.ctypes.data, c.ctypes.data, ho.ctypes.data, co.ctypes.data)
     return ho, co
+
+
+def shade_field(h: np.ndarray, num_theta: int, row0: int, radius, cam, n_film=1.33, lut=None, intensity=4.0,
+                mode=1, threads=1, max_nm=2000.0) -> np.ndarray:
+    """Colour frame (rows, num_phi, 4) uint8 of the band h (rows, num_phi) starting at global row row0."""
+    h = np.ascontiguousarray(h, dtype=np.float64)
+    rows, nphi = h.shape
+    out = np.empty((rows, nphi, 4), dtype=np.uint8)
+    a = (C.c_double * 3)(*cam)
+    if lut is None:
+        lut = generate_interference_lut(n_film, 1.0)
+    A, T = lut.shape[0], lut.shape[1]
+    lib().orc_shade_field(h.ctypes.data, num_theta, nphi, row0, rows, radius, a, n_film, lut.ctypes.data, T, A,
+                          max_nm, intensity, mode, out.ctypes.data, threads)
+    return out

@@ -255,9 +255,10 @@ def test_batched_bubbles_match_independent_oracles(S):
             ora.data[:] = fields[b]
             ora.step(1e-3, 5)
             assert np.abs(got[b] / ora.data - 1).max() <= 5 * tol, (prec, b)
-        # uniform start with per-bubble reference (delta storage)
-        sim.step(1e-3, 3)
-        got = sim.download()
+        # uniform start with per-bubble reference (delta storage for f32)
+        fresh = make_sim(S, nt, nphi, prec, batch=B, batch_h0_m=h0, batch_radius_m=rad)
+        fresh.step(1e-3, 3)
+        got = fresh.download()
         for b in range(B):
             ora = O.OracleDrainage(nt, nphi, h0_m=h0[b], radius_m=rad[b])
             ora.step(1e-3, 3)
