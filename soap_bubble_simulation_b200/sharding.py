@@ -39,6 +39,23 @@ def bubble_range(num_bubbles: int, world_size: int, rank: int) -> Tuple[int, int
     return b0, b0 + base + (1 if rank < rem else 0)
 
 
+def halo_plan(rank: int, world_size: int, rows_local: int):
+    """The per-step exchange libsbx performs (sbx_comm_halo), in local-row terms: owned rows are 1..rows_local,
+    ghost rows 0 and rows_local+1.  Returns [(send_local_row, peer, recv_ghost_row)]: the row sent to `peer` and
+    the ghost row filled from the same peer."""
+    plan = []
+    if rank > 0:
+        plan.append((1, rank - 1, 0))
+    if rank < world_size - 1:
+        plan.append((rows_local, rank + 1, rows_local + 1))
+    return plan
+
+
+def owns_poles(row_begin: int, row_end: int, num_theta: int):
+    """(has_top, has_bottom): which pole rows -- and therefore which ring means -- this band computes."""
+    return row_begin == 0, row_end == num_theta
+
+
 class Comm:
     """sbx_comm: an NCCL communicator owned by libsbx.  The 128-byte unique id is created on rank 0 and
     handed to the other ranks through torch.distributed (any backend: gloo on CPU hosts, nccl on GPUs)."""

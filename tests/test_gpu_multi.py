@@ -1,0 +1,36 @@
+"""Multi-GPU parity (needs >= 2 CUDA devices on the box): latitude bands + NCCL halo rows vs the oracle."""
+import os
+import socket
+import subprocess
+import sys
+
+import pytest
+
+pytestmark = pytest.mark.gpu
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _ngpu():
+    import torch
+
+    return torch.cuda.device_count()
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("nt,nphi,steps,prec", [(64, 128, 120, 0), (64, 128, 140, 2), (61, 50, 30, 1), (256, 1024, 8, 0)])
+def test_sharded_matches_oracle(world, nt, nphi, steps, prec):
+    if _ngpu() < world:
+        pytest.skip(f"needs {world} GPUs")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
+           "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
+           os.path.join(HERE, "mgpu_worker.py"), str(nt), str(nphi), str(steps), str(prec)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    sys.stdout.write(r.stdout[-2000:])
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
+    assert "ok=True" in r.stdout
