@@ -16,8 +16,8 @@ namespace sbx {
 
 namespace {
 
-constexpr int kStages = 4;        // ring depth
-constexpr int kRowsPerStage = 2;  // theta rows per stage
+constexpr int kStages = 3;        // ring depth
+constexpr int kRowsPerStage = 3;  // theta rows per stage == the unroll of the three-row register window
 constexpr int kHalo = 4;          // floats each side (16 B keeps every bulk copy aligned)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -102,7 +102,7 @@ __device__ __forceinline__ uint32_t shade_px(float h, float href, float href_u, 
 }  // namespace
 
 template <int MODE, bool TFE>
-__global__ void __launch_bounds__(288) k_march_tma(const StepArgs<float> a)
+__global__ void __launch_bounds__(288, 4) k_march_tma(const StepArgs<float> a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double warp_part[8];
@@ -184,27 +184,42 @@ __global__ void __launch_bounds__(288) k_march_tma(const StepArgs<float> a)
     const float camR2 = a.rgb.cam2 + Rv * Rv;
     const float href_u = href * a.rgb.nm_over_max;
 
-    int row_in_chunk = 0, stage = 0;
+    // Ring bookkeeping is static: a stage holds exactly the three rows one trip of the unrolled loop pulls
+    // (sub-step A takes slot 2 and releases the stage, B waits for the next stage and takes slot 0, C takes
+    // slot 1), so no per-row counters or modulo arithmetic are needed.
+    int stage = 0;
     uint32_t full_parity = 0;
+    const float *ring_t = ring + soff;                 // this thread's packet in ring row 0
+    const uint32_t stage_floats = kRowsPerStage * rowf;
+    const float *stage_p = ring_t;                     // this thread's packet in slot 0 of the current stage
 
-    auto load_row = [&](Row &r, int rows_loaded_after) {
-        if (row_in_chunk == 0) mbar_wait(&full[stage], full_parity);
-        const float *src = ring + ((size_t)stage * kRowsPerStage + row_in_chunk) * rowf + soff;
+    auto load_slot = [&](Row &r, int slot) {
+        const float *src = stage_p + slot * rowf;
         const float4 q = *reinterpret_cast<const float4 *>(src);
         r.v[0] = q.x; r.v[1] = q.y; r.v[2] = q.z; r.v[3] = q.w;
         r.eL = src[-1];
         r.eR = src[4];
-        if (++row_in_chunk == kRowsPerStage || rows_loaded_after == rows_load) {
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&empty[stage]);  // every lane of this warp has read the stage
-            row_in_chunk = 0;
-            if (++stage == kStages) { stage = 0; full_parity ^= 1u; }
-        }
+    };
+    auto release_stage = [&]() {
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[stage]);  // every lane of this warp has read the stage
+        if (++stage == kStages) { stage = 0; full_parity ^= 1u; stage_p = ring_t; }
+        else stage_p += stage_floats;
     };
 
-    auto compute_row = [&](const Row &up, const Row &cur, const Row &dn, int l) {
-        const int grow = a.row_begin + (l - 1);
-        const float4 cf = __ldg(reinterpret_cast<const float4 *>(a.coefF) + grow);  // {A+B, A-B, E, G}
+    // running output pointers (bumped by one row per sub-step)
+    float *out_p = out + (long long)l0 * N + jc;
+    uint32_t *rgb_p = reinterpret_cast<uint32_t *>(a.rgb.out) + (long long)b * a.rgb_bubble_stride +
+                      (long long)(l0 - 1) * N + jc;
+    const float4 *cf_p = reinterpret_cast<const float4 *>(a.coefF) + (a.row_begin + l0 - 1);
+    const float2 *sc_p = a.rowSC + (a.row_begin + l0 - 1);
+    int grow = a.row_begin + l0 - 1;
+    const int ring_top = 1, ring_bot = a.num_theta - 2;
+    const bool has_ring = (grow <= ring_top && ring_top <= a.row_begin + l1 - 1) ||
+                          (grow <= ring_bot && ring_bot <= a.row_begin + l1 - 1);  // block-uniform
+
+    auto compute_row = [&](const Row &up, const Row &cur, const Row &dn) {
+        const float4 cf = __ldg(cf_p);  // {A+B, A-B, E, G}
         float nw[4];
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
@@ -222,7 +237,7 @@ __global__ void __launch_bounds__(288) k_march_tma(const StepArgs<float> a)
             hn = fmaxf(hn, neg_href);      // max(h_abs, 0), drainage.rs:378
             nw[k] = habs < crit ? h : hn;  // below-critical cells keep their value, drainage.rs:331-333
         }
-        if (grow == 1 || grow == a.num_theta - 2) {  // block-uniform: ring sums for the poles (pre-TFE)
+        if (has_ring && (grow == ring_top || grow == ring_bot)) {  // ring sums for the poles (pre-TFE)
             double s = 0.0;
             if (active) s = ((double)nw[0] + (double)nw[1]) + ((double)nw[2] + (double)nw[3]);
 #pragma unroll
@@ -233,8 +248,8 @@ __global__ void __launch_bounds__(288) k_march_tma(const StepArgs<float> a)
                 double t = 0.0;
                 for (int i = 0; i < nwarps_c; ++i) t += warp_part[i];
                 double *pp = a.pole_partial + (long long)b * 2 * a.pole_slots;
-                if (grow == 1) pp[blockIdx.x] = t;
-                if (grow == a.num_theta - 2) pp[a.pole_slots + blockIdx.x] = t;
+                if (grow == ring_top) pp[blockIdx.x] = t;
+                if (grow == ring_bot) pp[a.pole_slots + blockIdx.x] = t;
             }
             bar_consumers(C);
         }
@@ -247,37 +262,41 @@ __global__ void __launch_bounds__(288) k_march_tma(const StepArgs<float> a)
             }
         }
         if (active) {
-            *reinterpret_cast<float4 *>(out + (long long)l * N + jc) = make_float4(nw[0], nw[1], nw[2], nw[3]);
+            *reinterpret_cast<float4 *>(out_p) = make_float4(nw[0], nw[1], nw[2], nw[3]);
             if constexpr (MODE != SBX_RGB_NONE) {
-                const float2 sc = __ldg(a.rowSC + grow);
+                const float2 sc = __ldg(sc_p);
                 const float ccy = sc.y * a.rgb.cam_y;
                 uint32_t px[4];
 #pragma unroll
                 for (int k = 0; k < 4; ++k)
                     px[k] = shade_px<MODE>(nw[k], href, href_u, colA[k], sc.x, ccy, Rv, camR2, a.rgb);
-                uint32_t *o = reinterpret_cast<uint32_t *>(a.rgb.out) + (long long)b * a.rgb_bubble_stride +
-                              (long long)(l - 1) * N + jc;
-                *reinterpret_cast<uint4 *>(o) = make_uint4(px[0], px[1], px[2], px[3]);
+                *reinterpret_cast<uint4 *>(rgb_p) = make_uint4(px[0], px[1], px[2], px[3]);
             }
         }
+        out_p += N;
+        rgb_p += N;
+        ++cf_p;
+        ++sc_p;
+        ++grow;
     };
 
     Row r0, r1, r2;
-    int loaded = 0;
-    load_row(r0, ++loaded);
-    load_row(r1, ++loaded);
-    int l = l0;
-    // three sub-steps per trip so that the three-row window rotates by renaming instead of by moves
+    mbar_wait(&full[0], 0);
+    load_slot(r0, 0);
+    load_slot(r1, 1);
+    int left = l1 - l0 + 1;  // rows still to compute
     while (true) {
-        load_row(r2, ++loaded);
-        compute_row(r0, r1, r2, l);
-        if (++l > l1) break;
-        load_row(r0, ++loaded);
-        compute_row(r1, r2, r0, l);
-        if (++l > l1) break;
-        load_row(r1, ++loaded);
-        compute_row(r2, r0, r1, l);
-        if (++l > l1) break;
+        load_slot(r2, 2);
+        release_stage();
+        compute_row(r0, r1, r2);
+        if (--left == 0) break;
+        mbar_wait(&full[stage], full_parity);
+        load_slot(r0, 0);
+        compute_row(r1, r2, r0);
+        if (--left == 0) break;
+        load_slot(r1, 1);
+        compute_row(r2, r0, r1);
+        if (--left == 0) break;
     }
 }
 
@@ -286,18 +305,34 @@ static size_t march_tma_smem_bytes(int consumers)
     return (size_t)kStages * kRowsPerStage * (4 * consumers + 2 * kHalo) * sizeof(float) + 2 * kStages * sizeof(uint64_t);
 }
 
+template <int MODE, bool TFE>
+static cudaError_t launch_one(const StepArgs<float> &a, dim3 grid, dim3 block, size_t smem, cudaStream_t st)
+{
+    // ask for the large shared-memory carveout once per device so that four 37 KB rings fit on an SM
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_march_tma<MODE, TFE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                             (int)cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    k_march_tma<MODE, TFE><<<grid, block, smem, st>>>(a);
+    return cudaGetLastError();
+}
+
 template <bool TFE>
 static cudaError_t launch_tma_mode(const StepArgs<float> &a, dim3 grid, dim3 block, size_t smem, cudaStream_t st)
 {
     switch (a.rgb.mode) {
-    case SBX_RGB_NONE: k_march_tma<SBX_RGB_NONE, TFE><<<grid, block, smem, st>>>(a); break;
-    case SBX_RGB_LUT: k_march_tma<SBX_RGB_LUT, TFE><<<grid, block, smem, st>>>(a); break;
-    case SBX_RGB_EXACT3: k_march_tma<SBX_RGB_EXACT3, TFE><<<grid, block, smem, st>>>(a); break;
-    case SBX_RGB_EXACT3_LINEAR: k_march_tma<SBX_RGB_EXACT3_LINEAR, TFE><<<grid, block, smem, st>>>(a); break;
-    case SBX_RGB_SCHLICK_WALL: k_march_tma<SBX_RGB_SCHLICK_WALL, TFE><<<grid, block, smem, st>>>(a); break;
+    case SBX_RGB_NONE: return launch_one<SBX_RGB_NONE, TFE>(a, grid, block, smem, st);
+    case SBX_RGB_LUT: return launch_one<SBX_RGB_LUT, TFE>(a, grid, block, smem, st);
+    case SBX_RGB_EXACT3: return launch_one<SBX_RGB_EXACT3, TFE>(a, grid, block, smem, st);
+    case SBX_RGB_EXACT3_LINEAR: return launch_one<SBX_RGB_EXACT3_LINEAR, TFE>(a, grid, block, smem, st);
+    case SBX_RGB_SCHLICK_WALL: return launch_one<SBX_RGB_SCHLICK_WALL, TFE>(a, grid, block, smem, st);
     default: return cudaErrorInvalidValue;
     }
-    return cudaGetLastError();
 }
 
 // The fast path handles: f32 storage, non-strict, RGBA8 output (or no colour), num_phi % 4 == 0.
@@ -315,7 +350,7 @@ cudaError_t launch_march_tma(StepArgs<float> a, int batch, bool tfe, int band_ro
     while (consumers > 32 && consumers * 2 >= a.num_phi) consumers >>= 1;  // narrow grids: fewer, fuller CTAs
     const int strip = consumers * 4;
     const int gx = (a.num_phi + strip - 1) / strip;
-    int band_rows = band_rows_req > 0 ? band_rows_req : 64;
+    int band_rows = band_rows_req > 0 ? band_rows_req : 24;  // multiple of the 3-row ring stage; measured best at 8192x16384
     if (band_rows > rows) band_rows = rows;
     const int gy = (rows + band_rows - 1) / band_rows;
     a.band_rows = band_rows;
