@@ -1,0 +1,106 @@
+//! Safe wrappers with the exact signatures of the reference's hot-path types, so that
+//! `src/physics/drainage.rs`, `src/render/gpu_drainage.rs` and `src/render/interference_lut.rs` can be
+//! replaced file-for-file.  Source only -- not compiled in this repository's image.
+use crate::config::SimulationConfig;
+use crate::sbx_sys::*;
+use std::cell::{Cell, RefCell};
+use std::ffi::CStr;
+
+fn check(rc: i32) {
+    // the reference hot path is infallible; a CUDA failure is treated like the OOB-index panic it has today
+    if rc != 0 {
+        let msg = unsafe { CStr::from_ptr(sbx_last_error()) }.to_string_lossy().into_owned();
+        panic!("libsbx error {rc}: {msg}");
+    }
+}
+
+/// Host mirror of the device field (drainage.rs:96-204); refreshed lazily by `thickness_field()`.
+#[derive(Debug, Clone)]
+pub struct ThicknessField { num_theta: usize, num_phi: usize, data: Vec<f64>, delta_theta: f64, delta_phi: f64 }
+
+impl ThicknessField {
+    pub fn new(num_theta: usize, num_phi: usize, initial_thickness: f64) -> Self {
+        Self { num_theta, num_phi, data: vec![initial_thickness; num_theta * num_phi],
+               delta_theta: std::f64::consts::PI / (num_theta - 1) as f64,
+               delta_phi: 2.0 * std::f64::consts::PI / num_phi as f64 }
+    }
+    #[inline] pub fn get(&self, t: usize, p: usize) -> f64 { self.data[t * self.num_phi + p] }
+    #[inline] pub fn set(&mut self, t: usize, p: usize, v: f64) { self.data[t * self.num_phi + p] = v; }
+    #[inline] pub fn theta_at(&self, t: usize) -> f64 { t as f64 * self.delta_theta }
+    #[inline] pub fn phi_at(&self, p: usize) -> f64 { p as f64 * self.delta_phi }
+    pub fn num_theta(&self) -> usize { self.num_theta }
+    pub fn num_phi(&self) -> usize { self.num_phi }
+    pub fn delta_theta(&self) -> f64 { self.delta_theta }
+    pub fn delta_phi(&self) -> f64 { self.delta_phi }
+    pub fn min_thickness(&self) -> f64 { self.data.iter().copied().fold(f64::INFINITY, f64::min) }
+    pub fn max_thickness(&self) -> f64 { self.data.iter().copied().fold(f64::NEG_INFINITY, f64::max) }
+    pub fn data(&self) -> &[f64] { &self.data }
+    pub fn data_mut(&mut self) -> &mut [f64] { &mut self.data }
+}
+
+/// DrainageSimulator (drainage.rs:212-614) over libsbx.
+pub struct DrainageSimulator { h: *mut sbx_drainage, mirror: RefCell<ThicknessField>, stale: Cell<bool> }
+
+impl DrainageSimulator {
+    pub fn new(config: &SimulationConfig) -> Self {
+        let mut cfg = unsafe { std::mem::zeroed::<sbx_drainage_cfg>() };
+        check(unsafe { sbx_drainage_cfg_default(&mut cfg) });
+        cfg.num_theta = config.resolution as i32;
+        cfg.num_phi = config.resolution as i32 * 2;
+        cfg.h0_m = config.film_thickness_meters();
+        cfg.density = config.fluid.density;
+        cfg.gravity = config.environment.gravity;
+        cfg.viscosity = config.fluid.viscosity;
+        cfg.diffusion = config.fluid.surfactant_diffusion;
+        cfg.critical_thickness_m = config.bubble.critical_thickness_nm * 1e-9;
+        cfg.radius_m = config.bubble_radius();
+        cfg.precision = SBX_PREC_F32;
+        cfg.h_ref_m = cfg.h0_m;
+        let mut h = std::ptr::null_mut();
+        check(unsafe { sbx_drainage_create(&cfg, 0, &mut h) });
+        let mirror = ThicknessField::new(cfg.num_theta as usize, cfg.num_phi as usize, cfg.h0_m);
+        Self { h, mirror: RefCell::new(mirror), stale: Cell::new(true) }
+    }
+    pub fn step(&mut self, dt: f64) { check(unsafe { sbx_drainage_step(self.h, dt, 1) }); self.stale.set(true); }
+    pub fn get_thickness(&self, theta: f64, phi: f64) -> f64 {
+        let mut out = 0.0;
+        check(unsafe { sbx_drainage_get_thickness(self.h, 0, theta, phi, &mut out) });
+        out
+    }
+    /// `&ThicknessField` has to be host memory: download on demand (this is why sbx_drainage_download exists).
+    pub fn thickness_field(&self) -> std::cell::Ref<'_, ThicknessField> {
+        if self.stale.get() {
+            let mut m = self.mirror.borrow_mut();
+            check(unsafe { sbx_drainage_download(self.h, m.data_mut().as_mut_ptr() as *mut _, SBX_F64) });
+            self.stale.set(false);
+        }
+        self.mirror.borrow()
+    }
+    /// device-side reductions for the two folds `RenderPipeline::update` does every frame (pipeline.rs:1298-1300)
+    pub fn min_max_thickness(&self) -> (f64, f64) {
+        let (mut a, mut b) = (0.0, 0.0);
+        check(unsafe { sbx_drainage_minmax(self.h, &mut a, &mut b) });
+        (a, b)
+    }
+    pub fn current_time(&self) -> f64 { let mut t = 0.0; check(unsafe { sbx_drainage_current_time(self.h, &mut t) }); t }
+    pub fn has_critical_region(&self) -> bool { let mut f = 0; check(unsafe { sbx_drainage_has_critical(self.h, &mut f) }); f != 0 }
+    pub fn critical_thickness(&self) -> f64 { let mut t = 0.0; check(unsafe { sbx_drainage_critical_thickness(self.h, &mut t) }); t }
+    pub fn reset(&mut self, initial_thickness: f64) { check(unsafe { sbx_drainage_reset(self.h, initial_thickness) }); self.stale.set(true); }
+    pub fn set_marginal_regeneration(&mut self, enabled: bool) { check(unsafe { sbx_drainage_set_marginal_regeneration(self.h, enabled as i32) }); }
+    pub fn marginal_regeneration_enabled(&self) -> bool { let mut f = 0; check(unsafe { sbx_drainage_marginal_regeneration(self.h, &mut f) }); f != 0 }
+    pub fn set_tfe_thickness_ratio(&mut self, ratio: f64) { check(unsafe { sbx_drainage_set_tfe_ratio(self.h, ratio) }); }
+    pub fn tfe_thickness_ratio(&self) -> f64 { let mut r = 0.0; check(unsafe { sbx_drainage_tfe_ratio(self.h, &mut r) }); r }
+    pub fn active_tfe_count(&self) -> usize { let mut n = 0; check(unsafe { sbx_drainage_active_tfe_count(self.h, &mut n) }); n as usize }
+}
+
+impl Drop for DrainageSimulator { fn drop(&mut self) { unsafe { sbx_drainage_destroy(self.h) }; } }
+
+/// generate_interference_lut (interference_lut.rs:18-41)
+pub const LUT_THICKNESS_SAMPLES: u32 = 256;
+pub const LUT_ANGLE_SAMPLES: u32 = 64;
+pub const LUT_MAX_THICKNESS_NM: f32 = 2000.0;
+pub fn generate_interference_lut(refractive_index: f32, intensity: f32) -> Vec<u8> {
+    let mut data = vec![0u8; (LUT_THICKNESS_SAMPLES * LUT_ANGLE_SAMPLES * 4) as usize];
+    check(unsafe { sbx_lut_build(refractive_index, intensity, data.as_mut_ptr(), 0) });
+    data
+}

@@ -1,0 +1,67 @@
+//! Raw FFI of libsbx (include/sbx.h).  Source only: this image has no Rust toolchain, so this file is not
+//! compiled here; it is what `bindgen include/sbx.h` produces, trimmed to the entry points the shim uses.
+#![allow(non_camel_case_types)]
+use std::os::raw::{c_char, c_void};
+
+#[repr(C)]
+#[derive(Debug, Clone, Copy)]
+pub struct sbx_drainage_params {
+    pub dt: f32, pub gravity: f32, pub viscosity: f32, pub density: f32, pub diffusion_coeff: f32,
+    pub bubble_radius: f32, pub critical_thickness: f32, pub grid_width: u32, pub grid_height: u32,
+    pub marangoni_enabled: u32, pub gamma_air: f32, pub gamma_reduction: f32,
+    pub surfactant_diffusion: f32, pub marangoni_coeff: f32, pub _padding1: u32, pub _padding2: u32,
+}
+
+#[repr(C)]
+pub struct sbx_drainage_cfg {
+    pub num_theta: i32, pub num_phi: i32, pub batch: i32,
+    pub h0_m: f64, pub density: f64, pub gravity: f64, pub viscosity: f64, pub diffusion: f64,
+    pub critical_thickness_m: f64, pub radius_m: f64,
+    pub semantics: i32, pub precision: i32, pub h_ref_m: f64,
+    pub tfe_enabled: i32, pub tfe_ratio: f64,
+    pub row_begin: i32, pub row_end: i32,
+    pub batch_h0_m: *const f64, pub batch_radius_m: *const f64,
+    pub wgsl: sbx_drainage_params,
+}
+
+#[repr(C)]
+pub struct sbx_view { pub cam_pos: [f64; 3], pub n_film: f64, pub intensity: f32, pub mode: i32, pub format: i32 }
+
+pub enum sbx_drainage {}
+
+pub const SBX_SEM_CPU: i32 = 0;
+pub const SBX_SEM_WGSL: i32 = 1;
+pub const SBX_PREC_F32: i32 = 0;
+pub const SBX_PREC_F64: i32 = 1;
+pub const SBX_PREC_F64_STRICT: i32 = 2;
+pub const SBX_F32: i32 = 0;
+pub const SBX_F64: i32 = 1;
+pub const SBX_PTR_THICKNESS: i32 = 0;
+pub const SBX_PTR_CONCENTRATION: i32 = 1;
+
+extern "C" {
+    pub fn sbx_last_error() -> *const c_char;
+    pub fn sbx_drainage_cfg_default(cfg: *mut sbx_drainage_cfg) -> i32;
+    pub fn sbx_drainage_create(cfg: *const sbx_drainage_cfg, device: i32, out: *mut *mut sbx_drainage) -> i32;
+    pub fn sbx_drainage_destroy(h: *mut sbx_drainage) -> i32;
+    pub fn sbx_drainage_upload(h: *mut sbx_drainage, host: *const c_void, dtype: i32) -> i32;
+    pub fn sbx_drainage_download(h: *mut sbx_drainage, host: *mut c_void, dtype: i32) -> i32;
+    pub fn sbx_drainage_step(h: *mut sbx_drainage, dt: f64, nsteps: i32) -> i32;
+    pub fn sbx_drainage_step_fused(h: *mut sbx_drainage, dt: f64, nsteps: i32, view: *const sbx_view) -> i32;
+    pub fn sbx_drainage_get_thickness(h: *mut sbx_drainage, bubble: i32, theta: f64, phi: f64, out: *mut f64) -> i32;
+    pub fn sbx_drainage_minmax(h: *mut sbx_drainage, min_out: *mut f64, max_out: *mut f64) -> i32;
+    pub fn sbx_drainage_has_critical(h: *mut sbx_drainage, out: *mut i32) -> i32;
+    pub fn sbx_drainage_critical_thickness(h: *mut sbx_drainage, out: *mut f64) -> i32;
+    pub fn sbx_drainage_current_time(h: *mut sbx_drainage, out: *mut f64) -> i32;
+    pub fn sbx_drainage_reset(h: *mut sbx_drainage, h0_m: f64) -> i32;
+    pub fn sbx_drainage_set_marginal_regeneration(h: *mut sbx_drainage, enabled: i32) -> i32;
+    pub fn sbx_drainage_marginal_regeneration(h: *mut sbx_drainage, out: *mut i32) -> i32;
+    pub fn sbx_drainage_set_tfe_ratio(h: *mut sbx_drainage, ratio: f64) -> i32;
+    pub fn sbx_drainage_tfe_ratio(h: *mut sbx_drainage, out: *mut f64) -> i32;
+    pub fn sbx_drainage_active_tfe_count(h: *mut sbx_drainage, out: *mut i32) -> i32;
+    pub fn sbx_drainage_update_params(h: *mut sbx_drainage, p: *const sbx_drainage_params) -> i32;
+    pub fn sbx_drainage_device_ptr(h: *mut sbx_drainage, kind: i32, out: *mut *mut c_void) -> i32;
+    pub fn sbx_lut_build(refractive_index: f32, intensity: f32, out65536: *mut u8, device: i32) -> i32;
+    pub fn sbx_interference_eval(n_film: f64, wavelengths_nm: *const f64, d_nm: *const f64, cos_i: *const f64,
+                                 n: usize, gamma: i32, rgb_out: *mut f64, device: i32) -> i32;
+}
