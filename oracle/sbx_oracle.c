@@ -649,9 +649,13 @@ void orc_generate_interference_lut(float n_film, float intensity, uint8_t *out)
 }
 
 /* bubble.wgsl:425-439 + sampler at pipeline.rs:350-359 (linear, clamp-to-edge, Rgba8Unorm).
- * Texel-centre addressing: texel i covers [i, i+1)/N, its centre is (i+0.5)/N. */
-void orc_lut_shade(const uint8_t *lut, int T, int A, float max_nm, float d_nm, float cos_theta,
-                   float intensity, float rgb[3])
+ * Texel-centre addressing: texel i covers [i, i+1)/N, its centre is (i+0.5)/N.
+ * weight_bits = 0: ideal bilinear weights in f32.  weight_bits = 8: the weights are rounded to 8 fractional
+ * bits first, which is what GPU texture units do (CUDA Programming Guide, "Texture Fetching": 9-bit fixed
+ * point with 8 bits of fractional value; Vulkan only guarantees subTexelPrecisionBits) -- i.e. what the
+ * reference's textureSample actually evaluates on hardware. */
+void orc_lut_shade_w(const uint8_t *lut, int T, int A, float max_nm, float d_nm, float cos_theta,
+                     float intensity, int weight_bits, float rgb[3])
 {
     float u = d_nm / max_nm;
     u = u < 0.f ? 0.f : (u > 1.f ? 1.f : u);
@@ -659,6 +663,11 @@ void orc_lut_shade(const uint8_t *lut, int T, int A, float max_nm, float d_nm, f
     float x = u * (float)T - 0.5f, y = v * (float)A - 0.5f;
     float fx0 = floorf(x), fy0 = floorf(y);
     float wx = x - fx0, wy = y - fy0;
+    if (weight_bits > 0) {
+        const float q = (float)(1 << weight_bits);
+        wx = floorf(wx * q + 0.5f) / q;
+        wy = floorf(wy * q + 0.5f) / q;
+    }
     int x0 = (int)fx0, y0 = (int)fy0, x1 = x0 + 1, y1 = y0 + 1;
     if (x0 < 0) x0 = 0;
     if (y0 < 0) y0 = 0;
@@ -669,11 +678,23 @@ void orc_lut_shade(const uint8_t *lut, int T, int A, float max_nm, float d_nm, f
         float t10 = (float)lut[4 * ((size_t)y0 * (size_t)T + (size_t)x1) + (size_t)k] / 255.0f;
         float t01 = (float)lut[4 * ((size_t)y1 * (size_t)T + (size_t)x0) + (size_t)k] / 255.0f;
         float t11 = (float)lut[4 * ((size_t)y1 * (size_t)T + (size_t)x1) + (size_t)k] / 255.0f;
-        float top = t00 + (t10 - t00) * wx;
-        float bot = t01 + (t11 - t01) * wx;
-        float c = (top + (bot - top) * wy) * intensity;
+        float c;
+        if (weight_bits > 0) {
+            c = (1.f - wx) * (1.f - wy) * t00 + wx * (1.f - wy) * t10 + (1.f - wx) * wy * t01 + wx * wy * t11;
+        } else {
+            float top = t00 + (t10 - t00) * wx;
+            float bot = t01 + (t11 - t01) * wx;
+            c = top + (bot - top) * wy;
+        }
+        c *= intensity;
         rgb[k] = c < 0.f ? 0.f : (c > 1.f ? 1.f : c);
     }
+}
+
+void orc_lut_shade(const uint8_t *lut, int T, int A, float max_nm, float d_nm, float cos_theta,
+                   float intensity, float rgb[3])
+{
+    orc_lut_shade_w(lut, T, A, max_nm, d_nm, cos_theta, intensity, 0, rgb);
 }
 
 double orc_view_cos(double theta, double phi, double radius, const double cam[3])
@@ -713,9 +734,9 @@ void orc_shade_field(const double *h, int num_theta, int num_phi, int row0, int 
             const double c = fabs((v[0] * n[0] + v[1] * n[1] + v[2] * n[2]) / len);
             const double d_nm = h[idx] * 1e9;
             double rgb[3];
-            if (mode == 1) {
+            if (mode == 1 || mode == 4) {
                 float f[3];
-                orc_lut_shade(lut, T, A, max_nm, (float)d_nm, (float)c, intensity, f);
+                orc_lut_shade_w(lut, T, A, max_nm, (float)d_nm, (float)c, intensity, mode == 4 ? 8 : 0, f);
                 rgb[0] = f[0]; rgb[1] = f[1]; rgb[2] = f[2];
             } else if (mode == 2) {
                 orc_interference_color(&ic, d_nm, c, rgb);

@@ -138,6 +138,9 @@ float orc_fresnel_unpolarized(float cos_i, float cos_t, float n1, float n2);   /
  * RGBA8-unorm T x A LUT at uv = (d/max_nm, cos), times intensity, clamped to [0,1]. */
 void orc_lut_shade(const uint8_t *lut_rgba, int T, int A, float max_nm, float d_nm, float cos_theta,
                    float intensity, float rgb[3]);
+/* the same with the bilinear weights rounded to `weight_bits` fractional bits (8 = GPU texture units) */
+void orc_lut_shade_w(const uint8_t *lut_rgba, int T, int A, float max_nm, float d_nm, float cos_theta,
+                     float intensity, int weight_bits, float rgb[3]);
 
 /* view cosine for cell (theta,phi) of a sphere of radius R seen from camera position cam:
  * n = (sin th cos ph, cos th, sin th sin ph) (src/physics/geometry.rs:184-186), world = R n,
@@ -145,7 +148,7 @@ void orc_lut_shade(const uint8_t *lut_rgba, int T, int A, float max_nm, float d_
 double orc_view_cos(double theta, double phi, double radius, const double cam[3]);
 
 /* Colour frame of a whole thickness field (row-major [theta][phi], metres), the CPU counterpart of the
- * fused colour stage: per cell view cosine as orc_view_cos, then mode 1 = orc_lut_shade (bubble.wgsl:425-439)
+ * fused colour stage: per cell view cosine as orc_view_cos, then mode 1 = orc_lut_shade (bubble.wgsl:425-439; mode 4 = the same with 8-bit filter weights)
  * or mode 2/3 = orc_interference_color / _linear (interference.rs:380-426); RGBA8 via round(255 x), A=255
  * (interference.rs:73-79).  row0/num_rows select a band of the global grid; OpenMP over rows. */
 void orc_shade_field(const double *h, int num_theta, int num_phi, int row0, int num_rows, double radius,

@@ -98,6 +98,7 @@ def lib() -> C.CDLL:
         "orc_snells_law": (f, [f, f]),
         "orc_fresnel_unpolarized": (f, [f, f, f, f]),
         "orc_lut_shade": (None, [p, i, i, f, f, f, f, C.POINTER(C.c_float)]),
+        "orc_lut_shade_w": (None, [p, i, i, f, f, f, f, i, C.POINTER(C.c_float)]),
         "orc_view_cos": (d, [d, d, d, dp]),
         "orc_shade_field": (None, [p, i, i, i, i, d, dp, d, p, i, i, f, f, i, p, i]),
     }
@@ -287,10 +288,11 @@ def schlick_wall_rgb(d_nm, cos_i, n=1.33):
     return tuple(o)
 
 
-def lut_shade(lut: np.ndarray, d_nm, cos_theta, intensity=4.0, max_nm=2000.0):
+def lut_shade(lut: np.ndarray, d_nm, cos_theta, intensity=4.0, max_nm=2000.0, weight_bits=0):
+    """weight_bits=0: ideal f32 bilinear; 8: weights rounded to 8 fractional bits like a GPU texture unit."""
     A, T = lut.shape[0], lut.shape[1]
     o = (C.c_float * 3)()
-    lib().orc_lut_shade(lut.ctypes.data, T, A, max_nm, d_nm, cos_theta, intensity, o)
+    lib().orc_lut_shade_w(lut.ctypes.data, T, A, max_nm, d_nm, cos_theta, intensity, weight_bits, o)
     return tuple(o)
 
 

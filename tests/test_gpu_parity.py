@@ -405,7 +405,8 @@ def test_fused_lut_rgba8_within_one_lsb(S):
     ref = np.empty((nt, nphi, 3))
     for i in range(nt):
         for j in range(nphi):
-            ref[i, j] = O.lut_shade(lut, float(np.float32(ora.data[i, j] * 1e9)), float(np.float32(cos[i, j])), 4.0)
+            ref[i, j] = O.lut_shade(lut, float(np.float32(ora.data[i, j] * 1e9)), float(np.float32(cos[i, j])), 4.0,
+                                    weight_bits=8)  # texture-unit filtering, as the reference's textureSample
     ref8 = np.floor(ref * 255.0 + 0.5)
     diff = np.abs(px[..., :3].astype(int) - ref8)
     print(f"\n[lut-shade] max diff {diff.max()} LSB, {np.count_nonzero(diff)} of {diff.size} channels differ")
