@@ -90,6 +90,9 @@ struct sbx_drainage {
     long long total_elems = 0;
 
     cudaStream_t own_stream = nullptr, stream = nullptr;
+    cudaStream_t copy_in = nullptr, copy_out = nullptr;  // host-pipelined step: H2D / D2H engines
+    std::vector<cudaEvent_t> ev_in, ev_comp;
+    cudaEvent_t ev_start = nullptr, ev_out = nullptr;
     void *buf[2] = {nullptr, nullptr};   // thickness ping-pong
     float *conc[2] = {nullptr, nullptr}; // WGSL concentration ping-pong
     int cur = 0;
@@ -171,6 +174,12 @@ static void free_all(sbx_drainage *h)
     if (h->lut_tex) cudaDestroyTextureObject(h->lut_tex);
     if (h->lut_array) cudaFreeArray(h->lut_array);
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
+    if (h->copy_in) cudaStreamDestroy(h->copy_in);
+    if (h->copy_out) cudaStreamDestroy(h->copy_out);
+    for (auto e : h->ev_in) cudaEventDestroy(e);
+    for (auto e : h->ev_comp) cudaEventDestroy(e);
+    if (h->ev_start) cudaEventDestroy(h->ev_start);
+    if (h->ev_out) cudaEventDestroy(h->ev_out);
     delete h;
 }
 
@@ -933,12 +942,91 @@ extern "C" int32_t sbx_drainage_download_rgb(sbx_drainage *h, void *host)
     return SBX_OK;
 }
 
+// One fused step with host buffers, pipelined over latitude chunks so that the H2D copy of chunk c+1, the
+// kernels of chunk c and the D2H copies of chunk c-1 overlap (three streams, both copy engines busy: the step is
+// PCIe-bound, so the round trip costs max(H2D, D2H) instead of their sum).  f32 in/out, CPU semantics, one
+// bubble, whole or banded sphere without a communicator.
+static int32_t step_host_pipelined(sbx_drainage *h, double dt, const sbx_view *view, const float *host_in,
+                                   float *host_out_h, void *host_out_rgb)
+{
+    int32_t rc = ensure_tables(h);
+    if (rc != SBX_OK) return rc;
+    RgbArgs rgb;
+    rc = prepare_rgb(h, view, rgb);
+    if (rc != SBX_OK) return rc;
+    const int N = h->num_phi, rows = h->rows_local;
+    const int chunk_rows = 504;  // ~32 MiB at 16384 columns; a multiple of the kernel's 24-row bands
+    const int nchunks = (rows + chunk_rows - 1) / chunk_rows;
+    if (!h->copy_in) {
+        CU(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
+    }
+    while ((int)h->ev_in.size() < nchunks) {
+        cudaEvent_t a, b;
+        CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        h->ev_in.push_back(a);
+        h->ev_comp.push_back(b);
+    }
+    FrontTable ft;
+    memset(&ft, 0, sizeof ft);
+    ft.row_min = 1; ft.row_max = 0;
+    if (h->tfe_enabled) { tfe_advance(h, dt); tfe_table(h, ft); }
+    StepArgs<float> a;
+    fill_step_args<float>(h, a, dt, rgb);
+    a.fronts = ft;
+    const int l_first = a.l_first, l_last = a.l_last;
+    float *in = tbuf<float>(h, h->cur), *out = tbuf<float>(h, 1 - h->cur);
+    const size_t px = rgb.mode == SBX_RGB_NONE ? 0 : (rgb.format == SBX_OUT_RGBA8 ? 4 : 12);
+    // everything queued on the handle's stream so far must be visible to the copy streams
+    CU(cudaEventRecord(h->ev_start, h->stream));
+    CU(cudaStreamWaitEvent(h->copy_in, h->ev_start, 0));
+    CU(cudaStreamWaitEvent(h->copy_out, h->ev_start, 0));
+    for (int c = 0; c < nchunks; ++c) {
+        const int r0 = c * chunk_rows, r1 = std::min(rows, r0 + chunk_rows);  // owned rows [r0, r1)
+        CU(cudaMemcpyAsync(in + (size_t)(r0 + 1) * N, host_in + (size_t)r0 * N, (size_t)(r1 - r0) * N * 4,
+                           cudaMemcpyHostToDevice, h->copy_in));
+        CU(cudaEventRecord(h->ev_in[c], h->copy_in));
+    }
+    int n = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        const int r0 = c * chunk_rows, r1 = std::min(rows, r0 + chunk_rows);
+        CU(cudaStreamWaitEvent(h->stream, h->ev_in[std::min(c + 1, nchunks - 1)], 0));  // needs the row below too
+        StepArgs<float> ac = a;
+        ac.l_first = std::max(l_first, r0 + 1);
+        ac.l_last = std::min(l_last, r1);
+        const bool top = c == 0 && h->row_begin == 0, bottom = c == nchunks - 1 && h->row_end == h->num_theta;
+        CU(launch_step<float>(ac, 1, ft.count > 0, false, top, bottom, h->band_rows, h->use_tma, h->stream, &n));
+        CU(cudaEventRecord(h->ev_comp[c], h->stream));
+        CU(cudaStreamWaitEvent(h->copy_out, h->ev_comp[c], 0));
+        if (host_out_rgb && px)
+            CU(cudaMemcpyAsync((char *)host_out_rgb + (size_t)r0 * N * px, (char *)h->rgb_buf + (size_t)r0 * N * px,
+                               (size_t)(r1 - r0) * N * px, cudaMemcpyDeviceToHost, h->copy_out));
+        if (host_out_h)
+            CU(cudaMemcpyAsync(host_out_h + (size_t)r0 * N, out + (size_t)(r0 + 1) * N, (size_t)(r1 - r0) * N * 4,
+                               cudaMemcpyDeviceToHost, h->copy_out));
+    }
+    h->launches += n;
+    h->cur = 1 - h->cur;
+    h->time += dt;
+    CU(cudaEventRecord(h->ev_out, h->copy_out));
+    CU(cudaStreamWaitEvent(h->stream, h->ev_out, 0));
+    CU(cudaStreamSynchronize(h->stream));
+    return SBX_OK;
+}
+
 extern "C" int32_t sbx_drainage_step_host(sbx_drainage *h, double dt, int32_t nsteps, const sbx_view *view,
                                           const void *host_in, int32_t in_dtype, void *host_out_h, int32_t out_dtype,
                                           void *host_out_rgb)
 {
     CHECK_H(h);
     int32_t rc = SBX_OK;
+    if (host_in && nsteps == 1 && !h->wgsl && !h->f64 && h->batch == 1 && !h->comm && h->href_zero &&
+        in_dtype == SBX_F32 && (!host_out_h || out_dtype == SBX_F32) && h->num_phi % 4 == 0 && h->rows_local >= 8 &&
+        !getenv("SBX_NO_HOST_PIPELINE"))
+        return step_host_pipelined(h, dt, view, (const float *)host_in, (float *)host_out_h, host_out_rgb);
     if (host_in) rc = sbx_drainage_upload(h, host_in, in_dtype);
     if (rc != SBX_OK) return rc;
     rc = do_steps(h, dt, nsteps, view);

@@ -448,3 +448,31 @@ def test_errors_are_reported_not_fatal(S):
         sim.upload(np.zeros((3, 3)))
     with pytest.raises(S.SbxError):
         sim.download_rgb()
+
+
+def test_step_host_pipelined_equals_separate_calls(S, monkeypatch):
+    """sbx_drainage_step_host (chunk-pipelined H2D / kernels / D2H) against upload + step_fused + download."""
+    nt, nphi = 1300, 256  # three 504-row chunks
+    f = synthetic_field(nt, nphi, dtype=np.float32)
+    dt = 0.25 * dt_max(nt, nphi)
+    view = S.View(mode=S.RGB_LUT, format=S.OUT_RGBA8)
+    ref = make_sim(S, nt, nphi, S.PREC_F32, h_ref=0.0)
+    out_h = np.empty((1, nt, nphi), np.float32)
+    out_px = np.empty((1, nt, nphi, 4), np.uint8)
+    sim = make_sim(S, nt, nphi, S.PREC_F32, h_ref=0.0)
+    cur = f[None].copy()
+    for step in range(3):
+        ref.upload(cur)
+        ref.step_fused(dt, view, 1)
+        want_h, want_px = ref.download(np.float32), ref.download_rgb()
+        sim.step_host(dt, 1, view, cur, out_h, out_px)
+        assert np.array_equal(out_h, want_h), step
+        assert np.array_equal(out_px, want_px), step
+        cur = want_h.copy()
+    assert sim.current_time() == ref.current_time()
+    # the non-pipelined fallback (f64 host buffers) gives the same field
+    sim64 = make_sim(S, nt, nphi, S.PREC_F32, h_ref=0.0)
+    o64 = np.empty((1, nt, nphi), np.float64)
+    sim64.step_host(dt, 1, view, f[None].astype(np.float64), o64, out_px)
+    sim.step_host(dt, 1, view, f[None].copy(), out_h, None)
+    assert np.array_equal(o64.astype(np.float32), out_h)
