@@ -118,12 +118,20 @@ __device__ __forceinline__ bool front_hit(const FrontTable &ft, unsigned rowmask
 // ------------------------------------------------------------------ colour stage (f32)
 __device__ __forceinline__ float clamp01(float x) { return fminf(fmaxf(x, 0.f), 1.f); }
 
+// 1/sqrt(x) on the SFU without the denormal pre/post-scaling rsqrtf() adds (|cam - R n|^2 is never denormal)
+__device__ __forceinline__ float rsqrt_approx(float x)
+{
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // cos(theta_i) = |n.(c - R n)| / |c - R n| with n.c = sin(th) A_j + cos(th) c_y
 __device__ __forceinline__ float view_cos(float sin_th, float cos_th_cy, float colA, float R, float cam2)
 {
     const float nc = fmaf(sin_th, colA, cos_th_cy);
     const float len2 = fmaf(-2.f * R, nc, cam2 + R * R);
-    return fabsf(nc - R) * rsqrtf(len2);
+    return fabsf(nc - R) * rsqrt_approx(len2);
 }
 
 // approximate SFU ops (1-2 ulp), one MUFU each

@@ -86,12 +86,12 @@ __device__ __forceinline__ uint32_t shade_px(float h, float href, float href_u, 
     if constexpr (MODE == SBX_RGB_LUT) {
         // u = clamp(d_nm / max_nm), v = clamp(cos theta_i): bubble.wgsl:429-433
         const float u = __saturatef(fmaf(h, rgb.nm_over_max, href_u));
-        const float v = __saturatef(fabsf(nc - R) * rsqrtf(len2));
+        const float v = __saturatef(fabsf(nc - R) * rsqrt_approx(len2));
         const float4 t = tex2D<float4>(rgb.lut, u, v);
         return pack_rgba8_fast(__saturatef(t.x * rgb.intensity), __saturatef(t.y * rgb.intensity),
                                __saturatef(t.z * rgb.intensity));
     } else {
-        const float ci = fabsf(nc - R) * rsqrtf(len2);
+        const float ci = fabsf(nc - R) * rsqrt_approx(len2);
         const double d_nm = ((double)h + (double)href) * 1e9;
         float c[3];
         rgb_eval<MODE>(d_nm, ci, rgb, c);
