@@ -23,8 +23,15 @@ import time
 
 import numpy as np
 
-# NCCL prints its version banner to stdout; this script's stdout carries exactly one JSON line
-os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
+# This script's stdout carries exactly one JSON line.  C libraries (NCCL's version banner) write to fd 1 too,
+# so fd 1 is pointed at stderr for the whole run and the JSON line goes to a saved copy of the real stdout.
+_REAL_STDOUT = os.dup(1)
+os.dup2(2, 1)
+
+
+def emit(line: dict) -> None:
+    os.write(_REAL_STDOUT, (json.dumps(line) + "\n").encode())
+
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
@@ -180,7 +187,7 @@ def run_reference(args):
         "e2e": {"value": val, "unit": "Gcell/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def main():
@@ -194,6 +201,8 @@ def main():
     ap.add_argument("--phi", type=int, default=NUM_PHI)
     ap.add_argument("--e2e-steps", type=int, default=5)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
+                    help="multi-GPU halo rows: in-kernel peer-memory push (default) or NCCL send/recv per step")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -245,6 +254,8 @@ def main():
     if world > 1:
         comm = Comm(rank, world, local_rank)
         sim.attach_comm(comm)
+        if args.halo == "peer":
+            comm.enable_peer_halo(sim)
 
     stream = torch.cuda.Stream()  # a real (non-null) stream so that torch's events see libsbx's launches
     torch.cuda.set_stream(stream)
@@ -322,7 +333,8 @@ def main():
                    "grid_per_gpu": [rows, nphi], "semantics": "cpu (DrainageSimulator::step) + TFE fronts",
                    "precision": "f32 storage, h_ref=0", "dt": dt,
                    "l2": f"inputs larger than L2 ({cells_local * 4 >> 20} MiB field per GPU vs 126 MB L2)",
-                   "halo_exchange": "nccl send/recv per step" if world > 1 else "none"},
+                   "halo_exchange": ("none" if world == 1 else "in-kernel peer-memory push over NVLink"
+                                     if args.halo == "peer" else "nccl send/recv per step")},
         "clocks": clocks,
         "e2e": e2e,
         "gpu_launches": int(launches),
@@ -338,7 +350,7 @@ def main():
         line["cpu_baseline"] = {"value": val, "unit": "Gcell/s", "cores": threads, "kind": "port",
                                 "sample": f"512x{NUM_PHI} grid, {cb_steps} fused steps, {sec:.2f} s/step (C restatement "
                                           "of DrainageSimulator::step f64 + LUT shading, OpenMP over rows)"}
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 

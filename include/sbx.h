@@ -249,6 +249,17 @@ int32_t sbx_comm_destroy(sbx_comm *c);
 /* attach a communicator to a sharded handle: every step then exchanges one halo row with the
  * latitude-band neighbours (rank-1 above, rank+1 below) */
 int32_t sbx_drainage_attach_comm(sbx_drainage *h, sbx_comm *c);
+/* Peer-memory halo push (all ranks on one NVLink/NVSwitch box).  Each rank exports a descriptor of its field
+ * buffers (CUDA IPC handles), the caller moves the blobs between processes (torch.distributed), and attach maps
+ * the neighbours' buffers.  From then on the f32 fast-path step stores each band's boundary rows directly into
+ * the neighbours' ghost rows from inside the stencil kernel and orders neighbouring steps with two flags in
+ * device memory -- no per-step collective.  Requires an attached communicator (used for the exchanges after
+ * upload/reset and for the precisions the fast path does not cover).  up/down = blob of rank-1 / rank+1 or NULL. */
+#define SBX_IPC_BYTES 256
+int32_t sbx_drainage_ipc_export(sbx_drainage *h, uint8_t out[SBX_IPC_BYTES]);
+int32_t sbx_drainage_ipc_attach(sbx_drainage *h, const uint8_t *up, const uint8_t *down);
+/* 0 = ok, 1 = a neighbour wait timed out during some step since the last query */
+int32_t sbx_drainage_peer_status(sbx_drainage *h, int32_t *out);
 /* global min/max over all ranks' bands */
 int32_t sbx_drainage_minmax_global(sbx_drainage *h, double *min_out, double *max_out);
 

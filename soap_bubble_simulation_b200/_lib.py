@@ -20,6 +20,7 @@ F32, F64 = 0, 1
 RGB_NONE, RGB_LUT, RGB_EXACT3, RGB_EXACT3_LINEAR, RGB_SCHLICK_WALL = 0, 1, 2, 3, 4
 OUT_RGBA8, OUT_RGB_F32 = 0, 1
 PTR_THICKNESS, PTR_CONCENTRATION, PTR_RGB = 0, 1, 2
+IPC_BYTES = 256
 
 
 class SbxError(RuntimeError):
@@ -112,6 +113,9 @@ _SIGS = {
     "sbx_comm_destroy": [C.c_void_p],
     "sbx_drainage_attach_comm": [C.c_void_p, C.c_void_p],
     "sbx_drainage_minmax_global": [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)],
+    "sbx_drainage_ipc_export": [C.c_void_p, C.c_void_p],
+    "sbx_drainage_ipc_attach": [C.c_void_p, C.c_void_p, C.c_void_p],
+    "sbx_drainage_peer_status": [C.c_void_p, C.POINTER(C.c_int32)],
 }
 
 EXPORTED_SYMBOLS = ["sbx_last_error"] + list(_SIGS)

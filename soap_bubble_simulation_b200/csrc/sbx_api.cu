@@ -142,6 +142,13 @@ struct sbx_drainage {
     bool lut_user = false;
 
     sbx_comm *comm = nullptr;
+    // peer-memory halo push
+    bool peer_enabled = false;
+    unsigned long long *sync_dev = nullptr;  // [0] flag from up, [1] flag from down, [2],[3] band counters, [4] status
+    void *peer_up_buf[2] = {nullptr, nullptr}, *peer_dn_buf[2] = {nullptr, nullptr};
+    unsigned long long *peer_up_sync = nullptr, *peer_dn_sync = nullptr;
+    int peer_up_rows = 0;
+    unsigned long long epoch = 0;
     int band_rows = 0;
     int64_t launches = 0;
 };
@@ -169,6 +176,13 @@ static void free_all(sbx_drainage *h)
     cudaFree(h->rgb_buf);
     cudaFree(h->colA);
     cudaFree(h->href_dev);
+    for (int i = 0; i < 2; ++i) {
+        if (h->peer_up_buf[i]) cudaIpcCloseMemHandle(h->peer_up_buf[i]);
+        if (h->peer_dn_buf[i]) cudaIpcCloseMemHandle(h->peer_dn_buf[i]);
+    }
+    if (h->peer_up_sync) cudaIpcCloseMemHandle(h->peer_up_sync);
+    if (h->peer_dn_sync) cudaIpcCloseMemHandle(h->peer_dn_sync);
+    cudaFree(h->sync_dev);
     if (h->mm_host) cudaFreeHost(h->mm_host);
     if (h->scalar_host) cudaFreeHost(h->scalar_host);
     if (h->lut_tex) cudaDestroyTextureObject(h->lut_tex);
@@ -411,6 +425,8 @@ extern "C" int32_t sbx_drainage_create(const sbx_drainage_cfg *cfg, int32_t devi
     CU_H(cudaHostAlloc(&h->scalar_host, 8 * sizeof(double), cudaHostAllocDefault));
     CU_H(cudaMalloc(&h->colA, (size_t)h->num_phi * sizeof(float)));
     CU_H(cudaMalloc(&h->href_dev, (size_t)h->batch * sizeof(double)));
+    CU_H(cudaMalloc(&h->sync_dev, 8 * sizeof(unsigned long long)));
+    CU_H(cudaMemset(h->sync_dev, 0, 8 * sizeof(unsigned long long)));
     CU_H(cudaMemcpy(h->href_dev, h->b_href.data(), (size_t)h->batch * sizeof(double), cudaMemcpyHostToDevice));
 #undef CU_H
 
@@ -828,8 +844,35 @@ static int32_t step_cpu_sem(sbx_drainage *h, double dt, const RgbArgs &rgb)
         }
     } else {
         a.fronts = ft;
+        bool pushed = false;
+        if constexpr (sizeof(T) == 4) {
+            if (h->peer_enabled && h->use_tma && march_tma_supported(a)) {
+                PeerArgs &p = a.peer;
+                p.enabled = 1;
+                p.epoch = ++h->epoch;
+                const size_t N = (size_t)h->num_phi;
+                const int o = 1 - h->cur;  // every rank writes the same ping-pong half in the same step
+                p.up_ghost = h->peer_up_buf[o] ? (float *)h->peer_up_buf[o] + (size_t)(h->peer_up_rows + 1) * N : nullptr;
+                p.dn_ghost = h->peer_dn_buf[o] ? (float *)h->peer_dn_buf[o] : nullptr;
+                p.up_flag_remote = h->peer_up_sync ? h->peer_up_sync + 1 : nullptr;  // I am its lower neighbour
+                p.dn_flag_remote = h->peer_dn_sync ? h->peer_dn_sync + 0 : nullptr;  // I am its upper neighbour
+                p.flag_from_up = h->sync_dev + 0;
+                p.flag_from_dn = h->sync_dev + 1;
+                p.done_first = (unsigned int *)(h->sync_dev + 2);
+                p.done_last = (unsigned int *)(h->sync_dev + 3);
+                p.status = (unsigned int *)(h->sync_dev + 4);
+                p.push_up_grow = p.up_ghost ? h->row_begin : -1;
+                p.push_dn_grow = p.dn_ghost ? h->row_end - 1 : -1;
+                pushed = true;
+            }
+        }
         CU(launch_step<T>(a, h->batch, ft.count > 0, false, has_top, has_bottom, h->band_rows, h->use_tma, h->stream, &n));
         h->cur = 1 - h->cur;
+        if (pushed) {
+            h->launches += n;
+            h->time += dt;
+            return SBX_OK;  // ghost rows were filled by the neighbours' kernels
+        }
     }
     h->launches += n;
     h->time += dt;  // drainage.rs:391
@@ -1367,6 +1410,72 @@ extern "C" int32_t sbx_drainage_attach_comm(sbx_drainage *h, sbx_comm *c)
     CHECK_H(h);
     h->comm = c;
     return halo_exchange(h);
+}
+
+struct IpcBlob {
+    cudaIpcMemHandle_t buf[2];
+    cudaIpcMemHandle_t sync;
+    int32_t rows_local, num_phi, esz, magic;
+};
+static_assert(sizeof(IpcBlob) <= SBX_IPC_BYTES, "IPC blob too large");
+
+extern "C" int32_t sbx_drainage_ipc_export(sbx_drainage *h, uint8_t out[SBX_IPC_BYTES])
+{
+    CHECK_H(h);
+    if (!out) return fail(SBX_ERR_INVALID, "out is null");
+    IpcBlob b;
+    memset(&b, 0, sizeof b);
+    CU(cudaIpcGetMemHandle(&b.buf[0], h->buf[0]));
+    CU(cudaIpcGetMemHandle(&b.buf[1], h->buf[1]));
+    CU(cudaIpcGetMemHandle(&b.sync, h->sync_dev));
+    b.rows_local = h->rows_local;
+    b.num_phi = h->num_phi;
+    b.esz = (int32_t)h->esz;
+    b.magic = 0x53425831;
+    memset(out, 0, SBX_IPC_BYTES);
+    memcpy(out, &b, sizeof b);
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_ipc_attach(sbx_drainage *h, const uint8_t *up, const uint8_t *down)
+{
+    CHECK_H(h);
+    if (!h->comm) return fail(SBX_ERR_INVALID, "attach a communicator first (sbx_drainage_attach_comm)");
+    if (h->wgsl || h->f64 || h->batch != 1) return fail(SBX_ERR_UNSUPPORTED, "peer halo push covers the f32 CPU-semantics fast path, one bubble");
+    if ((up == nullptr) != (h->row_begin == 0) || (down == nullptr) != (h->row_end == h->num_theta))
+        return fail(SBX_ERR_INVALID, "neighbour blobs do not match this band's position");
+    auto open_one = [&](const uint8_t *blob, void *bufs[2], unsigned long long **sync, int *rows) -> int32_t {
+        IpcBlob b;
+        memcpy(&b, blob, sizeof b);
+        if (b.magic != 0x53425831 || b.num_phi != h->num_phi || b.esz != (int32_t)h->esz)
+            return fail(SBX_ERR_INVALID, "neighbour blob is not a matching libsbx band");
+        for (int i = 0; i < 2; ++i) CU(cudaIpcOpenMemHandle(&bufs[i], b.buf[i], cudaIpcMemLazyEnablePeerAccess));
+        void *s = nullptr;
+        CU(cudaIpcOpenMemHandle(&s, b.sync, cudaIpcMemLazyEnablePeerAccess));
+        *sync = (unsigned long long *)s;
+        if (rows) *rows = b.rows_local;
+        return SBX_OK;
+    };
+    int32_t rc = SBX_OK;
+    if (up) rc = open_one(up, h->peer_up_buf, &h->peer_up_sync, &h->peer_up_rows);
+    if (rc == SBX_OK && down) rc = open_one(down, h->peer_dn_buf, &h->peer_dn_sync, nullptr);
+    if (rc != SBX_OK) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    h->peer_enabled = true;
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_peer_status(sbx_drainage *h, int32_t *out)
+{
+    CHECK_H(h);
+    if (!out) return fail(SBX_ERR_INVALID, "out is null");
+    unsigned long long v = 0;
+    CU(cudaMemcpyAsync(h->scalar_host, h->sync_dev + 4, sizeof v, cudaMemcpyDeviceToHost, h->stream));
+    CU(cudaStreamSynchronize(h->stream));
+    memcpy(&v, h->scalar_host, sizeof v);
+    *out = v ? 1 : 0;
+    if (v) CU(cudaMemsetAsync(h->sync_dev + 4, 0, sizeof v, h->stream));
+    return SBX_OK;
 }
 
 extern "C" int32_t sbx_drainage_minmax_global(sbx_drainage *h, double *min_out, double *max_out)

@@ -51,6 +51,23 @@ struct RgbArgs {
     double two_n_over_wl[3];  // 2 n / lambda_k at 650, 532, 450 nm (interference.rs:26-30)
 };
 
+// Peer-memory halo push (latitude-band sharding, one process per GPU): the CTAs that update a band's first /
+// last owned row store it straight into the neighbour's ghost row over NVLink, and the neighbours order
+// their steps with two monotonic flags instead of a collective.  See sbx_march_tma.cu.
+struct PeerArgs {
+    float *up_ghost;                           // up neighbour's OUT buffer, its bottom ghost row (nullptr: none)
+    float *dn_ghost;                           // down neighbour's OUT buffer, its top ghost row (nullptr: none)
+    unsigned long long *up_flag_remote;        // up neighbour's "my lower neighbour finished step e" word
+    unsigned long long *dn_flag_remote;        // down neighbour's "my upper neighbour finished step e" word
+    const unsigned long long *flag_from_up;    // mine: written by the up neighbour
+    const unsigned long long *flag_from_dn;    // mine: written by the down neighbour
+    unsigned int *done_first, *done_last;      // CTA counters of my first / last band
+    unsigned int *status;                      // != 0: a wait timed out
+    unsigned long long epoch;                  // number of this step, >= 1
+    int push_up_grow, push_dn_grow;            // global row whose new values go to the up / down neighbour (-1: none)
+    int enabled;
+};
+
 // arguments of one drainage step (CPU semantics)
 template <typename T>
 struct StepArgs {
@@ -75,6 +92,7 @@ struct StepArgs {
     double s_drain_coef, s_dth2, s_two_dth, s_dph2, s_r2, s_D, s_dt, s_crit, s_tfe_factor;
     FrontTable fronts;
     RgbArgs rgb;
+    PeerArgs peer;
 };
 
 // arguments of one WGSL-semantics dispatch

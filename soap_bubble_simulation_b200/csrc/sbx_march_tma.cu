@@ -61,6 +61,36 @@ __device__ __forceinline__ void bar_consumers(int nthreads)
     asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
 }
 
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// wait until a neighbour has finished the previous step (bounded: a dead neighbour must not hang the GPU)
+__device__ __forceinline__ void wait_neighbour(const unsigned long long *flag, unsigned long long want, unsigned int *status)
+{
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_acquire_sys(flag) < want) {
+        if (globaltimer_ns() - t0 > 5000000000ull) {  // 5 s
+            atomicExch(status, 1u);
+            break;
+        }
+        __nanosleep(64);
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");  // the rows the neighbour pushed are read by TMA next
+}
+
 struct Row {
     float v[4];
     float eL, eR;
@@ -138,6 +168,8 @@ __global__ void __launch_bounds__(288, 4) k_march_tma(const StepArgs<float> a)
     if (threadIdx.x >= C) {
         // ------------------------------------------------------------ producer warp (one lane issues)
         if (threadIdx.x == C) {
+            const bool touch_top = a.peer.enabled && a.peer.up_ghost && l0 == 1;
+            const bool touch_bot = a.peer.enabled && a.peer.dn_ghost && l1 == a.l_last && a.peer.push_dn_grow >= 0;
             const bool wrapL = c0 == 0, wrapR = c0 + w >= N;
             const uint32_t main_floats = (uint32_t)w + (wrapL ? 0 : kHalo) + (wrapR ? 0 : kHalo);
             const uint32_t row_bytes = ((uint32_t)w + 2 * kHalo) * 4u;
@@ -148,6 +180,9 @@ __global__ void __launch_bounds__(288, 4) k_march_tma(const StepArgs<float> a)
                 const int r_end = min(r_begin + kRowsPerStage, rows_load);
                 mbar_expect_tx(&full[s], row_bytes * (uint32_t)(r_end - r_begin));
                 for (int r = r_begin; r < r_end; ++r) {
+                    // ghost rows are written by the neighbours' previous step: wait for it before reading them
+                    if (r == 0 && touch_top) wait_neighbour(a.peer.flag_from_up, a.peer.epoch - 1, a.peer.status);
+                    if (r == rows_load - 1 && touch_bot) wait_neighbour(a.peer.flag_from_dn, a.peer.epoch - 1, a.peer.status);
                     const float *grow_ptr = in + (long long)(l0 - 1 + r) * N;
                     float *dst = ring + ((size_t)s * kRowsPerStage + (r - r_begin)) * rowf;
                     // ring row layout: [0,4) left halo | [4, 4+w) main | [4+w, 8+w) right halo
@@ -263,6 +298,12 @@ __global__ void __launch_bounds__(288, 4) k_march_tma(const StepArgs<float> a)
         }
         if (active) {
             *reinterpret_cast<float4 *>(out_p) = make_float4(nw[0], nw[1], nw[2], nw[3]);
+            if (a.peer.enabled) {  // boundary rows also land in the neighbours' ghost rows (peer stores over NVLink)
+                if (grow == a.peer.push_up_grow)
+                    *reinterpret_cast<float4 *>(a.peer.up_ghost + jc) = make_float4(nw[0], nw[1], nw[2], nw[3]);
+                if (grow == a.peer.push_dn_grow)
+                    *reinterpret_cast<float4 *>(a.peer.dn_ghost + jc) = make_float4(nw[0], nw[1], nw[2], nw[3]);
+            }
             if constexpr (MODE != SBX_RGB_NONE) {
                 const float2 sc = __ldg(sc_p);
                 const float ccy = sc.y * a.rgb.cam_y;
@@ -297,6 +338,27 @@ __global__ void __launch_bounds__(288, 4) k_march_tma(const StepArgs<float> a)
         load_slot(r1, 1);
         compute_row(r2, r0, r1);
         if (--left == 0) break;
+    }
+
+    if (a.peer.enabled) {
+        // when every CTA of my first (last) band is done -- ghost row consumed, boundary row pushed -- tell the up
+        // (down) neighbour that this step is finished here
+        const bool sig_up = a.peer.up_ghost && l0 == 1;
+        const bool sig_dn = a.peer.dn_ghost && l1 == a.l_last && a.peer.push_dn_grow >= 0;
+        if (sig_up || sig_dn) {
+            __threadfence_system();
+            bar_consumers(C);
+            if (tid == 0) {
+                if (sig_up && atomicAdd(a.peer.done_first, 1u) == gridDim.x - 1) {
+                    *a.peer.done_first = 0u;
+                    st_release_sys(a.peer.up_flag_remote, a.peer.epoch);
+                }
+                if (sig_dn && atomicAdd(a.peer.done_last, 1u) == gridDim.x - 1) {
+                    *a.peer.done_last = 0u;
+                    st_release_sys(a.peer.dn_flag_remote, a.peer.epoch);
+                }
+            }
+        }
     }
 }
 

@@ -76,6 +76,32 @@ class Comm:
         L.check(L.lib().sbx_comm_init(ident.ctypes.data, world_size, rank, device, C.byref(self._c)))
         del torch
 
+    def enable_peer_halo(self, sim) -> None:
+        """Switch `sim` (already attached to this communicator) from per-step NCCL send/recv to the in-kernel
+        peer-memory halo push: exchange CUDA IPC descriptors of the field buffers with the two latitude
+        neighbours and map them (sbx_drainage_ipc_export / _attach)."""
+        import torch.distributed as dist
+
+        blob = np.zeros(L.IPC_BYTES, dtype=np.uint8)
+        L.check(L.lib().sbx_drainage_ipc_export(sim._h, blob.ctypes.data))
+        blobs = [None] * self.world_size
+        if self.world_size > 1:
+            dist.all_gather_object(blobs, blob.tobytes())
+        else:
+            blobs[0] = blob.tobytes()
+        up = np.frombuffer(blobs[self.rank - 1], dtype=np.uint8).copy() if self.rank > 0 else None
+        dn = np.frombuffer(blobs[self.rank + 1], dtype=np.uint8).copy() if self.rank < self.world_size - 1 else None
+        L.check(L.lib().sbx_drainage_ipc_attach(sim._h, up.ctypes.data if up is not None else None,
+                                                dn.ctypes.data if dn is not None else None))
+        if self.world_size > 1:
+            dist.barrier()  # nobody steps before every neighbour has mapped every buffer
+
+    @staticmethod
+    def peer_status(sim) -> int:
+        out = C.c_int32()
+        L.check(L.lib().sbx_drainage_peer_status(sim._h, C.byref(out)))
+        return out.value
+
     def close(self) -> None:
         if self._c:
             L.lib().sbx_comm_destroy(self._c)

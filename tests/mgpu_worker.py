@@ -19,6 +19,7 @@ from synth import dt_max, synthetic_field  # noqa: E402
 
 def main():
     nt, nphi, steps, prec = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
+    halo = sys.argv[5] if len(sys.argv) > 5 else "nccl"
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
@@ -31,6 +32,8 @@ def main():
     sim.upload(band)
     comm = Comm(rank, world, local)
     sim.attach_comm(comm)
+    if halo == "peer":
+        comm.enable_peer_halo(sim)
     dt = min(5e-3, 0.25 * dt_max(nt, nphi))  # 5 ms steps reach the first TFE front (t = 0.5 s) quickly
     view = S.View(mode=S.RGB_LUT, format=S.OUT_RGBA8)
     sim.step(dt, steps - 1)
@@ -38,8 +41,9 @@ def main():
     got = sim.download()[0]
     px = sim.download_rgb()[0]
     mn, mx = sim.minmax_global()
+    peer_bad = Comm.peer_status(sim) if halo == "peer" else 0
     gathered = [None] * world
-    dist.all_gather_object(gathered, (rb, re, got, px, sim.fronts()))
+    dist.all_gather_object(gathered, (rb, re, got, px, sim.fronts(), peer_bad))
     ok = True
     if rank == 0:
         full = np.concatenate([g[2] for g in gathered])
@@ -56,12 +60,12 @@ def main():
         else:
             err = float(np.abs(full / ora.data - 1).max())
             ok = err <= (1e-5 if prec == S.PREC_F32 else 1e-12)  # f32: ~6e-8 per step accumulates
-        ok = ok and gathered[0][4] == ora.fronts()
+        ok = ok and gathered[0][4] == ora.fronts() and not any(g[5] for g in gathered)
         ok = ok and abs(mn - ora.min_thickness()) <= 1e-5 * mn and abs(mx - ora.max_thickness()) <= 1e-5 * mx
         ref = O.shade_field(ora.data, nt, 0, 0.025, view.cam_pos, intensity=4.0, mode=1)
         dpx = int(np.abs(frame.astype(int) - ref.astype(int)).max())
         ok = ok and dpx <= 1
-        print(f"MGPU world={world} grid={nt}x{nphi} prec={prec}: err={err:.3e} rgba_max_diff={dpx} ok={ok}", flush=True)
+        print(f"MGPU world={world} grid={nt}x{nphi} prec={prec} halo={halo}: err={err:.3e} rgba_max_diff={dpx} ok={ok}", flush=True)
     flag = torch.tensor([1 if ok else 0], device="cuda")
     dist.broadcast(flag, src=0)
     comm.close()
