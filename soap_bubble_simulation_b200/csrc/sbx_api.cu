@@ -105,6 +105,8 @@ struct sbx_drainage {
     float *rowW = nullptr;      // WGSL per-row float4
     void *bub = nullptr;        // BubbleParam<T>[batch]
     double *pole_partial = nullptr;
+    unsigned long long *pole_count = nullptr;
+    unsigned long long fold_count[2] = {0, 0};  // folded pole launches so far (top, bottom)
     int pole_slots_cap = 0;
     double *mm_part = nullptr;  // minmax partials
     double *mm_host = nullptr;  // pinned
@@ -171,6 +173,7 @@ static void free_all(sbx_drainage *h)
     cudaFree(h->rowW);
     cudaFree(h->bub);
     cudaFree(h->pole_partial);
+    cudaFree(h->pole_count);
     cudaFree(h->mm_part);
     cudaFree(h->scalar_dev);
     cudaFree(h->rgb_buf);
@@ -419,6 +422,8 @@ extern "C" int32_t sbx_drainage_create(const sbx_drainage_cfg *cfg, int32_t devi
     h->pole_slots_cap = h->num_phi / 32 + 2;
     CU_H(cudaMalloc(&h->pole_partial, (size_t)h->batch * 2 * h->pole_slots_cap * sizeof(double)));
     CU_H(cudaMemsetAsync(h->pole_partial, 0, (size_t)h->batch * 2 * h->pole_slots_cap * sizeof(double), h->stream));
+    CU_H(cudaMalloc(&h->pole_count, (size_t)h->batch * 2 * sizeof(unsigned long long)));
+    CU_H(cudaMemsetAsync(h->pole_count, 0, (size_t)h->batch * 2 * sizeof(unsigned long long), h->stream));
     CU_H(cudaMalloc(&h->mm_part, 2 * sbx_drainage::kMinmaxBlocks * sizeof(double)));
     CU_H(cudaHostAlloc(&h->mm_host, 2 * sbx_drainage::kMinmaxBlocks * sizeof(double), cudaHostAllocDefault));
     CU_H(cudaMalloc(&h->scalar_dev, 8 * sizeof(double)));
@@ -788,6 +793,7 @@ static void fill_step_args(sbx_drainage *h, StepArgs<T> &a, double dt, const Rgb
     a.coefX = h->coefX;
     a.bub = reinterpret_cast<const BubbleParam<T> *>(h->bub);
     a.pole_partial = h->pole_partial;
+    a.pole_count = h->pole_count;
     a.num_phi = h->num_phi;
     a.num_theta = h->num_theta;
     a.row_begin = h->row_begin;
@@ -810,6 +816,15 @@ static void fill_step_args(sbx_drainage *h, StepArgs<T> &a, double dt, const Rgb
     a.s_crit = h->critical;
     a.s_tfe_factor = 1.0 - reduction_rate * dt;  // drainage.rs:454
     a.rgb = rgb;
+}
+
+// decide whether this launch writes the pole rows inside the TMA kernel, and which arrival count it waits for
+static void set_pole_fold(sbx_drainage *h, StepArgs<float> &a, bool top, bool bottom)
+{
+    a.fold_top = a.fold_bottom = 0;
+    if (!h->use_tma || h->strict || !march_tma_folds_poles(a)) return;
+    if (top) { a.fold_top = 1; a.pole_want[0] = ++h->fold_count[0]; }
+    if (bottom) { a.fold_bottom = 1; a.pole_want[1] = ++h->fold_count[1]; }
 }
 
 template <typename T>
@@ -845,6 +860,7 @@ static int32_t step_cpu_sem(sbx_drainage *h, double dt, const RgbArgs &rgb)
     } else {
         a.fronts = ft;
         bool pushed = false;
+        if constexpr (sizeof(T) == 4) set_pole_fold(h, a, has_top, has_bottom);
         if constexpr (sizeof(T) == 4) {
             if (h->peer_enabled && h->use_tma && march_tma_supported(a)) {
                 PeerArgs &p = a.peer;
@@ -1040,7 +1056,10 @@ static int32_t step_host_pipelined(sbx_drainage *h, double dt, const sbx_view *v
         StepArgs<float> ac = a;
         ac.l_first = std::max(l_first, r0 + 1);
         ac.l_last = std::min(l_last, r1);
-        const bool top = c == 0 && h->row_begin == 0, bottom = c == nchunks - 1 && h->row_end == h->num_theta;
+        // the pole rows are written by the launch that holds the ring next to them
+        const bool top = c == 0 && h->row_begin == 0;
+        const bool bottom = c == (rows - 2) / chunk_rows && h->row_end == h->num_theta;
+        set_pole_fold(h, ac, top, bottom);
         CU(launch_step<float>(ac, 1, ft.count > 0, false, top, bottom, h->band_rows, h->use_tma, h->stream, &n));
         CU(cudaEventRecord(h->ev_comp[c], h->stream));
         CU(cudaStreamWaitEvent(h->copy_out, h->ev_comp[c], 0));

@@ -289,4 +289,38 @@ __device__ __forceinline__ uint32_t pack_rgba8(const float rgb[3])
     return r | (g << 8) | (b << 16) | 0xff000000u;
 }
 
+// RGBA8 from three floats in [0,1]: the low mantissa byte of (255 x + 2^23) is round(255 x); the blue
+// channel's magic constant also plants 0xff in byte 1, which becomes alpha.  Two PRMTs gather the bytes.
+__device__ __forceinline__ uint32_t pack_rgba8_fast(float r, float g, float b)
+{
+    const uint32_t ur = __float_as_uint(fmaf(r, 255.f, 8388608.0f));
+    const uint32_t ug = __float_as_uint(fmaf(g, 255.f, 8388608.0f));
+    const uint32_t ub = __float_as_uint(fmaf(b, 255.f, 8453888.0f));  // 2^23 + 0xff00
+    const uint32_t rg = __byte_perm(ur, ug, 0x0040);                  // bytes: r, g, -, -
+    return __byte_perm(rg, ub, 0x5410);                               // bytes: r, g, b, 0xff
+}
+
+template <int MODE>
+__device__ __forceinline__ uint32_t shade_px(float h, float href, float href_u, float colA, float sin_th, float ccy,
+                                             float R, float camR2, const RgbArgs &rgb)
+{
+    const float nc = fmaf(sin_th, colA, ccy);      // n . cam
+    const float len2 = fmaf(-2.f * R, nc, camR2);  // |cam - R n|^2
+    if constexpr (MODE == SBX_RGB_LUT) {
+        // u = clamp(d_nm / max_nm), v = clamp(cos theta_i): bubble.wgsl:429-433
+        const float u = __saturatef(fmaf(h, rgb.nm_over_max, href_u));
+        const float v = __saturatef(fabsf(nc - R) * rsqrt_approx(len2));
+        const float4 t = tex2D<float4>(rgb.lut, u, v);
+        return pack_rgba8_fast(__saturatef(t.x * rgb.intensity), __saturatef(t.y * rgb.intensity),
+                               __saturatef(t.z * rgb.intensity));
+    } else {
+        const float ci = fabsf(nc - R) * rsqrt_approx(len2);
+        const double d_nm = ((double)h + (double)href) * 1e9;
+        float c[3];
+        rgb_eval<MODE>(d_nm, ci, rgb, c);
+        return pack_rgba8(c);
+    }
+}
+
+
 }  // namespace sbx

@@ -79,6 +79,9 @@ struct StepArgs {
     const double4 *coefX;    // strict mode per global row: {sin theta, cos/sin_safe, sin_safe^2, 0}
     const BubbleParam<T> *bub;
     double *pole_partial;    // [batch][2][pole_slots]
+    unsigned long long *pole_count;  // [batch][2] monotonic arrival counters (TMA kernel's folded pole rows)
+    unsigned long long pole_want[2]; // arrivals per strip count the folded launches: wait for pole_want * strips
+    int fold_top, fold_bottom;       // TMA kernel: this launch also writes the top / bottom pole row
     int pole_slots;
     int num_phi, num_theta;  // global grid
     int row_begin;           // global row of local row 1

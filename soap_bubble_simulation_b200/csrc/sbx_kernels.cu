@@ -287,6 +287,20 @@ __global__ void __launch_bounds__(256) k_shade(const StepArgs<T> a)
         const Vec<T, VEC> h = ldv<T, VEC>(in + (long long)l * N + j0);
         const float2 sc = __ldg(a.rowSC + grow);
         const float ccy = sc.y * a.rgb.cam_y;
+        if constexpr (sizeof(T) == 4 && VEC == 4) {
+            if (a.rgb.format == SBX_OUT_RGBA8) {  // streaming fast path: 4 pixels per thread, one 16-byte store
+                const float camR2 = a.rgb.cam2 + bp.radius * bp.radius;
+                const float href_u = bp.h_ref * a.rgb.nm_over_max;
+                uint32_t px[4];
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                    px[k] = shade_px<MODE>(h.v[k], bp.h_ref, href_u, colA[k], sc.x, ccy, bp.radius, camR2, a.rgb);
+                uint32_t *o = reinterpret_cast<uint32_t *>(a.rgb.out) + (long long)b * a.rgb_bubble_stride +
+                              (long long)(l - 1) * N + j0;
+                *reinterpret_cast<uint4 *>(o) = make_uint4(px[0], px[1], px[2], px[3]);
+                continue;
+            }
+        }
         using DN = typename Dnm<MODE>::type;
         DN d_nm[VEC];
         float ci[VEC];
@@ -296,6 +310,47 @@ __global__ void __launch_bounds__(256) k_shade(const StepArgs<T> a)
             ci[k] = view_cos(sc.x, ccy, colA[k], bp.radius, a.rgb.cam2);
         }
         emit_rgb<MODE, VEC>(d_nm, ci, a.rgb, (long long)b * a.rgb_bubble_stride + (long long)(l - 1) * N + j0);
+    }
+}
+
+// f32 -> RGBA8 streaming variant of k_shade: four rows per trip with all four 16-byte loads issued before the
+// first use, so that every thread keeps 64 B in flight (the plain loop above has one dependent load per row).
+template <int MODE>
+__global__ void __launch_bounds__(256) k_shade_rgba8(const StepArgs<float> a)
+{
+    const int N = a.num_phi;
+    const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+    if (j0 >= N) return;
+    const int b = blockIdx.z;
+    const float *__restrict__ in = a.in + (long long)b * a.bubble_stride;
+    uint32_t *__restrict__ out = reinterpret_cast<uint32_t *>(a.rgb.out) + (long long)b * a.rgb_bubble_stride;
+    const BubbleParam<float> bp = a.bub[b];
+    const float4 ca = __ldg(reinterpret_cast<const float4 *>(a.rgb.colA + j0));
+    const float colA[4] = {ca.x, ca.y, ca.z, ca.w};
+    const float camR2 = a.rgb.cam2 + bp.radius * bp.radius;
+    const float href_u = bp.h_ref * a.rgb.nm_over_max;
+    const int l0 = a.l_first + blockIdx.y * a.band_rows;
+    const int l1 = min(l0 + a.band_rows - 1, a.l_last);
+    for (int l = l0; l <= l1; l += 4) {
+        float4 h[4];
+        float2 sc[4];
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const int lr = min(l + r, l1);
+            h[r] = __ldg(reinterpret_cast<const float4 *>(in + (long long)lr * N + j0));
+            sc[r] = __ldg(a.rowSC + a.row_begin + (lr - 1));
+        }
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            if (l + r > l1) break;
+            const float ccy = sc[r].y * a.rgb.cam_y;
+            const float hv[4] = {h[r].x, h[r].y, h[r].z, h[r].w};
+            uint32_t px[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                px[k] = shade_px<MODE>(hv[k], bp.h_ref, href_u, colA[k], sc[r].x, ccy, bp.radius, camR2, a.rgb);
+            *reinterpret_cast<uint4 *>(out + (long long)(l + r - 1) * N + j0) = make_uint4(px[0], px[1], px[2], px[3]);
+        }
     }
 }
 
@@ -708,9 +763,12 @@ cudaError_t launch_step(StepArgs<T> a, int batch, bool tfe, bool strict, bool ha
         if constexpr (sizeof(T) == 4) {
             if (!strict && use_tma && march_tma_supported(a)) {
                 int slots = 0;
+                // a.fold_top / a.fold_bottom / a.pole_want were set by the caller iff march_tma_folds_poles(a)
                 e = launch_march_tma(a, batch, tfe, band_rows_req, st, &slots);
                 a.pole_slots = slots;
                 done = true;
+                if (a.fold_top) has_top = false;  // the strips of the ring rows wrote the pole rows themselves
+                if (a.fold_bottom) has_bottom = false;
             }
         }
         if (!done)
@@ -769,6 +827,9 @@ cudaError_t launch_shade(StepArgs<T> a, int batch, int band_rows_req, cudaStream
     march_geometry(a.num_phi, vec_ok ? VECW : 1, rows, batch, band_rows_req, grid, block, band_rows);
     a.band_rows = band_rows;
 #define SBX_SHADE(MODE)                                                       \
+    if constexpr (sizeof(T) == 4) {                                           \
+        if (vec_ok && a.rgb.format == SBX_OUT_RGBA8) { k_shade_rgba8<MODE><<<grid, block, 0, st>>>(a); break; } \
+    }                                                                         \
     if (vec_ok) k_shade<T, VECW, MODE><<<grid, block, 0, st>>>(a);            \
     else k_shade<T, 1, MODE><<<grid, block, 0, st>>>(a)
     switch (a.rgb.mode) {

@@ -13,6 +13,7 @@ cudaError_t launch_step(StepArgs<T> a, int batch, bool tfe, bool strict, bool ha
 
 // f32 fast path (sbx_march_tma.cu): TMA-staged ring, RGBA8 or no colour, num_phi % 4 == 0
 bool march_tma_supported(const StepArgs<float> &a);
+bool march_tma_folds_poles(const StepArgs<float> &a);
 cudaError_t launch_march_tma(StepArgs<float> a, int batch, bool tfe, int band_rows_req, cudaStream_t st, int *pole_slots);
 
 template <typename T>

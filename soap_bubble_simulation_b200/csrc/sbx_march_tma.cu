@@ -96,39 +96,6 @@ struct Row {
     float eL, eR;
 };
 
-// RGBA8 from three floats in [0,1]: the low mantissa byte of (255 x + 2^23) is round(255 x); the blue
-// channel's magic constant also plants 0xff in byte 1, which becomes alpha.  Two PRMTs gather the bytes.
-__device__ __forceinline__ uint32_t pack_rgba8_fast(float r, float g, float b)
-{
-    const uint32_t ur = __float_as_uint(fmaf(r, 255.f, 8388608.0f));
-    const uint32_t ug = __float_as_uint(fmaf(g, 255.f, 8388608.0f));
-    const uint32_t ub = __float_as_uint(fmaf(b, 255.f, 8453888.0f));  // 2^23 + 0xff00
-    const uint32_t rg = __byte_perm(ur, ug, 0x0040);                  // bytes: r, g, -, -
-    return __byte_perm(rg, ub, 0x5410);                               // bytes: r, g, b, 0xff
-}
-
-template <int MODE>
-__device__ __forceinline__ uint32_t shade_px(float h, float href, float href_u, float colA, float sin_th, float ccy,
-                                             float R, float camR2, const RgbArgs &rgb)
-{
-    const float nc = fmaf(sin_th, colA, ccy);      // n . cam
-    const float len2 = fmaf(-2.f * R, nc, camR2);  // |cam - R n|^2
-    if constexpr (MODE == SBX_RGB_LUT) {
-        // u = clamp(d_nm / max_nm), v = clamp(cos theta_i): bubble.wgsl:429-433
-        const float u = __saturatef(fmaf(h, rgb.nm_over_max, href_u));
-        const float v = __saturatef(fabsf(nc - R) * rsqrt_approx(len2));
-        const float4 t = tex2D<float4>(rgb.lut, u, v);
-        return pack_rgba8_fast(__saturatef(t.x * rgb.intensity), __saturatef(t.y * rgb.intensity),
-                               __saturatef(t.z * rgb.intensity));
-    } else {
-        const float ci = fabsf(nc - R) * rsqrt_approx(len2);
-        const double d_nm = ((double)h + (double)href) * 1e9;
-        float c[3];
-        rgb_eval<MODE>(d_nm, ci, rgb, c);
-        return pack_rgba8(c);
-    }
-}
-
 }  // namespace
 
 template <int MODE, bool TFE>
@@ -285,6 +252,9 @@ __global__ void __launch_bounds__(288, 4) k_march_tma(const StepArgs<float> a)
                 double *pp = a.pole_partial + (long long)b * 2 * a.pole_slots;
                 if (grow == ring_top) pp[blockIdx.x] = t;
                 if (grow == ring_bot) pp[a.pole_slots + blockIdx.x] = t;
+                __threadfence();  // partial visible before the arrival count
+                if (grow == ring_top && a.fold_top) atomicAdd(a.pole_count + 2 * b, 1ull);
+                if (grow == ring_bot && a.fold_bottom) atomicAdd(a.pole_count + 2 * b + 1, 1ull);
             }
             bar_consumers(C);
         }
@@ -338,6 +308,57 @@ __global__ void __launch_bounds__(288, 4) k_march_tma(const StepArgs<float> a)
         load_slot(r1, 1);
         compute_row(r2, r0, r1);
         if (--left == 0) break;
+    }
+
+    // Pole rows (drainage.rs:480-503), folded into this kernel: the strips that updated a pole-adjacent ring wait
+    // until all strips of that ring have published their partial sums (they were dispatched together, so this
+    // is a short spin among co-resident CTAs), add them in a fixed order and write their own slice of the pole
+    // row, its TFE reduction (drainage.rs:437-460) and its colour.
+    if (has_ring && (a.fold_top || a.fold_bottom)) {
+        const int g_first = a.row_begin + l0 - 1, g_last = a.row_begin + l1 - 1;
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) {
+            const int ring = which == 0 ? ring_top : ring_bot;
+            if (!(which == 0 ? a.fold_top : a.fold_bottom) || ring < g_first || ring > g_last) continue;
+            const unsigned long long want = a.pole_want[which] * (unsigned long long)gridDim.x;
+            if (tid == 0) {
+                const volatile unsigned long long *cnt = a.pole_count + 2 * b + which;
+                while (*cnt < want) __nanosleep(32);
+                __threadfence();
+                const double *pp = a.pole_partial + (long long)b * 2 * a.pole_slots + which * a.pole_slots;
+                double t = 0.0;
+                for (int i = 0; i < (int)gridDim.x; ++i) t += __ldcg(pp + i);  // fixed order
+                warp_part[0] = t / (double)N;
+            }
+            bar_consumers(C);
+            const float v = (float)warp_part[0];
+            bar_consumers(C);
+            if (active) {
+                const int prow = which == 0 ? 0 : a.num_theta - 1;
+                const int pl = prow - a.row_begin + 1;
+                float pv[4] = {v, v, v, v};
+                if constexpr (TFE) {
+                    const unsigned rm = front_row_mask(a.fronts, prow);
+                    if (rm) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k)
+                            if (front_hit(a.fronts, rm, jc + k)) pv[k] = fmaf(-(pv[k] + href), a.tfe_rdt, pv[k]);
+                    }
+                }
+                *reinterpret_cast<float4 *>(out + (long long)pl * N + jc) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+                if constexpr (MODE != SBX_RGB_NONE) {
+                    const float2 sc = __ldg(a.rowSC + prow);
+                    const float ccy = sc.y * a.rgb.cam_y;
+                    uint32_t px[4];
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        px[k] = shade_px<MODE>(pv[k], href, href_u, colA[k], sc.x, ccy, Rv, camR2, a.rgb);
+                    uint32_t *o = reinterpret_cast<uint32_t *>(a.rgb.out) + (long long)b * a.rgb_bubble_stride +
+                                  (long long)(pl - 1) * N + jc;
+                    *reinterpret_cast<uint4 *>(o) = make_uint4(px[0], px[1], px[2], px[3]);
+                }
+            }
+        }
     }
 
     if (a.peer.enabled) {
@@ -405,11 +426,26 @@ bool march_tma_supported(const StepArgs<float> &a)
     return true;
 }
 
+static int tma_consumers(int num_phi)
+{
+    int consumers = 256;
+    while (consumers > 32 && consumers * 2 >= num_phi) consumers >>= 1;  // narrow grids: fewer, fuller CTAs
+    return consumers;
+}
+
+// The pole rows are folded into the kernel only when all strips of a ring are certainly co-resident (they
+// wait for each other); otherwise k_poles finishes them.
+bool march_tma_folds_poles(const StepArgs<float> &a)
+{
+    if (!march_tma_supported(a) || a.l_last < a.l_first) return false;
+    const int strip = tma_consumers(a.num_phi) * 4;
+    return (a.num_phi + strip - 1) / strip <= 128;
+}
+
 cudaError_t launch_march_tma(StepArgs<float> a, int batch, bool tfe, int band_rows_req, cudaStream_t st, int *pole_slots)
 {
     const int rows = a.l_last - a.l_first + 1;
-    int consumers = 256;
-    while (consumers > 32 && consumers * 2 >= a.num_phi) consumers >>= 1;  // narrow grids: fewer, fuller CTAs
+    const int consumers = tma_consumers(a.num_phi);
     const int strip = consumers * 4;
     const int gx = (a.num_phi + strip - 1) / strip;
     int band_rows = band_rows_req > 0 ? band_rows_req : 24;  // multiple of the 3-row ring stage; measured best at 8192x16384
