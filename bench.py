@@ -340,7 +340,7 @@ def main():
         "gpu_launches": int(launches),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": ncu_traffic(), "peak_source": peak_src,
-                     "kernel": "k_march (+ k_poles, 2 launches per step)",
+                     "kernel": "k_march_tma<LUT> (one launch per step; pole rows folded in)" if mode == S.RGB_LUT else "k_march_tma",
                      "algorithmic_bytes_per_cell": bytes_per_cell},
     }
     if world == 1 and not args.no_cpu_baseline:
