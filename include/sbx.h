@@ -229,6 +229,11 @@ int32_t sbx_lut_build(float refractive_index, float intensity, uint8_t *out65536
 int32_t sbx_lut_build_spectral(float refractive_index, float intensity, const float *wavelengths_nm,
                                int32_t n_lambda, int32_t T, int32_t A, float max_nm, uint8_t *out,
                                int32_t device);
+/* thin_film_interference() of the fragment shader (src/render/shaders/bubble.wgsl:425-439) for n arbitrary
+ * (thickness_nm, cos_theta) pairs in host memory: bilinear, clamp-to-edge fetch of a T x A RGBA8 LUT through the
+ * texture unit at uv = (d/max_nm, cos), times intensity, clamped; rgb_out = n x 3 floats. */
+int32_t sbx_lut_shade_points(const uint8_t *lut_rgba, int32_t T, int32_t A, float max_nm, const float *d_nm,
+                             const float *cos_theta, size_t n, float intensity, float *rgb_out, int32_t device);
 /* InterferenceCalculator (src/physics/interference.rs:127-513) evaluated in f64 on the device for n
  * (thickness_nm, cos_theta_incident) pairs held in host memory; rgb_out = n x 3 doubles.
  * gamma != 0: calculate_interference_color (:380-400); gamma == 0: _linear (:413-426). */

@@ -9,6 +9,6 @@ from .drainage import DrainageSimulator, ThicknessField, View, camera_position
 from .gpu_drainage import DrainageParams, GPUDrainageSimulator
 from .interference import (LUT_ANGLE_SAMPLES, LUT_MAX_THICKNESS_NM, LUT_THICKNESS_SAMPLES,
                            FresnelCoefficients, InterferenceCalculator, RgbColor,
-                           generate_interference_lut, generate_spectral_lut)
+                           generate_interference_lut, generate_spectral_lut, thin_film_interference)
 
 __all__ = [n for n in dir() if not n.startswith("_")]

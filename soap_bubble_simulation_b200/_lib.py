@@ -104,6 +104,8 @@ _SIGS = {
     "sbx_lut_build": [C.c_float, C.c_float, C.c_void_p, C.c_int32],
     "sbx_lut_build_spectral": [C.c_float, C.c_float, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                C.c_float, C.c_void_p, C.c_int32],
+    "sbx_lut_shade_points": [C.c_void_p, C.c_int32, C.c_int32, C.c_float, C.c_void_p, C.c_void_p, C.c_size_t,
+                             C.c_float, C.c_void_p, C.c_int32],
     "sbx_interference_eval": [C.c_double, C.POINTER(C.c_double), C.c_void_p, C.c_void_p, C.c_size_t,
                               C.c_int32, C.c_void_p, C.c_int32],
     "sbx_interference_terms": [C.c_double, C.c_void_p, C.c_void_p, C.c_size_t, C.c_double, C.c_void_p,

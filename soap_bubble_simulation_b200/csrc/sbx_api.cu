@@ -1334,6 +1334,45 @@ extern "C" int32_t sbx_lut_build(float n, float intensity, uint8_t *out65536, in
     return sbx_lut_build_spectral(n, intensity, kLutWl7, 7, 256, 64, 2000.f, out65536, device);
 }
 
+extern "C" int32_t sbx_lut_shade_points(const uint8_t *lut_rgba, int32_t T, int32_t A, float max_nm, const float *d_nm,
+                                        const float *cos_theta, size_t n, float intensity, float *rgb_out, int32_t device)
+{
+    if (!lut_rgba || !d_nm || !cos_theta || !rgb_out || T < 2 || A < 2 || !(max_nm > 0.f))
+        return fail(SBX_ERR_INVALID, "bad arguments");
+    int32_t rc = pick_device(device);
+    if (rc != SBX_OK) return rc;
+    if (n == 0) return SBX_OK;
+    cudaArray_t arr = nullptr;
+    cudaTextureObject_t tex = 0;
+    float *dd = nullptr, *dc = nullptr, *dr = nullptr;
+    cudaChannelFormatDesc ch = cudaCreateChannelDesc<uchar4>();
+    cudaError_t e = cudaMallocArray(&arr, &ch, (size_t)T, (size_t)A);
+    if (e == cudaSuccess) e = cudaMemcpy2DToArray(arr, 0, 0, lut_rgba, (size_t)T * 4, (size_t)T * 4, (size_t)A, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        cudaResourceDesc rd{};
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = arr;
+        cudaTextureDesc td{};
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModeLinear;
+        td.readMode = cudaReadModeNormalizedFloat;
+        td.normalizedCoords = 1;
+        e = cudaCreateTextureObject(&tex, &rd, &td, nullptr);
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&dd, n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&dc, n * 4);
+    if (e == cudaSuccess) e = cudaMalloc(&dr, n * 12);
+    if (e == cudaSuccess) e = cudaMemcpy(dd, d_nm, n * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(dc, cos_theta, n * 4, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = launch_lut_shade_points(tex, 1.0f / max_nm, intensity, dd, dc, n, dr, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(rgb_out, dr, n * 12, cudaMemcpyDeviceToHost);
+    cudaFree(dd); cudaFree(dc); cudaFree(dr);
+    if (tex) cudaDestroyTextureObject(tex);
+    if (arr) cudaFreeArray(arr);
+    if (e != cudaSuccess) return fail(SBX_ERR_CUDA, "LUT shading failed: %s", cudaGetErrorString(e));
+    return SBX_OK;
+}
+
 extern "C" int32_t sbx_interference_eval(double n_film, const double wl[3], const double *d_nm, const double *cos_i,
                                          size_t n, int32_t gamma, double *rgb_out, int32_t device)
 {

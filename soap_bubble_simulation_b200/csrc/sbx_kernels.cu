@@ -682,6 +682,25 @@ __global__ void k_interference_terms(InterfD c, const double *d_nm, const double
     if (out_intensity) out_intensity[i] = d_reflected_intensity(c, d_nm[i], cos_i[i], wl);
 }
 
+// bubble.wgsl:425-439 for arbitrary (thickness, cos) pairs: same texture-unit fetch as the fused colour stage
+__global__ void k_lut_shade_points(cudaTextureObject_t lut, float inv_max_nm, float intensity, const float *d_nm,
+                                   const float *cos_theta, size_t n, float *rgb)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float4 t = tex2D<float4>(lut, clamp01(d_nm[i] * inv_max_nm), clamp01(cos_theta[i]));
+    rgb[3 * i + 0] = clamp01(t.x * intensity);
+    rgb[3 * i + 1] = clamp01(t.y * intensity);
+    rgb[3 * i + 2] = clamp01(t.z * intensity);
+}
+
+cudaError_t launch_lut_shade_points(cudaTextureObject_t lut, float inv_max_nm, float intensity, const float *d_nm,
+                                    const float *cos_theta, size_t n, float *rgb, cudaStream_t st)
+{
+    k_lut_shade_points<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(lut, inv_max_nm, intensity, d_nm, cos_theta, n, rgb);
+    return cudaGetLastError();
+}
+
 // per-column view term A_j = cos(phi_j) cam_x + sin(phi_j) cam_z, evaluated in f64
 __global__ void k_col_view(float *colA, int num_phi, double cam_x, double cam_z)
 {

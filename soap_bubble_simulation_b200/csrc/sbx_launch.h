@@ -43,6 +43,8 @@ cudaError_t launch_interference_eval(double n_film, const double wl[3], const do
                                      size_t n, int gamma, double *rgb, cudaStream_t st);
 cudaError_t launch_interference_terms(double n_film, const double *d_nm, const double *cos_i, size_t n, double wl,
                                       double *out_cos_t, double *out_fresnel, double *out_intensity, cudaStream_t st);
+cudaError_t launch_lut_shade_points(cudaTextureObject_t lut, float inv_max_nm, float intensity, const float *d_nm,
+                                    const float *cos_theta, size_t n, float *rgb, cudaStream_t st);
 cudaError_t launch_col_view(float *colA, int num_phi, double cam_x, double cam_z, cudaStream_t st);
 
 }  // namespace sbx

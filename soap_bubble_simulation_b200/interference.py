@@ -173,3 +173,18 @@ def generate_spectral_lut(refractive_index: float, intensity: float, wavelengths
                                            thickness_samples, angle_samples, max_thickness_nm,
                                            out.ctypes.data, device))
     return out
+
+
+def thin_film_interference(lut_rgba: np.ndarray, thickness_nm, cos_theta, interference_intensity: float = 4.0,
+                           max_thickness_nm: float = LUT_MAX_THICKNESS_NM, *, device: int = 0) -> np.ndarray:
+    """thin_film_interference() of the bubble fragment shader (src/render/shaders/bubble.wgsl:425-439) for arrays of
+    (thickness, cos theta): bilinear LUT fetch through the GPU's texture unit, times intensity, clamped.
+    lut_rgba: (A, T, 4) uint8 as returned by generate_interference_lut(...).reshape(64, 256, 4); returns (n, 3) f32."""
+    lut = np.ascontiguousarray(lut_rgba, dtype=np.uint8)
+    A, T = lut.shape[0], lut.shape[1]
+    d = np.ascontiguousarray(thickness_nm, dtype=np.float32).ravel()
+    c = np.ascontiguousarray(cos_theta, dtype=np.float32).ravel()
+    out = np.empty((d.size, 3), dtype=np.float32)
+    L.check(L.lib().sbx_lut_shade_points(lut.ctypes.data, T, A, max_thickness_nm, d.ctypes.data, c.ctypes.data,
+                                         d.size, interference_intensity, out.ctypes.data, device))
+    return out
