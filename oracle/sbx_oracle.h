@@ -9,7 +9,7 @@
  * PARITY PINNING STATUS: *partially pinned*.  The reference (Rust 2024, wgpu) cannot be compiled or imported in
  * this image (no cargo/rustc).
  *   - Interference LUT path (generate_interference_lut, thin_film_interference, LUT sampling, view cosine):
- *     pinned against the reference's own outputs -- its eight golden screenshots (tests/golden/*.png of the
+ *     pinned against the reference's own outputs -- its eight golden screenshots (the PNGs under tests/golden of the
  *     reference, copied to tests/golden/reference_png) are re-rendered with this oracle's LUT and pass the
  *     reference's own comparator rule with margin (<= 2.1 % of pixels off by more than 5/255, limit 5 %;
  *     tests/test_reference_golden_images.py, incl. a negative test showing wrong LUTs fail).
