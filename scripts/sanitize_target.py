@@ -1,0 +1,47 @@
+"""Small workload touching every kernel family once; run under compute-sanitizer (scripts/sanitize.sh)."""
+import os
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import soap_bubble_simulation_b200 as S  # noqa: E402
+from synth import dt_max, synthetic_field  # noqa: E402
+
+view = S.View()
+for nt, nphi in ((130, 1028), (64, 2048), (37, 50)):
+    f = synthetic_field(nt, nphi, dtype=np.float32)
+    dt = min(1e-3, 0.25 * dt_max(nt, nphi))
+    for prec in (S.PREC_F32, S.PREC_F64, S.PREC_F64_STRICT):
+        sim = S.DrainageSimulator(S.SimulationConfig.default(), precision=prec, num_theta=nt, num_phi=nphi, h_ref=0.0)
+        sim.upload(f)
+        sim.step(dt, 2)
+        sim.step_fused(dt, view, 2)
+        sim.step_fused(dt, S.View(mode=S.RGB_EXACT3, format=S.OUT_RGB_F32), 1)
+        sim.shade(view)
+        sim.minmax()
+        sim.get_thickness(1.0, 2.0)
+        sim.download()
+        sim.download_rgb()
+        sim.close()
+# TFE fronts active (t > 0.5 s) on the TMA path, offset storage, batch
+sim = S.DrainageSimulator(S.SimulationConfig.default(), num_theta=64, num_phi=256, batch=3)
+sim.step_fused(5e-3, view, 130)
+assert sim.active_tfe_count() >= 1
+sim.download()
+sim.close()
+g = S.GPUDrainageSimulator(500e-9, 256, 64)
+g.set_marangoni_enabled(True)
+g.dispatch(3, view)
+g.download_concentration()
+g.close()
+out = np.empty((1, 1300, 256), np.float32)
+px = np.empty((1, 1300, 256, 4), np.uint8)
+sim = S.DrainageSimulator(S.SimulationConfig.default(), num_theta=1300, num_phi=256, h_ref=0.0)
+sim.step_host(1e-6, 1, view, synthetic_field(1300, 256, dtype=np.float32)[None].copy(), out, px)
+sim.close()
+S.generate_interference_lut(1.33, 1.0)
+S.InterferenceCalculator(1.33).batch(np.linspace(0, 2000, 100), np.linspace(0, 1, 100))
+print("SANITIZE_TARGET_DONE")
