@@ -476,3 +476,56 @@ def test_step_host_pipelined_equals_separate_calls(S, monkeypatch):
     sim64.step_host(dt, 1, view, f[None].astype(np.float64), o64, out_px)
     sim.step_host(dt, 1, view, f[None].copy(), out_h, None)
     assert np.array_equal(o64.astype(np.float32), out_h)
+
+
+def test_wgsl_sin_safe_threshold_on_weak_scaled_grid(S):
+    """65,536 theta rows (the 8-GPU weak-scaled grid): sin(theta_1) = 4.8e-5 is below the shader's 1e-4 guard
+    (drainage.wgsl:101), so the rings next to the poles run on the clamped value -- and must still match."""
+    w, h = 16, 65536
+    sim = S.GPUDrainageSimulator(500e-9, w, h)
+    rng = np.random.default_rng(5)
+    hf = (5e-6 * (1 + 0.05 * rng.standard_normal((h, w)))).astype(np.float32)
+    cf = np.clip(0.5 + 0.1 * rng.standard_normal((h, w)), 0, 1).astype(np.float32)
+    p = O.wgsl_params(grid_width=w, grid_height=h, marangoni_enabled=1, dt=1e-9)
+    sim.set_marangoni_enabled(True)
+    sim.set_dt(1e-9)
+    sim.upload(hf)
+    sim.upload_concentration(cf)
+    ho, co = O.wgsl_step(p, hf, cf)
+    ho, co = O.wgsl_step(p, ho, co)
+    sim.dispatch(2)
+    gh, gc = sim.download(np.float32)[0], sim.download_concentration()[0]
+    assert np.abs(gh[:4].astype(np.float64) / ho[:4] - 1).max() <= 1e-5
+    assert np.abs(gh.astype(np.float64) / ho - 1).max() <= 1e-5
+    assert np.abs(gc.astype(np.float64) - co).max() <= 1e-5
+
+
+def test_nan_inf_and_huge_cells_follow_the_reference(S):
+    """Non-finite and extreme cells: f64::max(NaN, 0.0) is 0.0 in Rust (drainage.rs:378), comparisons with NaN are
+    false (so a NaN cell is not 'below critical'), +inf stays +inf.  The strict mode must agree bit for bit, f32 in
+    the same places."""
+    nt, nphi = 24, 32
+    f = synthetic_field(nt, nphi)
+    f[5, 7] = np.nan
+    f[9, 0] = np.inf
+    f[12, 31] = 1e-3      # a millimetre-thick cell: huge h^3 term, clamps to 0
+    f[15, 3] = 0.0
+    f[1, 4] = np.nan      # in the ring that feeds the top pole mean
+    ora = O.OracleDrainage(nt, nphi)
+    ora.data[:] = f
+    ora.step(1e-3, 3)
+    strict = make_sim(S, nt, nphi, S.PREC_F64_STRICT)
+    strict.upload(f)
+    strict.step(1e-3, 3)
+    got = strict.download()[0]
+    assert np.array_equal(np.isnan(got), np.isnan(ora.data))
+    assert np.array_equal(got[~np.isnan(got)], ora.data[~np.isnan(ora.data)])
+    f32sim = make_sim(S, nt, nphi, S.PREC_F32, h_ref=0.0)
+    f32sim.upload(f)
+    f32sim.step(1e-3, 3)
+    g32 = f32sim.download()[0]
+    assert np.array_equal(np.isnan(g32), np.isnan(ora.data))
+    fin = np.isfinite(ora.data) & (ora.data > 0)
+    assert np.array_equal(np.isinf(g32), np.isinf(ora.data))
+    assert np.array_equal(g32 == 0, ora.data == 0)
+    assert np.abs(g32[fin] / ora.data[fin] - 1).max() <= 1e-5
