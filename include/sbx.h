@@ -80,7 +80,8 @@ typedef enum {
 typedef enum {
     SBX_PTR_THICKNESS = 0,     /* latest thickness, first owned row (device pointer) */
     SBX_PTR_CONCENTRATION = 1, /* latest concentration (SBX_SEM_WGSL only) */
-    SBX_PTR_RGB = 2            /* last colour frame written by step_fused/shade */
+    SBX_PTR_RGB = 2,           /* last colour frame written by step_fused/shade */
+    SBX_PTR_CAUSTICS = 3       /* last caustic map written by sbx_drainage_caustics */
 } sbx_ptr_kind;
 
 /* DrainageParams, src/render/gpu_drainage.rs:10-44 == src/render/shaders/drainage.wgsl:14-31
@@ -219,6 +220,21 @@ int32_t sbx_drainage_set_lut(sbx_drainage *h, const uint8_t *rgba, int32_t T, in
 
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int32_t sbx_drainage_launch_count(sbx_drainage *h, int64_t *out);
+
+/* ---------------------------------------------------------------- thickness-buffer consumer: caustic map */
+/* CausticParams (src/render/caustics.rs:19-79 == src/render/shaders/caustics_compute.wgsl:5-22), 64-byte POD */
+typedef struct {
+    uint32_t grid_width, grid_height;
+    float refractive_index, film_thickness_scale, light_dir_x, light_dir_y, light_dir_z, light_intensity;
+    float focal_length, caustic_intensity, caustic_sharpness, branch_threshold, ground_y, bubble_radius, time;
+    uint32_t _padding;
+} sbx_caustic_params;
+int32_t sbx_caustic_params_default(sbx_caustic_params *p);
+/* CausticRenderer::compute (caustics.rs:441-457) = caustics_compute.wgsl::main (:114-126) on the handle's LATEST
+ * thickness buffer (the reference reads the second-to-last one): gradient / Laplacian / Hessian
+ * caustic intensity per cell, f32.  host_out (may be NULL) receives batch*rows*num_phi floats; the map also stays
+ * on the device (SBX_PTR_CAUSTICS).  grid_width/grid_height in p are overridden by the handle's grid. */
+int32_t sbx_drainage_caustics(sbx_drainage *h, const sbx_caustic_params *p, float *host_out);
 
 /* ---------------------------------------------------------------- interference LUT / calculator */
 /* generate_interference_lut(refractive_index, intensity) -> 256x64 RGBA8

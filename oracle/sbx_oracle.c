@@ -754,3 +754,61 @@ void orc_shade_field(const double *h, int num_theta, int num_phi, int row0, int 
     free(sp);
     free(cp);
 }
+
+/* ================================================================== caustic intensity map (f32) */
+
+void orc_caustic_params_default(orc_caustic_params *p)
+{
+    memset(p, 0, sizeof(*p));
+    p->grid_width = 128;
+    p->grid_height = 64;
+    p->refractive_index = 1.33f;
+    p->film_thickness_scale = 1e6f;
+    p->light_dir_y = -1.0f;
+    p->light_intensity = 1.0f;
+    p->focal_length = 0.1f;
+    p->caustic_intensity = 2.0f;
+    p->caustic_sharpness = 1.5f;
+    p->branch_threshold = 0.001f;
+    p->ground_y = -0.1f;
+    p->bubble_radius = 0.025f;
+}
+
+static float caustic_sample(const orc_caustic_params *p, const float *t, int x, int y)
+{ /* caustics_compute.wgsl:29-43 */
+    int W = (int)p->grid_width, H = (int)p->grid_height;
+    int sx = x % W;
+    if (sx < 0) sx += W;
+    int sy = y < 0 ? 0 : (y > H - 1 ? H - 1 : y);
+    return t[(size_t)sy * (size_t)W + (size_t)sx];
+}
+
+void orc_caustic_map(const orc_caustic_params *p, const float *t, float *out)
+{
+    const int W = (int)p->grid_width, H = (int)p->grid_height;
+    for (int y = 0; y < H; ++y) {
+        for (int x = 0; x < W; ++x) {
+            const float h = 1.0f, h2 = h * h;
+            const float center = caustic_sample(p, t, x, y);
+            const float left = caustic_sample(p, t, x - 1, y), right = caustic_sample(p, t, x + 1, y);
+            const float up = caustic_sample(p, t, x, y - 1), down = caustic_sample(p, t, x, y + 1);
+            const float gx = (right - left) / (2.0f * h), gy = (down - up) / (2.0f * h);          /* :46-51 */
+            const float laplacian = (left + right + up + down - 4.0f * center) / h2;              /* :54-65 */
+            const float d2x = (left + right - 2.0f * center) / h2;                                /* :68-92 */
+            const float d2y = (up + down - 2.0f * center) / h2;
+            const float ul = caustic_sample(p, t, x - 1, y - 1), ur = caustic_sample(p, t, x + 1, y - 1);
+            const float dl = caustic_sample(p, t, x - 1, y + 1), dr = caustic_sample(p, t, x + 1, y + 1);
+            const float dxy = (dr - dl - ur + ul) / (4.0f * h2);
+            const float hessian_det = d2x * d2y - dxy * dxy;
+            const float curvature_factor = -laplacian * p->focal_length;                          /* :95-112 */
+            const float focusing = 1.0f / fmaxf(fabsf(1.0f - curvature_factor), 0.01f);
+            const float branch_factor = hessian_det < -p->branch_threshold ? 1.5f : 1.0f;
+            const float grad_mag = sqrtf(gx * gx + gy * gy);
+            const float refraction_factor = 1.0f + grad_mag * 0.5f;
+            float intensity = focusing * branch_factor * refraction_factor;
+            intensity = powf(intensity, p->caustic_sharpness);
+            intensity *= p->caustic_intensity;
+            out[(size_t)y * (size_t)W + (size_t)x] = intensity < 0.f ? 0.f : (intensity > 10.f ? 10.f : intensity);
+        }
+    }
+}

@@ -160,6 +160,21 @@ void orc_shade_field(const double *h, int num_theta, int num_phi, int row0, int 
                      const double cam[3], double n_film, const uint8_t *lut_rgba, int T, int A, float max_nm,
                      float intensity, int mode, uint8_t *out_rgba, int nthreads);
 
+/* ------------------------------------------------------------------ caustic intensity map (f32), "next" row f2 */
+
+/* CausticParams (src/render/caustics.rs:19-56; src/render/shaders/caustics_compute.wgsl:5-22), 64-byte POD */
+typedef struct {
+    uint32_t grid_width, grid_height;
+    float refractive_index, film_thickness_scale, light_dir_x, light_dir_y, light_dir_z, light_intensity;
+    float focal_length, caustic_intensity, caustic_sharpness, branch_threshold, ground_y, bubble_radius, time;
+    uint32_t _padding;
+} orc_caustic_params;
+
+void orc_caustic_params_default(orc_caustic_params *p); /* src/render/caustics.rs:58-79 */
+/* caustics_compute.wgsl::main (:114-126) over the whole grid: gradient, Laplacian and Hessian determinant of the
+ * thickness field (phi wrapped, theta clamped, :29-92) -> focusing x branch x refraction factors (:95-112) */
+void orc_caustic_map(const orc_caustic_params *p, const float *thickness, float *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -144,6 +144,23 @@ if "c5" in which:
            f"LUT build 256x64x64 lambda incl. D2H: {t_lut * 1e3:.3f} ms per build (host wall clock)")
     sim.close()
 
+if "f2" in which or "c3" in which:
+    sim = S.DrainageSimulator(S.SimulationConfig.default(), precision=S.PREC_F32, num_theta=8192, num_phi=16384, h_ref=0.0)
+    sim.upload(synthetic_field(8192, 16384, dtype=np.float32))
+    sim.set_stream(stream.cuda_stream)
+    import ctypes as C
+    from soap_bubble_simulation_b200 import _lib as L
+    cp = L.CausticParamsC()
+    L.check(L.lib().sbx_caustic_params_default(C.byref(cp)))
+
+    def caus(n):
+        for _ in range(n):
+            L.check(L.lib().sbx_drainage_caustics(sim._h, C.byref(cp), None))
+
+    ms = timed(caus, 50)
+    report("f2 caustic map (9-point stencil consumer) of 8192x16384", 8192 * 16384, 8, ms, "first version: direct loads")
+    sim.close()
+
 print("\n| config | ms/step | Gcell/s | B/cell | GB/s | % of measured HBM peak | note |")
 print("|---|---|---|---|---|---|---|")
 for r in rows:

@@ -19,7 +19,7 @@ PREC_F32, PREC_F64, PREC_F64_STRICT = 0, 1, 2
 F32, F64 = 0, 1
 RGB_NONE, RGB_LUT, RGB_EXACT3, RGB_EXACT3_LINEAR, RGB_SCHLICK_WALL = 0, 1, 2, 3, 4
 OUT_RGBA8, OUT_RGB_F32 = 0, 1
-PTR_THICKNESS, PTR_CONCENTRATION, PTR_RGB = 0, 1, 2
+PTR_THICKNESS, PTR_CONCENTRATION, PTR_RGB, PTR_CAUSTICS = 0, 1, 2, 3
 IPC_BYTES = 256
 
 
@@ -38,6 +38,15 @@ class DrainageParamsC(C.Structure):
                 ("gamma_air", C.c_float), ("gamma_reduction", C.c_float),
                 ("surfactant_diffusion", C.c_float), ("marangoni_coeff", C.c_float),
                 ("_padding1", C.c_uint32), ("_padding2", C.c_uint32)]
+
+
+class CausticParamsC(C.Structure):
+    """sbx_caustic_params == CausticParams (src/render/caustics.rs:19-56), 64 bytes."""
+    _fields_ = [("grid_width", C.c_uint32), ("grid_height", C.c_uint32), ("refractive_index", C.c_float),
+                ("film_thickness_scale", C.c_float), ("light_dir_x", C.c_float), ("light_dir_y", C.c_float),
+                ("light_dir_z", C.c_float), ("light_intensity", C.c_float), ("focal_length", C.c_float),
+                ("caustic_intensity", C.c_float), ("caustic_sharpness", C.c_float), ("branch_threshold", C.c_float),
+                ("ground_y", C.c_float), ("bubble_radius", C.c_float), ("time", C.c_float), ("_padding", C.c_uint32)]
 
 
 class DrainageCfgC(C.Structure):
@@ -101,6 +110,8 @@ _SIGS = {
     "sbx_drainage_device_ptr": [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)],
     "sbx_drainage_set_lut": [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float],
     "sbx_drainage_launch_count": [C.c_void_p, C.POINTER(C.c_int64)],
+    "sbx_caustic_params_default": [C.POINTER(CausticParamsC)],
+    "sbx_drainage_caustics": [C.c_void_p, C.POINTER(CausticParamsC), C.c_void_p],
     "sbx_lut_build": [C.c_float, C.c_float, C.c_void_p, C.c_int32],
     "sbx_lut_build_spectral": [C.c_float, C.c_float, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                C.c_float, C.c_void_p, C.c_int32],

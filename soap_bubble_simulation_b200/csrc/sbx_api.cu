@@ -98,7 +98,7 @@ struct sbx_drainage {
     int cur = 0;
 
     void *coefS = nullptr;      // T x 4 per global row
-    float *coefF = nullptr;     // f32 fast path: float4 per global row
+    void *coefF = nullptr;      // TMA fast path: 4 T per global row
     bool use_tma = true;        // SBX_NO_TMA=1 forces the direct-load kernel (A/B measurements)
     float2 *rowSC = nullptr;
     double4 *coefX = nullptr;
@@ -143,6 +143,7 @@ struct sbx_drainage {
     float lut_max_nm = 2000.f;
     bool lut_user = false;
 
+    float *caustic_buf = nullptr;
     sbx_comm *comm = nullptr;
     // peer-memory halo push
     bool peer_enabled = false;
@@ -186,6 +187,7 @@ static void free_all(sbx_drainage *h)
     if (h->peer_up_sync) cudaIpcCloseMemHandle(h->peer_up_sync);
     if (h->peer_dn_sync) cudaIpcCloseMemHandle(h->peer_dn_sync);
     cudaFree(h->sync_dev);
+    cudaFree(h->caustic_buf);
     if (h->mm_host) cudaFreeHost(h->mm_host);
     if (h->scalar_host) cudaFreeHost(h->scalar_host);
     if (h->lut_tex) cudaDestroyTextureObject(h->lut_tex);
@@ -254,7 +256,7 @@ static int32_t upload_tables_t(sbx_drainage *h)
     const double coef = h->density * h->gravity / (3.0 * h->viscosity);  // drainage.rs:305
     const double r2 = h->radius * h->radius;
     std::vector<T> cs((size_t)N * 4, T(0));
-    std::vector<float> cf((size_t)N * 4, 0.f);
+    std::vector<T> cf((size_t)N * 4, T(0));
     std::vector<float2> sc((size_t)N);
     std::vector<double4> cx((size_t)N);
     for (int g = 0; g < N; ++g) {
@@ -269,15 +271,15 @@ static int32_t upload_tables_t(sbx_drainage *h)
             cs[4 * (size_t)g + 2] = (T)(h->diffusion / (r2 * dph * dph * s_safe * s_safe));
             const double A = h->diffusion / (r2 * dth * dth);
             const double B = h->diffusion * (c / s_safe) / (r2 * 2.0 * dth);
-            cf[4 * (size_t)g + 0] = (float)(A + B);
-            cf[4 * (size_t)g + 1] = (float)(A - B);
-            cf[4 * (size_t)g + 2] = (float)(h->diffusion / (r2 * dph * dph * s_safe * s_safe));
-            cf[4 * (size_t)g + 3] = (float)(coef * s);
+            cf[4 * (size_t)g + 0] = (T)(A + B);
+            cf[4 * (size_t)g + 1] = (T)(A - B);
+            cf[4 * (size_t)g + 2] = (T)(h->diffusion / (r2 * dph * dph * s_safe * s_safe));
+            cf[4 * (size_t)g + 3] = (T)(coef * s);
         }
     }
     h->coefA = h->diffusion / (r2 * dth * dth);
     CU(cudaMemcpyAsync(h->coefS, cs.data(), cs.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
-    CU(cudaMemcpyAsync(h->coefF, cf.data(), cf.size() * sizeof(float), cudaMemcpyHostToDevice, h->stream));
+    CU(cudaMemcpyAsync(h->coefF, cf.data(), cf.size() * sizeof(T), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->rowSC, sc.data(), sc.size() * sizeof(float2), cudaMemcpyHostToDevice, h->stream));
     CU(cudaMemcpyAsync(h->coefX, cx.data(), cx.size() * sizeof(double4), cudaMemcpyHostToDevice, h->stream));
     CU(cudaStreamSynchronize(h->stream));  // host vectors go out of scope
@@ -414,7 +416,7 @@ extern "C" int32_t sbx_drainage_create(const sbx_drainage_cfg *cfg, int32_t devi
         for (int i = 0; i < 2; ++i) CU_H(cudaMalloc(&h->conc[i], (size_t)h->total_elems * 4));
     const int N = h->num_theta;
     CU_H(cudaMalloc(&h->coefS, (size_t)N * 4 * h->esz));
-    CU_H(cudaMalloc(&h->coefF, (size_t)N * 4 * sizeof(float)));
+    CU_H(cudaMalloc(&h->coefF, (size_t)N * 4 * h->esz));
     CU_H(cudaMalloc(&h->rowSC, (size_t)N * sizeof(float2)));
     CU_H(cudaMalloc(&h->coefX, (size_t)N * sizeof(double4)));
     CU_H(cudaMalloc(&h->rowW, (size_t)N * sizeof(float4)));
@@ -788,7 +790,7 @@ static void fill_step_args(sbx_drainage *h, StepArgs<T> &a, double dt, const Rgb
     a.in = tbuf<T>(h, h->cur);
     a.out = tbuf<T>(h, 1 - h->cur);
     a.coefS = reinterpret_cast<const T *>(h->coefS);
-    a.coefF = h->coefF;
+    a.coefF = reinterpret_cast<const T *>(h->coefF);
     a.rowSC = h->rowSC;
     a.coefX = h->coefX;
     a.bub = reinterpret_cast<const BubbleParam<T> *>(h->bub);
@@ -819,10 +821,11 @@ static void fill_step_args(sbx_drainage *h, StepArgs<T> &a, double dt, const Rgb
 }
 
 // decide whether this launch writes the pole rows inside the TMA kernel, and which arrival count it waits for
-static void set_pole_fold(sbx_drainage *h, StepArgs<float> &a, bool top, bool bottom)
+template <typename T>
+static void set_pole_fold(sbx_drainage *h, StepArgs<T> &a, bool top, bool bottom)
 {
     a.fold_top = a.fold_bottom = 0;
-    if (!h->use_tma || h->strict || !march_tma_folds_poles(a)) return;
+    if (!h->use_tma || h->strict || !march_tma_folds_poles<T>(a)) return;
     if (top) { a.fold_top = 1; a.pole_want[0] = ++h->fold_count[0]; }
     if (bottom) { a.fold_bottom = 1; a.pole_want[1] = ++h->fold_count[1]; }
 }
@@ -860,9 +863,9 @@ static int32_t step_cpu_sem(sbx_drainage *h, double dt, const RgbArgs &rgb)
     } else {
         a.fronts = ft;
         bool pushed = false;
-        if constexpr (sizeof(T) == 4) set_pole_fold(h, a, has_top, has_bottom);
+        set_pole_fold<T>(h, a, has_top, has_bottom);
         if constexpr (sizeof(T) == 4) {
-            if (h->peer_enabled && h->use_tma && march_tma_supported(a)) {
+            if (h->peer_enabled && h->use_tma && march_tma_supported<T>(a)) {
                 PeerArgs &p = a.peer;
                 p.enabled = 1;
                 p.epoch = ++h->epoch;
@@ -1059,7 +1062,7 @@ static int32_t step_host_pipelined(sbx_drainage *h, double dt, const sbx_view *v
         // the pole rows are written by the launch that holds the ring next to them
         const bool top = c == 0 && h->row_begin == 0;
         const bool bottom = c == (rows - 2) / chunk_rows && h->row_end == h->num_theta;
-        set_pole_fold(h, ac, top, bottom);
+        set_pole_fold<float>(h, ac, top, bottom);
         CU(launch_step<float>(ac, 1, ft.count > 0, false, top, bottom, h->band_rows, h->use_tma, h->stream, &n));
         CU(cudaEventRecord(h->ev_comp[c], h->stream));
         CU(cudaStreamWaitEvent(h->copy_out, h->ev_comp[c], 0));
@@ -1291,6 +1294,10 @@ extern "C" int32_t sbx_drainage_device_ptr(sbx_drainage *h, int32_t kind, void *
         if (!h->rgb_buf) return fail(SBX_ERR_INVALID, "no colour frame has been produced yet");
         *out = h->rgb_buf;
         return SBX_OK;
+    case SBX_PTR_CAUSTICS:
+        if (!h->caustic_buf) return fail(SBX_ERR_INVALID, "no caustic map has been produced yet");
+        *out = h->caustic_buf;
+        return SBX_OK;
     }
     return fail(SBX_ERR_INVALID, "bad pointer kind %d", kind);
 }
@@ -1299,6 +1306,39 @@ extern "C" int32_t sbx_drainage_launch_count(sbx_drainage *h, int64_t *out)
 {
     if (!h || !out) return fail(SBX_ERR_INVALID, "null argument");
     *out = h->launches;
+    return SBX_OK;
+}
+
+// ------------------------------------------------------------------ caustic map (thickness-buffer consumer)
+extern "C" int32_t sbx_caustic_params_default(sbx_caustic_params *p)
+{
+    if (!p) return fail(SBX_ERR_INVALID, "p is null");
+    memset(p, 0, sizeof *p);  // src/render/caustics.rs:58-79
+    p->grid_width = 128; p->grid_height = 64; p->refractive_index = 1.33f; p->film_thickness_scale = 1e6f;
+    p->light_dir_y = -1.0f; p->light_intensity = 1.0f; p->focal_length = 0.1f; p->caustic_intensity = 2.0f;
+    p->caustic_sharpness = 1.5f; p->branch_threshold = 0.001f; p->ground_y = -0.1f; p->bubble_radius = 0.025f;
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_caustics(sbx_drainage *h, const sbx_caustic_params *p, float *host_out)
+{
+    CHECK_H(h);
+    if (!p) return fail(SBX_ERR_INVALID, "p is null");
+    const size_t cells = (size_t)h->batch * h->rows_local * h->num_phi;
+    if (!h->caustic_buf) CU(cudaMalloc(&h->caustic_buf, cells * sizeof(float)));
+    sbx_caustic_params q = *p;
+    q.grid_width = (uint32_t)h->num_phi;
+    q.grid_height = (uint32_t)h->num_theta;
+    const double *href = h->href_zero ? nullptr : h->href_dev;
+    if (h->f64) CU(launch_caustics<double>(tbuf<double>(h, h->cur), h->bubble_stride, h->caustic_buf, h->num_phi, h->num_theta,
+                                           h->row_begin, h->rows_local, h->batch, href, q, h->stream));
+    else CU(launch_caustics<float>(tbuf<float>(h, h->cur), h->bubble_stride, h->caustic_buf, h->num_phi, h->num_theta,
+                                   h->row_begin, h->rows_local, h->batch, href, q, h->stream));
+    h->launches++;
+    if (host_out) {
+        CU(cudaMemcpyAsync(host_out, h->caustic_buf, cells * sizeof(float), cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+    }
     return SBX_OK;
 }
 

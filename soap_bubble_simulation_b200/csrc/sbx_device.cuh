@@ -300,15 +300,15 @@ __device__ __forceinline__ uint32_t pack_rgba8_fast(float r, float g, float b)
     return __byte_perm(rg, ub, 0x5410);                               // bytes: r, g, b, 0xff
 }
 
-template <int MODE>
-__device__ __forceinline__ uint32_t shade_px(float h, float href, float href_u, float colA, float sin_th, float ccy,
+template <int MODE, typename T = float>
+__device__ __forceinline__ uint32_t shade_px(T h, T href, float href_u, float colA, float sin_th, float ccy,
                                              float R, float camR2, const RgbArgs &rgb)
 {
     const float nc = fmaf(sin_th, colA, ccy);      // n . cam
     const float len2 = fmaf(-2.f * R, nc, camR2);  // |cam - R n|^2
     if constexpr (MODE == SBX_RGB_LUT) {
         // u = clamp(d_nm / max_nm), v = clamp(cos theta_i): bubble.wgsl:429-433
-        const float u = __saturatef(fmaf(h, rgb.nm_over_max, href_u));
+        const float u = __saturatef(fmaf((float)h, rgb.nm_over_max, href_u));
         const float v = __saturatef(fabsf(nc - R) * rsqrt_approx(len2));
         const float4 t = tex2D<float4>(rgb.lut, u, v);
         return pack_rgba8_fast(__saturatef(t.x * rgb.intensity), __saturatef(t.y * rgb.intensity),

@@ -74,7 +74,7 @@ struct StepArgs {
     const T *in;   // local buffer incl. ghost row at local row 0
     T *out;
     const T *coefS;          // per global row: {G, B, E, 0} (see host: upload_tables_t)
-    const float *coefF;      // f32 fast path, per global row: {A+B, A-B, E, G}
+    const T *coefF;          // TMA fast path, per global row: {A+B, A-B, E, G}
     const float2 *rowSC;     // per global row: {sin theta, cos theta}
     const double4 *coefX;    // strict mode per global row: {sin theta, cos/sin_safe, sin_safe^2, 0}
     const BubbleParam<T> *bub;

@@ -701,6 +701,80 @@ cudaError_t launch_lut_shade_points(cudaTextureObject_t lut, float inv_max_nm, f
     return cudaGetLastError();
 }
 
+// caustics_compute.wgsl::main (src/render/shaders/caustics_compute.wgsl:29-126): 9-point stencil on the thickness
+// buffer, phi wrapped, theta clamped at the poles (ghost rows supply the neighbours of a latitude band).
+__device__ __forceinline__ float caustic_intensity(float center, float left, float right, float up, float down,
+                                                   float ul, float ur, float dl, float dr, const sbx_caustic_params &p)
+{
+    // h = 1: the divisions by 2h, h^2 and 4h^2 are exact scalings (caustics_compute.wgsl:46-92)
+    const float gx = (right - left) * 0.5f, gy = (down - up) * 0.5f;
+    const float lr = left + right, ud = up + down;
+    const float laplacian = ((lr + up) + down) - 4.0f * center;
+    const float d2x = lr - 2.0f * center, d2y = ud - 2.0f * center;
+    const float dxy = (((dr - dl) - ur) + ul) * 0.25f;
+    const float hessian_det = __fsub_rn(__fmul_rn(d2x, d2y), __fmul_rn(dxy, dxy));
+    const float curvature_factor = -laplacian * p.focal_length;                                   // :95-112
+    const float focusing = rcp_approx(fmaxf(fabsf(1.0f - curvature_factor), 0.01f));
+    const float branch_factor = hessian_det < -p.branch_threshold ? 1.5f : 1.0f;
+    const float grad_mag = sqrt_approx(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)));
+    const float refraction_factor = fmaf(grad_mag, 0.5f, 1.0f);
+    float intensity = focusing * branch_factor * refraction_factor;
+    intensity = ex2_approx(lg2_approx(intensity) * p.caustic_sharpness);  // pow(x, sharpness), x >= 0.005
+    intensity *= p.caustic_intensity;
+    return fminf(fmaxf(intensity, 0.f), 10.f);
+}
+
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) k_caustics(const T *buf, long long bubble_stride, float *out, int num_phi,
+                                                  int num_theta, int row_begin, int rows_local, const double *href,
+                                                  sbx_caustic_params p)
+{
+    const int x0 = (blockIdx.x * blockDim.x + threadIdx.x) * VEC;
+    const int l = blockIdx.y * blockDim.y + threadIdx.y + 1;  // local row, 1..rows_local
+    const int b = blockIdx.z;
+    if (x0 >= num_phi || l > rows_local) return;
+    const T *in = buf + (long long)b * bubble_stride;
+    const float hr = href ? (float)href[b] : 0.f;
+    const int g = row_begin + l - 1;
+    const int lu = g == 0 ? l : l - 1, ld = g == num_theta - 1 ? l : l + 1;  // clamp(y, 0, height-1)
+    const int xl = x0 == 0 ? num_phi - 1 : x0 - 1, xr = x0 + VEC >= num_phi ? 0 : x0 + VEC;
+    float r[3][VEC + 2];  // rows up / centre / down: [left edge, VEC cells, right edge]
+    const int rows[3] = {lu, l, ld};
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const T *row = in + (long long)rows[k] * num_phi;
+        const Vec<T, VEC> v = ldv<T, VEC>(row + x0);
+        r[k][0] = (float)__ldg(row + xl) + hr;
+#pragma unroll
+        for (int j = 0; j < VEC; ++j) r[k][1 + j] = (float)v.v[j] + hr;
+        r[k][VEC + 1] = (float)__ldg(row + xr) + hr;
+    }
+    float o[VEC];
+#pragma unroll
+    for (int j = 0; j < VEC; ++j)
+        o[j] = caustic_intensity(r[1][1 + j], r[1][j], r[1][2 + j], r[0][1 + j], r[2][1 + j], r[0][j], r[0][2 + j],
+                                 r[2][j], r[2][2 + j], p);
+    float *dst = out + ((long long)b * rows_local + (l - 1)) * num_phi + x0;
+    if constexpr (VEC == 4) *reinterpret_cast<float4 *>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+    else if constexpr (VEC == 2) *reinterpret_cast<float2 *>(dst) = make_float2(o[0], o[1]);
+    else dst[0] = o[0];
+}
+
+template <typename T>
+cudaError_t launch_caustics(const T *buf, long long bubble_stride, float *out, int num_phi, int num_theta, int row_begin,
+                            int rows_local, int batch, const double *href, const sbx_caustic_params &p, cudaStream_t st)
+{
+    constexpr int VECW = 16 / (int)sizeof(T);
+    const bool vec_ok = num_phi % VECW == 0;
+    const int packets = vec_ok ? num_phi / VECW : num_phi;
+    const dim3 block(64, 4), grid((unsigned)((packets + 63) / 64), (unsigned)((rows_local + 3) / 4), (unsigned)batch);
+    if (vec_ok) k_caustics<T, VECW><<<grid, block, 0, st>>>(buf, bubble_stride, out, num_phi, num_theta, row_begin, rows_local, href, p);
+    else k_caustics<T, 1><<<grid, block, 0, st>>>(buf, bubble_stride, out, num_phi, num_theta, row_begin, rows_local, href, p);
+    return cudaGetLastError();
+}
+template cudaError_t launch_caustics<float>(const float *, long long, float *, int, int, int, int, int, const double *, const sbx_caustic_params &, cudaStream_t);
+template cudaError_t launch_caustics<double>(const double *, long long, float *, int, int, int, int, int, const double *, const sbx_caustic_params &, cudaStream_t);
+
 // per-column view term A_j = cos(phi_j) cam_x + sin(phi_j) cam_z, evaluated in f64
 __global__ void k_col_view(float *colA, int num_phi, double cam_x, double cam_z)
 {
@@ -779,11 +853,11 @@ cudaError_t launch_step(StepArgs<T> a, int batch, bool tfe, bool strict, bool ha
     cudaError_t e = cudaSuccess;
     if (rows > 0) {
         bool done = false;
-        if constexpr (sizeof(T) == 4) {
-            if (!strict && use_tma && march_tma_supported(a)) {
+        {
+            if (!strict && use_tma && march_tma_supported<T>(a)) {
                 int slots = 0;
                 // a.fold_top / a.fold_bottom / a.pole_want were set by the caller iff march_tma_folds_poles(a)
-                e = launch_march_tma(a, batch, tfe, band_rows_req, st, &slots);
+                e = launch_march_tma<T>(a, batch, tfe, band_rows_req, st, &slots);
                 a.pole_slots = slots;
                 done = true;
                 if (a.fold_top) has_top = false;  // the strips of the ring rows wrote the pole rows themselves

@@ -11,10 +11,13 @@ template <typename T>
 cudaError_t launch_step(StepArgs<T> a, int batch, bool tfe, bool strict, bool has_top, bool has_bottom,
                         int band_rows_req, bool use_tma, cudaStream_t st, int *launches);
 
-// f32 fast path (sbx_march_tma.cu): TMA-staged ring, RGBA8 or no colour, num_phi % 4 == 0
-bool march_tma_supported(const StepArgs<float> &a);
-bool march_tma_folds_poles(const StepArgs<float> &a);
-cudaError_t launch_march_tma(StepArgs<float> a, int batch, bool tfe, int band_rows_req, cudaStream_t st, int *pole_slots);
+// fast path (sbx_march_tma.cu): TMA-staged ring, f32 or f64 (non-strict), RGBA8 or no colour, whole 16-byte packets
+template <typename T>
+bool march_tma_supported(const StepArgs<T> &a);
+template <typename T>
+bool march_tma_folds_poles(const StepArgs<T> &a);
+template <typename T>
+cudaError_t launch_march_tma(StepArgs<T> a, int batch, bool tfe, int band_rows_req, cudaStream_t st, int *pole_slots);
 
 template <typename T>
 cudaError_t launch_tfe_pass(T *buf, long long bubble_stride, int num_phi, int row_begin, int rows_local,
@@ -45,6 +48,9 @@ cudaError_t launch_interference_terms(double n_film, const double *d_nm, const d
                                       double *out_cos_t, double *out_fresnel, double *out_intensity, cudaStream_t st);
 cudaError_t launch_lut_shade_points(cudaTextureObject_t lut, float inv_max_nm, float intensity, const float *d_nm,
                                     const float *cos_theta, size_t n, float *rgb, cudaStream_t st);
+template <typename T>
+cudaError_t launch_caustics(const T *buf, long long bubble_stride, float *out, int num_phi, int num_theta, int row_begin,
+                            int rows_local, int batch, const double *href, const sbx_caustic_params &p, cudaStream_t st);
 cudaError_t launch_col_view(float *colA, int num_phi, double cam_x, double cam_z, cudaStream_t st);
 
 }  // namespace sbx

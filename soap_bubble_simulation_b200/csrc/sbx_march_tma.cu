@@ -20,7 +20,6 @@ namespace {
 
 constexpr int kStages = 3;        // ring depth
 constexpr int kRowsPerStage = 3;  // theta rows per stage == the unroll of the three-row register window
-constexpr int kHalo = 4;          // floats each side (16 B keeps every bulk copy aligned)
 
 __device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -93,30 +92,42 @@ __device__ __forceinline__ void wait_neighbour(const unsigned long long *flag, u
     asm volatile("fence.proxy.async;" ::: "memory");  // the rows the neighbour pushed are read by TMA next
 }
 
+template <typename T, int VEC>
 struct Row {
-    float v[4];
-    float eL, eR;
+    T v[VEC];
+    T eL, eR;
 };
+
+template <typename T> __device__ __forceinline__ T tmax(T a, T b);
+template <> __device__ __forceinline__ float tmax<float>(float a, float b) { return fmaxf(a, b); }
+template <> __device__ __forceinline__ double tmax<double>(double a, double b) { return fmax(a, b); }
+
+template <typename T> struct MinBlocks { static constexpr int value = 4; };
+template <> struct MinBlocks<double> { static constexpr int value = 3; };
 
 }  // namespace
 
-template <int MODE, bool TFE>
-__global__ void __launch_bounds__(288, 4) k_march_tma(const StepArgs<float> a)
+// T = float (VEC 4) or double (VEC 2): a thread always owns one 16-byte packet of a row, a strip is 16*C bytes
+// wide plus a 16-byte halo each side, so ring geometry and copy sizes are identical for both types.
+template <typename T, int MODE, bool TFE>
+__global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const StepArgs<T> a)
 {
+    constexpr int VEC = 16 / (int)sizeof(T);
+    constexpr int HALO = VEC;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double warp_part[8];
     const int C = blockDim.x - 32;  // consumer threads
     const int N = a.num_phi;
-    const int strip_w_max = 4 * C;
+    const int strip_w_max = VEC * C;
     const int c0 = blockIdx.x * strip_w_max;
-    const int w = min(strip_w_max, N - c0);    // multiple of 4
-    const int rowf = strip_w_max + 2 * kHalo;  // floats per ring row
-    float *ring = reinterpret_cast<float *>(smem_raw);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStages * kRowsPerStage * rowf * sizeof(float));
+    const int w = min(strip_w_max, N - c0);   // multiple of VEC
+    const int rowf = strip_w_max + 2 * HALO;  // elements per ring row
+    T *ring = reinterpret_cast<T *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStages * kRowsPerStage * rowf * sizeof(T));
     uint64_t *empty = full + kStages;
 
     const int b = blockIdx.z;
-    const float *in = a.in + (long long)b * a.bubble_stride;
+    const T *in = a.in + (long long)b * a.bubble_stride;
     const int l0 = a.l_first + blockIdx.y * a.band_rows;
     const int l1 = min(l0 + a.band_rows - 1, a.l_last);
     if (l0 > l1) return;
@@ -144,8 +155,8 @@ __global__ void __launch_bounds__(288, 4) k_march_tma(const StepArgs<float> a)
             const bool touch_top = a.peer.enabled && a.peer.up_ghost && l0 == 1;
             const bool touch_bot = a.peer.enabled && a.peer.dn_ghost && l1 == a.l_last && a.peer.push_dn_grow >= 0;
             const bool wrapL = c0 == 0, wrapR = c0 + w >= N;
-            const uint32_t main_floats = (uint32_t)w + (wrapL ? 0 : kHalo) + (wrapR ? 0 : kHalo);
-            const uint32_t row_bytes = ((uint32_t)w + 2 * kHalo) * 4u;
+            const uint32_t main_elems = (uint32_t)w + (wrapL ? 0 : HALO) + (wrapR ? 0 : HALO);
+            const uint32_t row_bytes = ((uint32_t)w + 2 * HALO) * (uint32_t)sizeof(T);
             for (int c = 0; c < nchunks; ++c) {
                 const int s = c % kStages;
                 if (c >= kStages) mbar_wait(&empty[s], (uint32_t)(((c / kStages) - 1) & 1));
@@ -156,12 +167,13 @@ __global__ void __launch_bounds__(288, 4) k_march_tma(const StepArgs<float> a)
                     // ghost rows are written by the neighbours' previous step: wait for it before reading them
                     if (r == 0 && touch_top) wait_neighbour(a.peer.flag_from_up, a.peer.epoch - 1, a.peer.status);
                     if (r == rows_load - 1 && touch_bot) wait_neighbour(a.peer.flag_from_dn, a.peer.epoch - 1, a.peer.status);
-                    const float *grow_ptr = in + (long long)(l0 - 1 + r) * N;
-                    float *dst = ring + ((size_t)s * kRowsPerStage + (r - r_begin)) * rowf;
-                    // ring row layout: [0,4) left halo | [4, 4+w) main | [4+w, 8+w) right halo
-                    tma_bulk_g2s(dst + (wrapL ? kHalo : 0), grow_ptr + c0 - (wrapL ? 0 : kHalo), main_floats * 4u, &full[s]);
-                    if (wrapL) tma_bulk_g2s(dst, grow_ptr + (N - kHalo), kHalo * 4u, &full[s]);           // seam
-                    if (wrapR) tma_bulk_g2s(dst + kHalo + w, grow_ptr, kHalo * 4u, &full[s]);             // seam
+                    const T *grow_ptr = in + (long long)(l0 - 1 + r) * N;
+                    T *dst = ring + ((size_t)s * kRowsPerStage + (r - r_begin)) * rowf;
+                    // ring row layout: [0,HALO) left halo | [HALO, HALO+w) main | [HALO+w, 2 HALO+w) right halo
+                    tma_bulk_g2s(dst + (wrapL ? HALO : 0), grow_ptr + c0 - (wrapL ? 0 : HALO),
+                                 main_elems * (uint32_t)sizeof(T), &full[s]);
+                    if (wrapL) tma_bulk_g2s(dst, grow_ptr + (N - HALO), 16u, &full[s]);       // periodic seam
+                    if (wrapR) tma_bulk_g2s(dst + HALO + w, grow_ptr, 16u, &full[s]);         // periodic seam
                 }
             }
         }
@@ -171,83 +183,106 @@ __global__ void __launch_bounds__(288, 4) k_march_tma(const StepArgs<float> a)
     // ---------------------------------------------------------------- consumers
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const int jloc = tid * 4;  // column offset inside the strip
+    const int jloc = tid * VEC;  // column offset inside the strip
     const bool active = jloc < w;
     const int jc = c0 + (active ? jloc : 0);
-    const int soff = kHalo + (active ? jloc : 0);  // float offset of this thread's packet in a ring row
-    float *out = a.out + (long long)b * a.bubble_stride;
-    const BubbleParam<float> bp = a.bub[b];
-    const float href = bp.h_ref;
-    const float neg_href = -href;
-    const float dscale = bp.diff_scale;
-    const float dt = a.dt;
-    const float crit = a.crit;
+    const int soff = HALO + (active ? jloc : 0);  // element offset of this thread's packet in a ring row
+    T *out = a.out + (long long)b * a.bubble_stride;
+    const BubbleParam<T> bp = a.bub[b];
+    const T href = bp.h_ref;
+    const T neg_href = -href;
+    const T dscale = bp.diff_scale;
+    const T dt = a.dt;
+    const T crit = a.crit;
 
-    float colA[4] = {0.f, 0.f, 0.f, 0.f};
+    float colA[VEC];
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) colA[k] = 0.f;
     if constexpr (MODE != SBX_RGB_NONE) {
-        const float4 ca = __ldg(reinterpret_cast<const float4 *>(a.rgb.colA + jc));
-        colA[0] = ca.x; colA[1] = ca.y; colA[2] = ca.z; colA[3] = ca.w;
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) colA[k] = __ldg(a.rgb.colA + jc + k);
     }
     const float Rv = bp.radius;
     const float camR2 = a.rgb.cam2 + Rv * Rv;
-    const float href_u = href * a.rgb.nm_over_max;
+    const float href_u = (float)href * a.rgb.nm_over_max;
 
     // Ring bookkeeping is static: a stage holds exactly the three rows one trip of the unrolled loop pulls
     // (sub-step A takes slot 2 and releases the stage, B waits for the next stage and takes slot 0, C takes
     // slot 1), so no per-row counters or modulo arithmetic are needed.
     int stage = 0;
     uint32_t full_parity = 0;
-    const float *ring_t = ring + soff;                 // this thread's packet in ring row 0
-    const uint32_t stage_floats = kRowsPerStage * rowf;
-    const float *stage_p = ring_t;                     // this thread's packet in slot 0 of the current stage
+    const T *ring_t = ring + soff;                 // this thread's packet in ring row 0
+    const uint32_t stage_elems = kRowsPerStage * rowf;
+    const T *stage_p = ring_t;                     // this thread's packet in slot 0 of the current stage
+    using RowT = Row<T, VEC>;
 
-    auto load_slot = [&](Row &r, int slot) {
-        const float *src = stage_p + slot * rowf;
-        const float4 q = *reinterpret_cast<const float4 *>(src);
-        r.v[0] = q.x; r.v[1] = q.y; r.v[2] = q.z; r.v[3] = q.w;
+    auto load_slot = [&](RowT &r, int slot) {
+        const T *src = stage_p + slot * rowf;
+        if constexpr (VEC == 4) {
+            const float4 q = *reinterpret_cast<const float4 *>(src);
+            r.v[0] = q.x; r.v[1] = q.y; r.v[2] = q.z; r.v[3] = q.w;
+        } else {
+            const double2 q = *reinterpret_cast<const double2 *>(src);
+            r.v[0] = q.x; r.v[1] = q.y;
+        }
         r.eL = src[-1];
-        r.eR = src[4];
+        r.eR = src[VEC];
     };
     auto release_stage = [&]() {
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[stage]);  // every lane of this warp has read the stage
         if (++stage == kStages) { stage = 0; full_parity ^= 1u; stage_p = ring_t; }
-        else stage_p += stage_floats;
+        else stage_p += stage_elems;
+    };
+    auto store_px = [&](uint32_t *dst, const uint32_t *px) {
+        if constexpr (VEC == 4) *reinterpret_cast<uint4 *>(dst) = make_uint4(px[0], px[1], px[2], px[3]);
+        else *reinterpret_cast<uint2 *>(dst) = make_uint2(px[0], px[1]);
     };
 
     // running output pointers (bumped by one row per sub-step)
-    float *out_p = out + (long long)l0 * N + jc;
+    T *out_p = out + (long long)l0 * N + jc;
     uint32_t *rgb_p = reinterpret_cast<uint32_t *>(a.rgb.out) + (long long)b * a.rgb_bubble_stride +
                       (long long)(l0 - 1) * N + jc;
-    const float4 *cf_p = reinterpret_cast<const float4 *>(a.coefF) + (a.row_begin + l0 - 1);
+    const T *cf_p = a.coefF + 4 * (long long)(a.row_begin + l0 - 1);
     const float2 *sc_p = a.rowSC + (a.row_begin + l0 - 1);
     int grow = a.row_begin + l0 - 1;
     const int ring_top = 1, ring_bot = a.num_theta - 2;
     const bool has_ring = (grow <= ring_top && ring_top <= a.row_begin + l1 - 1) ||
                           (grow <= ring_bot && ring_bot <= a.row_begin + l1 - 1);  // block-uniform
 
-    auto compute_row = [&](const Row &up, const Row &cur, const Row &dn) {
-        const float4 cf = __ldg(cf_p);  // {A+B, A-B, E, G}
-        float nw[4];
+    auto compute_row = [&](const RowT &up, const RowT &cur, const RowT &dn) {
+        T cApB, cAmB, cE, cG;  // {A+B, A-B, E, G}
+        if constexpr (VEC == 4) {
+            const float4 cf = __ldg(reinterpret_cast<const float4 *>(cf_p));
+            cApB = cf.x; cAmB = cf.y; cE = cf.z; cG = cf.w;
+        } else {
+            const double2 c01 = __ldg(reinterpret_cast<const double2 *>(cf_p));
+            const double2 c23 = __ldg(reinterpret_cast<const double2 *>(cf_p) + 1);
+            cApB = c01.x; cAmB = c01.y; cE = c23.x; cG = c23.y;
+        }
+        Vec<T, VEC> nw;
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            const float h = cur.v[k];
-            const float lf = k == 0 ? cur.eL : cur.v[k - 1];
-            const float rt = k == 3 ? cur.eR : cur.v[k + 1];
-            const float habs = h + href;
+        for (int k = 0; k < VEC; ++k) {
+            const T h = cur.v[k];
+            const T lf = k == 0 ? cur.eL : cur.v[k - 1];
+            const T rt = k == VEC - 1 ? cur.eR : cur.v[k + 1];
+            const T habs = h + href;
             // A (dN + dS) + B (dN - dS) + E (dE + dW) with neighbour-minus-centre differences
-            float diff = cf.x * (dn.v[k] - h);
-            diff = fmaf(cf.y, up.v[k] - h, diff);
-            diff = fmaf(cf.z, (rt - h) + (lf - h), diff);
-            const float g3 = (cf.w * habs) * (habs * habs);
-            const float rate = fmaf(dscale, diff, -g3);
-            float hn = fmaf(dt, rate, h);
-            hn = fmaxf(hn, neg_href);      // max(h_abs, 0), drainage.rs:378
-            nw[k] = habs < crit ? h : hn;  // below-critical cells keep their value, drainage.rs:331-333
+            T diff = cApB * (dn.v[k] - h);
+            diff = fma(cAmB, up.v[k] - h, diff);
+            diff = fma(cE, (rt - h) + (lf - h), diff);
+            const T g3 = (cG * habs) * (habs * habs);
+            const T rate = fma(dscale, diff, -g3);
+            T hn = fma(dt, rate, h);
+            hn = tmax<T>(hn, neg_href);      // max(h_abs, 0), drainage.rs:378
+            nw.v[k] = habs < crit ? h : hn;  // below-critical cells keep their value, drainage.rs:331-333
         }
         if (has_ring && (grow == ring_top || grow == ring_bot)) {  // ring sums for the poles (pre-TFE)
             double s = 0.0;
-            if (active) s = ((double)nw[0] + (double)nw[1]) + ((double)nw[2] + (double)nw[3]);
+            if (active) {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) s += (double)nw.v[k];
+            }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
             if (lane == 0) warp_part[tid >> 5] = s;
@@ -268,36 +303,36 @@ __global__ void __launch_bounds__(288, 4) k_march_tma(const StepArgs<float> a)
             const unsigned rm = front_row_mask(a.fronts, grow);
             if (rm) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    if (front_hit(a.fronts, rm, jc + k)) nw[k] = fmaf(-(nw[k] + href), a.tfe_rdt, nw[k]);
+                for (int k = 0; k < VEC; ++k)
+                    if (front_hit(a.fronts, rm, jc + k)) nw.v[k] = fma(-(nw.v[k] + href), a.tfe_rdt, nw.v[k]);
             }
         }
         if (active) {
-            *reinterpret_cast<float4 *>(out_p) = make_float4(nw[0], nw[1], nw[2], nw[3]);
+            stv<T, VEC>(out_p, nw);
             if (a.peer.enabled) {  // boundary rows also land in the neighbours' ghost rows (peer stores over NVLink)
-                if (grow == a.peer.push_up_grow)
-                    *reinterpret_cast<float4 *>(a.peer.up_ghost + jc) = make_float4(nw[0], nw[1], nw[2], nw[3]);
-                if (grow == a.peer.push_dn_grow)
-                    *reinterpret_cast<float4 *>(a.peer.dn_ghost + jc) = make_float4(nw[0], nw[1], nw[2], nw[3]);
+                if constexpr (sizeof(T) == 4) {
+                    if (grow == a.peer.push_up_grow) stv<T, VEC>(reinterpret_cast<T *>(a.peer.up_ghost) + jc, nw);
+                    if (grow == a.peer.push_dn_grow) stv<T, VEC>(reinterpret_cast<T *>(a.peer.dn_ghost) + jc, nw);
+                }
             }
             if constexpr (MODE != SBX_RGB_NONE) {
                 const float2 sc = __ldg(sc_p);
                 const float ccy = sc.y * a.rgb.cam_y;
-                uint32_t px[4];
+                uint32_t px[VEC];
 #pragma unroll
-                for (int k = 0; k < 4; ++k)
-                    px[k] = shade_px<MODE>(nw[k], href, href_u, colA[k], sc.x, ccy, Rv, camR2, a.rgb);
-                *reinterpret_cast<uint4 *>(rgb_p) = make_uint4(px[0], px[1], px[2], px[3]);
+                for (int k = 0; k < VEC; ++k)
+                    px[k] = shade_px<MODE, T>(nw.v[k], href, href_u, colA[k], sc.x, ccy, Rv, camR2, a.rgb);
+                store_px(rgb_p, px);
             }
         }
         out_p += N;
         rgb_p += N;
-        ++cf_p;
+        cf_p += 4;
         ++sc_p;
         ++grow;
     };
 
-    Row r0, r1, r2;
+    RowT r0, r1, r2;
     mbar_wait(&full[0], 0);
     load_slot(r0, 0);
     load_slot(r1, 1);
@@ -337,31 +372,32 @@ __global__ void __launch_bounds__(288, 4) k_march_tma(const StepArgs<float> a)
                 warp_part[0] = t / (double)N;
             }
             bar_consumers(C);
-            const float v = (float)warp_part[0];
+            const T v = (T)warp_part[0];
             bar_consumers(C);
             if (active) {
                 const int prow = which == 0 ? 0 : a.num_theta - 1;
                 const int pl = prow - a.row_begin + 1;
-                float pv[4] = {v, v, v, v};
+                Vec<T, VEC> pv;
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) pv.v[k] = v;
                 if constexpr (TFE) {
                     const unsigned rm = front_row_mask(a.fronts, prow);
                     if (rm) {
 #pragma unroll
-                        for (int k = 0; k < 4; ++k)
-                            if (front_hit(a.fronts, rm, jc + k)) pv[k] = fmaf(-(pv[k] + href), a.tfe_rdt, pv[k]);
+                        for (int k = 0; k < VEC; ++k)
+                            if (front_hit(a.fronts, rm, jc + k)) pv.v[k] = fma(-(pv.v[k] + href), a.tfe_rdt, pv.v[k]);
                     }
                 }
-                *reinterpret_cast<float4 *>(out + (long long)pl * N + jc) = make_float4(pv[0], pv[1], pv[2], pv[3]);
+                stv<T, VEC>(out + (long long)pl * N + jc, pv);
                 if constexpr (MODE != SBX_RGB_NONE) {
                     const float2 sc = __ldg(a.rowSC + prow);
                     const float ccy = sc.y * a.rgb.cam_y;
-                    uint32_t px[4];
+                    uint32_t px[VEC];
 #pragma unroll
-                    for (int k = 0; k < 4; ++k)
-                        px[k] = shade_px<MODE>(pv[k], href, href_u, colA[k], sc.x, ccy, Rv, camR2, a.rgb);
-                    uint32_t *o = reinterpret_cast<uint32_t *>(a.rgb.out) + (long long)b * a.rgb_bubble_stride +
-                                  (long long)(pl - 1) * N + jc;
-                    *reinterpret_cast<uint4 *>(o) = make_uint4(px[0], px[1], px[2], px[3]);
+                    for (int k = 0; k < VEC; ++k)
+                        px[k] = shade_px<MODE, T>(pv.v[k], href, href_u, colA[k], sc.x, ccy, Rv, camR2, a.rgb);
+                    store_px(reinterpret_cast<uint32_t *>(a.rgb.out) + (long long)b * a.rgb_bubble_stride +
+                                 (long long)(pl - 1) * N + jc, px);
                 }
             }
         }
@@ -391,7 +427,7 @@ __global__ void __launch_bounds__(288, 4) k_march_tma(const StepArgs<float> a)
 
 static size_t march_tma_smem_bytes(int consumers)
 {
-    return (size_t)kStages * kRowsPerStage * (4 * consumers + 2 * kHalo) * sizeof(float) + 2 * kStages * sizeof(uint64_t);
+    return (size_t)kStages * kRowsPerStage * (16 * consumers + 32) + 2 * kStages * sizeof(uint64_t);
 }
 
 static bool use_pdl()
@@ -400,15 +436,15 @@ static bool use_pdl()
     return on;
 }
 
-template <int MODE, bool TFE>
-static cudaError_t launch_one(const StepArgs<float> &a, dim3 grid, dim3 block, size_t smem, cudaStream_t st)
+template <typename T, int MODE, bool TFE>
+static cudaError_t launch_one(const StepArgs<T> &a, dim3 grid, dim3 block, size_t smem, cudaStream_t st)
 {
     // ask for the large shared-memory carveout once per device so that four 37 KB rings fit on an SM
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_march_tma<MODE, TFE>, cudaFuncAttributePreferredSharedMemoryCarveout,
+        cudaError_t e = cudaFuncSetAttribute(k_march_tma<T, MODE, TFE>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                              (int)cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         configured[dev] = true;
@@ -424,51 +460,59 @@ static cudaError_t launch_one(const StepArgs<float> &a, dim3 grid, dim3 block, s
     cfg.attrs = attr;
     // PDL pays when the grid has several waves (measured: +1 % at 8192x16384, -10 % at the single-wave 2048x4096)
     cfg.numAttrs = (use_pdl() && (size_t)grid.x * grid.y * grid.z >= 1184) ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, k_march_tma<MODE, TFE>, a);
+    return cudaLaunchKernelEx(&cfg, k_march_tma<T, MODE, TFE>, a);
 }
 
-template <bool TFE>
-static cudaError_t launch_tma_mode(const StepArgs<float> &a, dim3 grid, dim3 block, size_t smem, cudaStream_t st)
+template <typename T, bool TFE>
+static cudaError_t launch_tma_mode(const StepArgs<T> &a, dim3 grid, dim3 block, size_t smem, cudaStream_t st)
 {
     switch (a.rgb.mode) {
-    case SBX_RGB_NONE: return launch_one<SBX_RGB_NONE, TFE>(a, grid, block, smem, st);
-    case SBX_RGB_LUT: return launch_one<SBX_RGB_LUT, TFE>(a, grid, block, smem, st);
-    case SBX_RGB_EXACT3: return launch_one<SBX_RGB_EXACT3, TFE>(a, grid, block, smem, st);
-    case SBX_RGB_EXACT3_LINEAR: return launch_one<SBX_RGB_EXACT3_LINEAR, TFE>(a, grid, block, smem, st);
-    case SBX_RGB_SCHLICK_WALL: return launch_one<SBX_RGB_SCHLICK_WALL, TFE>(a, grid, block, smem, st);
+    case SBX_RGB_NONE: return launch_one<T, SBX_RGB_NONE, TFE>(a, grid, block, smem, st);
+    case SBX_RGB_LUT: return launch_one<T, SBX_RGB_LUT, TFE>(a, grid, block, smem, st);
+    case SBX_RGB_EXACT3: return launch_one<T, SBX_RGB_EXACT3, TFE>(a, grid, block, smem, st);
+    case SBX_RGB_EXACT3_LINEAR: return launch_one<T, SBX_RGB_EXACT3_LINEAR, TFE>(a, grid, block, smem, st);
+    case SBX_RGB_SCHLICK_WALL: return launch_one<T, SBX_RGB_SCHLICK_WALL, TFE>(a, grid, block, smem, st);
     default: return cudaErrorInvalidValue;
     }
 }
 
-// The fast path handles: f32 storage, non-strict, RGBA8 output (or no colour), num_phi % 4 == 0.
-bool march_tma_supported(const StepArgs<float> &a)
+// The fast path handles: non-strict f32/f64 storage, RGBA8 output (or no colour), rows of whole 16-byte packets.
+template <typename T>
+bool march_tma_supported(const StepArgs<T> &a)
 {
-    if (a.num_phi % 4 != 0 || a.num_phi < 128) return false;
+    constexpr int VEC = 16 / (int)sizeof(T);
+    if (a.num_phi % VEC != 0 || a.num_phi < 32 * VEC) return false;
     if (a.rgb.mode != SBX_RGB_NONE && a.rgb.format != SBX_OUT_RGBA8) return false;
     return true;
 }
 
+template <typename T>
 static int tma_consumers(int num_phi)
 {
+    constexpr int VEC = 16 / (int)sizeof(T);
     int consumers = 256;
-    while (consumers > 32 && consumers * 2 >= num_phi) consumers >>= 1;  // narrow grids: fewer, fuller CTAs
+    while (consumers > 32 && consumers * VEC / 2 >= num_phi) consumers >>= 1;  // narrow grids: fewer, fuller CTAs
     return consumers;
 }
 
 // The pole rows are folded into the kernel only when all strips of a ring are certainly co-resident (they
 // wait for each other); otherwise k_poles finishes them.
-bool march_tma_folds_poles(const StepArgs<float> &a)
+template <typename T>
+bool march_tma_folds_poles(const StepArgs<T> &a)
 {
-    if (!march_tma_supported(a) || a.l_last < a.l_first) return false;
-    const int strip = tma_consumers(a.num_phi) * 4;
+    constexpr int VEC = 16 / (int)sizeof(T);
+    if (!march_tma_supported<T>(a) || a.l_last < a.l_first) return false;
+    const int strip = tma_consumers<T>(a.num_phi) * VEC;
     return (a.num_phi + strip - 1) / strip <= 128;
 }
 
-cudaError_t launch_march_tma(StepArgs<float> a, int batch, bool tfe, int band_rows_req, cudaStream_t st, int *pole_slots)
+template <typename T>
+cudaError_t launch_march_tma(StepArgs<T> a, int batch, bool tfe, int band_rows_req, cudaStream_t st, int *pole_slots)
 {
+    constexpr int VEC = 16 / (int)sizeof(T);
     const int rows = a.l_last - a.l_first + 1;
-    const int consumers = tma_consumers(a.num_phi);
-    const int strip = consumers * 4;
+    const int consumers = tma_consumers<T>(a.num_phi);
+    const int strip = consumers * VEC;
     const int gx = (a.num_phi + strip - 1) / strip;
     int band_rows = band_rows_req > 0 ? band_rows_req : 24;  // multiple of the 3-row ring stage; measured best at 8192x16384
     if (band_rows > rows) band_rows = rows;
@@ -478,7 +522,14 @@ cudaError_t launch_march_tma(StepArgs<float> a, int batch, bool tfe, int band_ro
     *pole_slots = gx;
     const dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)batch), block((unsigned)(consumers + 32));
     const size_t smem = march_tma_smem_bytes(consumers);
-    return tfe ? launch_tma_mode<true>(a, grid, block, smem, st) : launch_tma_mode<false>(a, grid, block, smem, st);
+    return tfe ? launch_tma_mode<T, true>(a, grid, block, smem, st) : launch_tma_mode<T, false>(a, grid, block, smem, st);
 }
+
+template bool march_tma_supported<float>(const StepArgs<float> &);
+template bool march_tma_supported<double>(const StepArgs<double> &);
+template bool march_tma_folds_poles<float>(const StepArgs<float> &);
+template bool march_tma_folds_poles<double>(const StepArgs<double> &);
+template cudaError_t launch_march_tma<float>(StepArgs<float>, int, bool, int, cudaStream_t, int *);
+template cudaError_t launch_march_tma<double>(StepArgs<double>, int, bool, int, cudaStream_t, int *);
 
 }  // namespace sbx

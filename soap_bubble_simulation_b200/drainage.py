@@ -219,6 +219,18 @@ class _DeviceField:
             host_out_rgb.ctypes.data if host_out_rgb is not None else None))
         self._host_stale = True
 
+    def caustic_map(self, **params) -> np.ndarray:
+        """CausticRenderer::compute (src/render/caustics.rs:441-457, caustics_compute.wgsl:114-126) on the latest
+        thickness buffer; keyword arguments override CausticParams::default (caustics.rs:58-79).  Returns the
+        (batch, rows, num_phi) float32 caustic intensity map."""
+        p = L.CausticParamsC()
+        L.check(L.lib().sbx_caustic_params_default(C.byref(p)))
+        for k, v in params.items():
+            setattr(p, k, v)
+        out = np.empty(self._shape(), dtype=np.float32)
+        L.check(L.lib().sbx_drainage_caustics(self._h, C.byref(p), out.ctypes.data))
+        return out
+
     def attach_comm(self, comm) -> None:
         L.check(L.lib().sbx_drainage_attach_comm(self._h, comm._c))
         self._comm = comm

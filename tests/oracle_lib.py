@@ -39,6 +39,14 @@ class WgslParams(C.Structure):
                 ("_padding1", C.c_uint32), ("_padding2", C.c_uint32)]
 
 
+class CausticParams(C.Structure):
+    _fields_ = [("grid_width", C.c_uint32), ("grid_height", C.c_uint32), ("refractive_index", C.c_float),
+                ("film_thickness_scale", C.c_float), ("light_dir_x", C.c_float), ("light_dir_y", C.c_float),
+                ("light_dir_z", C.c_float), ("light_intensity", C.c_float), ("focal_length", C.c_float),
+                ("caustic_intensity", C.c_float), ("caustic_sharpness", C.c_float), ("branch_threshold", C.c_float),
+                ("ground_y", C.c_float), ("bubble_radius", C.c_float), ("time", C.c_float), ("_padding", C.c_uint32)]
+
+
 class Interference(C.Structure):
     _fields_ = [("n_film", C.c_double), ("n_medium", C.c_double), ("wavelengths_nm", C.c_double * 3)]
 
@@ -100,6 +108,8 @@ def lib() -> C.CDLL:
         "orc_lut_shade": (None, [p, i, i, f, f, f, f, C.POINTER(C.c_float)]),
         "orc_lut_shade_w": (None, [p, i, i, f, f, f, f, i, C.POINTER(C.c_float)]),
         "orc_view_cos": (d, [d, d, d, dp]),
+        "orc_caustic_params_default": (None, [C.POINTER(CausticParams)]),
+        "orc_caustic_map": (None, [C.POINTER(CausticParams), p, p]),
         "orc_shade_field": (None, [p, i, i, i, i, d, dp, d, p, i, i, f, f, i, p, i]),
     }
     for name, (res, args) in sig.items():
@@ -329,4 +339,19 @@ def shade_field(h: np.ndarray, num_theta: int, row0: int, radius, cam, n_film=1.
     A, T = lut.shape[0], lut.shape[1]
     lib().orc_shade_field(h.ctypes.data, num_theta, nphi, row0, rows, radius, a, n_film, lut.ctypes.data, T, A,
                           max_nm, intensity, mode, out.ctypes.data, threads)
+    return out
+
+
+def caustic_params(**kw) -> CausticParams:
+    p = CausticParams()
+    lib().orc_caustic_params_default(C.byref(p))
+    for k, v in kw.items():
+        setattr(p, k, v)
+    return p
+
+
+def caustic_map(p: CausticParams, thickness: np.ndarray) -> np.ndarray:
+    t = np.ascontiguousarray(thickness, dtype=np.float32)
+    out = np.empty_like(t)
+    lib().orc_caustic_map(C.byref(p), t.ctypes.data, out.ctypes.data)
     return out

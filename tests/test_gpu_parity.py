@@ -529,3 +529,32 @@ def test_nan_inf_and_huge_cells_follow_the_reference(S):
     assert np.array_equal(np.isinf(g32), np.isinf(ora.data))
     assert np.array_equal(g32 == 0, ora.data == 0)
     assert np.abs(g32[fin] / ora.data[fin] - 1).max() <= 1e-5
+
+
+def test_caustic_map_consumer_matches_oracle(S):
+    """f2: the caustic compute pass that reads the thickness buffer right after the drainage step
+    (pipeline.rs:1808-1810, caustics_compute.wgsl:29-126)."""
+    nt, nphi = 64, 128  # the reference's fixed GPU grid (pipeline.rs:673-674)
+    rng = np.random.default_rng(2)
+    for scale, kw in ((1.0, {}), (1e6, dict(focal_length=0.7, branch_threshold=1e-4)), (3e5, dict(caustic_sharpness=2.5))):
+        # thickness in metres gives a flat map (2.0); scaled-up fields exercise focusing, branches and the clamp
+        f = (synthetic_field(nt, nphi, noise_nm=40.0) * scale).astype(np.float32)
+        f += (scale * 2e-7 * rng.standard_normal((nt, nphi))).astype(np.float32)
+        sim = S.GPUDrainageSimulator(500e-9, nphi, nt)
+        sim.upload(f)
+        got = sim.caustic_map(**kw)[0]
+        ref = O.caustic_map(O.caustic_params(grid_width=nphi, grid_height=nt, **kw), f)
+        assert got.shape == ref.shape
+        assert np.abs(got - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max()), scale
+        assert 0.0 <= got.min() and got.max() <= 10.0
+        if scale == 1.0:
+            assert np.allclose(got, 2.0, atol=1e-4)
+    # through a CPU-semantics handle with offset storage and f64 storage, after a fused step
+    cpu = make_sim(S, nt, nphi, S.PREC_F32)
+    cpu.step(1e-3, 3)
+    m = cpu.caustic_map()[0]
+    assert np.allclose(m, 2.0, atol=1e-4)
+    d = make_sim(S, nt, nphi, S.PREC_F64)
+    d.upload(synthetic_field(nt, nphi) * 1e6)
+    ref = O.caustic_map(O.caustic_params(grid_width=nphi, grid_height=nt), (synthetic_field(nt, nphi) * 1e6).astype(np.float32))
+    assert np.abs(d.caustic_map()[0] - ref).max() <= 1e-4 * np.abs(ref).max()
