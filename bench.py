@@ -128,33 +128,41 @@ def pinned(nbytes: int):
     return arr, p
 
 
-def cpu_reference_run(steps: int, warmup: int, sample_rows: int, threads: int):
-    """The reference's CPU path on host cores: DrainageSimulator::step (f64) + per-cell LUT shading of the
-    same view, on a bounded sample grid (sample_rows x 16384).  Returns (Gcell/s, seconds per step)."""
-    import oracle_lib as O
-    from synth import dt_max, synthetic_field
+class CpuReference:
+    """The reference's CPU path on host cores: DrainageSimulator::step (f64) + per-cell LUT shading of the same
+    view, on a bounded sample grid (sample_rows x 16384 of the 8192 x 16384 workload)."""
 
-    nt, nphi = sample_rows, NUM_PHI
-    ora = O.OracleDrainage(nt, nphi, threads=threads)
-    ora.data[:] = synthetic_field(nt, nphi)
-    dt = 0.25 * dt_max(nt, nphi)
-    lut = O.generate_interference_lut(1.33, 1.0)
-    from soap_bubble_simulation_b200.drainage import camera_position
+    def __init__(self, sample_rows: int, threads: int):
+        import oracle_lib as O
+        from soap_bubble_simulation_b200.drainage import camera_position
+        from synth import dt_max, synthetic_field
 
-    cam = camera_position(0.2, 0.0, 0.3)
+        self.O, self.nt, self.nphi, self.threads = O, sample_rows, NUM_PHI, threads
+        self.ora = O.OracleDrainage(self.nt, self.nphi, threads=threads)
+        self.ora.data[:] = synthetic_field(self.nt, self.nphi)
+        self.dt = 0.25 * dt_max(self.nt, self.nphi)
+        self.lut = O.generate_interference_lut(1.33, 1.0)
+        self.cam = camera_position(0.2, 0.0, 0.3)
 
-    def one():
-        ora.step(dt, 1)
-        return O.shade_field(ora.data, nt, 0, 0.025, cam, lut=lut, intensity=4.0, mode=1, threads=threads)
+    def step(self):
+        self.ora.step(self.dt, 1)
+        return self.O.shade_field(self.ora.data, self.nt, 0, 0.025, self.cam, lut=self.lut, intensity=4.0, mode=1,
+                                  threads=self.threads)
 
-    for _ in range(warmup):
-        one()
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        one()
-    el = time.perf_counter() - t0
-    cells = nt * nphi * steps
-    return cells / el / 1e9, el / steps
+    def run(self, steps: int, warmup: int):
+        for _ in range(warmup):
+            self.step()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            self.step()
+        el = time.perf_counter() - t0
+        return self.nt * self.nphi * steps / el / 1e9, el / steps
+
+    def calibrated_steps(self, budget_s: float, lo: int = 3, hi: int = 400) -> int:
+        t0 = time.perf_counter()
+        self.step()
+        t = time.perf_counter() - t0
+        return max(lo, min(hi, int(budget_s / max(t, 1e-6))))
 
 
 def host_threads() -> int:
@@ -169,16 +177,19 @@ def run_reference(args):
     if rank != 0:
         return
     threads = host_threads()
-    sample_rows = 512
-    steps = max(1, min(args.steps, 8))
-    warmup = max(1, min(args.warmup, 2))
-    val, sec = cpu_reference_run(steps, warmup, sample_rows, threads)
+    sample_rows = 2048
+    ref = CpuReference(sample_rows, threads)
+    # honour --steps/--warmup up to a ~2 minute budget for the whole run
+    cap = ref.calibrated_steps(100.0, lo=1, hi=10**6)
+    steps = max(1, min(args.steps, cap))
+    warmup = max(1, min(args.warmup, 3, max(1, cap // 10)))
+    val, sec = ref.run(steps, warmup)
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": "Gcell/s", "n_gpus": args.gpus,
         "steps": steps, "warmup": warmup, "ms_per_step": sec * 1e3, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "single bubble 8192x16384 fused drainage+interference (LUT shading), CPU path "
-                               f"timed on a {sample_rows}x{NUM_PHI} sample grid per step",
+                               f"timed on a {sample_rows}x{NUM_PHI} sample grid (a quarter of the rows) per step",
                    "grid_per_gpu": [ROWS_PER_GPU, NUM_PHI]},
         "cpu_baseline": {"value": val, "unit": "Gcell/s", "cores": threads, "kind": "port",
                          "sample": f"{sample_rows}x{NUM_PHI} grid, {steps} fused steps (C restatement of "
@@ -345,11 +356,14 @@ def main():
     }
     if world == 1 and not args.no_cpu_baseline:
         threads = host_threads()
-        cb_steps = 4
-        val, sec = cpu_reference_run(cb_steps, 1, 512, threads)
+        ref = CpuReference(2048, threads)
+        cb_steps = ref.calibrated_steps(15.0)  # about 15 s of CPU work
+        val, sec = ref.run(cb_steps, 1)
         line["cpu_baseline"] = {"value": val, "unit": "Gcell/s", "cores": threads, "kind": "port",
-                                "sample": f"512x{NUM_PHI} grid, {cb_steps} fused steps, {sec:.2f} s/step (C restatement "
-                                          "of DrainageSimulator::step f64 + LUT shading, OpenMP over rows)"}
+                                "sample": f"2048x{NUM_PHI} grid (a quarter of the workload's rows), {cb_steps} fused steps, "
+                                          f"{sec:.3f} s/step (C restatement of DrainageSimulator::step f64 + LUT shading, "
+                                          "OpenMP over rows on all host cores; the Rust reference is single-threaded "
+                                          "and cannot be built in this image)"}
     emit(line)
     if world > 1:
         dist.destroy_process_group()
