@@ -68,7 +68,11 @@ typedef enum {
                                    src/physics/interference.rs:380-400 (3 wavelengths, exact Fresnel,
                                    multi-bounce Airy, gamma 1/2.2) */
     SBX_RGB_EXACT3_LINEAR = 3,  /* calculate_interference_color_linear, interference.rs:413-426 */
-    SBX_RGB_SCHLICK_WALL = 4    /* wall.wgsl:165-207: Schlick Fresnel, transmitted Airy, 650/532/450 nm */
+    SBX_RGB_SCHLICK_WALL = 4,   /* wall.wgsl:165-207: Schlick Fresnel, transmitted Airy, 650/532/450 nm */
+    SBX_RGB_SCHLICK_TWO_BEAM = 5 /* the documented original model (docs/key-insights.md:288-309): two-beam
+                                   I = (1+cos phi)/2 with phi = 2 pi (2 n d cos theta_t)/lambda + pi, times Schlick
+                                   Fresnel, times 4 -- what README/north_star describe; no compiled reference code
+                                   implements it any more, so it is checked against the restated formula only */
 } sbx_rgb_mode;
 
 typedef enum {

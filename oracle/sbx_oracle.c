@@ -535,6 +535,24 @@ void orc_schlick_wall_rgb(float d_nm, float cos_i, float n_film, float rgb[3])
     }
 }
 
+/* docs/key-insights.md:288-309 (== soap_bubble_simulation_roadmap.md:371-399) */
+void orc_schlick_two_beam_rgb(float d_nm, float cos_i, float n_film, float rgb[3])
+{
+    static const float WL[3] = {650.0f, 532.0f, 450.0f};
+    float sin_i = sqrtf(fmaxf(0.0f, 1.0f - cos_i * cos_i)); /* snells_law, bubble.wgsl:336-341 */
+    float sin_t = sin_i * 1.0f / n_film;
+    float cos_t = sqrtf(fmaxf(0.0f, 1.0f - sin_t * sin_t));
+    float optical_path = 2.0f * n_film * d_nm * cos_t;
+    float q = (n_film - 1.0f) / (n_film + 1.0f);
+    float r0 = q * q;
+    float fresnel = r0 + (1.0f - r0) * powf(1.0f - cos_i, 5.0f);
+    for (int k = 0; k < 3; ++k) {
+        float phase = 2.0f * PI_F * optical_path / WL[k] + PI_F;
+        float intensity = 0.5f * (1.0f + cosf(phase));
+        rgb[k] = intensity * fresnel * 4.0f;
+    }
+}
+
 /* ================================================================== interference LUT (f32) */
 
 float orc_snells_law(float cos_i, float n_film)

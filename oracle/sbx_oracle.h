@@ -123,6 +123,12 @@ void orc_interference_batch(const orc_interference *c, const double *d_nm, const
 /* wall.wgsl:165-207 variant: Schlick Fresnel + transmitted Airy at 650/532/450 nm (f32) */
 void orc_schlick_wall_rgb(float d_nm, float cos_i, float n_film, float rgb[3]);
 
+/* The reference's *documented* original model -- no compiled code implements it any more: two-beam interference
+ * I = (1 + cos phi)/2, phi = 2 pi * 2 n d cos(theta_t) / lambda + pi, times Schlick Fresnel R0 + (1-R0)(1-cos)^5, times 4,
+ * at 650/532/450 nm (WGSL snippet in docs/key-insights.md:288-309, soap_bubble_simulation_roadmap.md:371-399,
+ * docs/physics-reference.md:146-166).  Unclamped f32. */
+void orc_schlick_two_beam_rgb(float d_nm, float cos_i, float n_film, float rgb[3]);
+
 /* ------------------------------------------------------------------ interference LUT (f32) */
 
 #define ORC_LUT_THICKNESS_SAMPLES 256   /* src/render/interference_lut.rs:9  */

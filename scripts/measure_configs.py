@@ -98,6 +98,8 @@ if "c3" in which:
 if "modes" in which:
     single("C3 f32 fused EXACT3 (3-lambda exact Fresnel + gamma)->RGBA8", 8192, 16384, S.PREC_F32, S.RGB_EXACT3, 30, 12,
            note="SFU/issue-bound: 3 sinpi + 3 pow per cell, f64 phase")
+    single("C3 f32 fused two-beam Schlick (the documented original model)->RGBA8", 8192, 16384, S.PREC_F32,
+           S.RGB_SCHLICK_TWO_BEAM, 50, 12, note="analytic 3-lambda colour, no LUT")
     single("C3 f64 fused LUT->RGBA8", 8192, 16384, S.PREC_F64, S.RGB_LUT, 50, 20)
     single("C3 f64 drainage only", 8192, 16384, S.PREC_F64, S.RGB_NONE, 50, 16)
     single("C3 f64 STRICT drainage only (bit-identical mode)", 8192, 16384, S.PREC_F64_STRICT, S.RGB_NONE, 20, 16,

@@ -17,7 +17,7 @@ SBX_OK = 0
 SEM_CPU, SEM_WGSL = 0, 1
 PREC_F32, PREC_F64, PREC_F64_STRICT = 0, 1, 2
 F32, F64 = 0, 1
-RGB_NONE, RGB_LUT, RGB_EXACT3, RGB_EXACT3_LINEAR, RGB_SCHLICK_WALL = 0, 1, 2, 3, 4
+RGB_NONE, RGB_LUT, RGB_EXACT3, RGB_EXACT3_LINEAR, RGB_SCHLICK_WALL, RGB_SCHLICK_TWO_BEAM = 0, 1, 2, 3, 4, 5
 OUT_RGBA8, OUT_RGB_F32 = 0, 1
 PTR_THICKNESS, PTR_CONCENTRATION, PTR_RGB, PTR_CAUSTICS = 0, 1, 2, 3
 IPC_BYTES = 256

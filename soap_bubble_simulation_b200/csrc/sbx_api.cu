@@ -668,7 +668,7 @@ static int32_t prepare_rgb(sbx_drainage *h, const sbx_view *v, RgbArgs &r)
 {
     memset(&r, 0, sizeof r);
     if (!v || v->mode == SBX_RGB_NONE) { r.mode = SBX_RGB_NONE; return SBX_OK; }
-    if (v->mode < SBX_RGB_NONE || v->mode > SBX_RGB_SCHLICK_WALL) return fail(SBX_ERR_INVALID, "bad rgb mode %d", v->mode);
+    if (v->mode < SBX_RGB_NONE || v->mode > SBX_RGB_SCHLICK_TWO_BEAM) return fail(SBX_ERR_INVALID, "bad rgb mode %d", v->mode);
     if (v->format != SBX_OUT_RGBA8 && v->format != SBX_OUT_RGB_F32) return fail(SBX_ERR_INVALID, "bad rgb format %d", v->format);
     if (!(v->n_film > 0.0)) return fail(SBX_ERR_INVALID, "n_film must be > 0");
     const size_t cells = (size_t)h->batch * h->rows_local * h->num_phi;
@@ -701,8 +701,11 @@ static int32_t prepare_rgb(sbx_drainage *h, const sbx_view *v, RgbArgs &r)
     r.nm_over_max = 1e9f / h->lut_max_nm;
     r.lut = h->lut_tex;
     r.inv_n2_d = 1.0 / (v->n_film * v->n_film);
+    r.two_n = (float)(2.0 * v->n_film);
+    r.r0 = (float)(((v->n_film - 1.0) / (v->n_film + 1.0)) * ((v->n_film - 1.0) / (v->n_film + 1.0)));
+    r.omr0 = 1.0f - r.r0;
     const double wl[3] = {650.0, 532.0, 450.0};  // interference.rs:26-30
-    for (int k = 0; k < 3; ++k) r.two_n_over_wl[k] = 2.0 * v->n_film / wl[k];
+    for (int k = 0; k < 3; ++k) { r.two_n_over_wl[k] = 2.0 * v->n_film / wl[k]; r.inv_wl_f[k] = (float)(1.0 / wl[k]); }
     return SBX_OK;
 }
 

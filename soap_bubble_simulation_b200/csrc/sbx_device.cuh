@@ -252,6 +252,27 @@ __device__ __forceinline__ void rgb_schlick_wall(double d_nm, float ci, const Rg
     for (int k = 0; k < 3; ++k) rgb[k] = rcp_approx(fmaf(F, fringe_sin2(ph.y[k]), 1.f));
 }
 
+// The documented original model (docs/key-insights.md:288-309): two-beam interference with the pi reflection shift,
+// I = (1 + cos(2 pi cyc + pi))/2 = sin^2(pi cyc), cyc = 2 n d cos(theta_t)/lambda, times Schlick Fresnel, times 4.
+// Low finesse, so f32 cycles and the SFU sine on the reduced argument are ample for the 1e-4 colour tolerance.
+__device__ __forceinline__ void rgb_two_beam(float d_nm, float ci, const RgbArgs &a, float rgb[3])
+{
+    const float s2 = (1.f - ci * ci) * a.inv_n2;
+    const float ct = sqrt_approx(fmaxf(1.f - s2, 0.f));
+    const float opd = a.two_n * d_nm * ct;
+    const float m = 1.f - ci, m2 = m * m;
+    const float fres4 = 4.f * fmaf(a.omr0, m2 * m2 * m, a.r0);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float cyc = opd * a.inv_wl_f[k];
+        // round-to-nearest by the 1.5*2^23 magic add (FADD pipe) instead of FRND, which shares the SFU port with
+        // the sine; cyc stays far below 2^22
+        const float r = __fsub_rn(__fadd_rn(cyc, 12582912.f), 12582912.f);
+        const float s = __sinf(3.14159265358979f * (cyc - r));
+        rgb[k] = clamp01(s * s * fres4);
+    }
+}
+
 // bubble.wgsl:425-439 through the texture unit: linear filter, clamp-to-edge, normalised coordinates,
 // unorm8 -> float (sampler at pipeline.rs:350-359, texture format Rgba8Unorm at pipeline.rs:325)
 __device__ __forceinline__ void rgb_lut(float d_nm, float ci, const RgbArgs &a, float rgb[3])
@@ -269,6 +290,7 @@ __device__ __forceinline__ void rgb_lut(float d_nm, float ci, const RgbArgs &a, 
 template <int MODE> struct Dnm { using type = double; };
 template <> struct Dnm<SBX_RGB_LUT> { using type = float; };
 template <> struct Dnm<SBX_RGB_NONE> { using type = float; };
+template <> struct Dnm<SBX_RGB_SCHLICK_TWO_BEAM> { using type = float; };
 
 template <int MODE>
 __device__ __forceinline__ void rgb_eval(typename Dnm<MODE>::type d_nm, float ci, const RgbArgs &a, float rgb[3])
@@ -277,6 +299,7 @@ __device__ __forceinline__ void rgb_eval(typename Dnm<MODE>::type d_nm, float ci
     else if constexpr (MODE == SBX_RGB_EXACT3) rgb_exact3(d_nm, ci, a, true, rgb);
     else if constexpr (MODE == SBX_RGB_EXACT3_LINEAR) rgb_exact3(d_nm, ci, a, false, rgb);
     else if constexpr (MODE == SBX_RGB_SCHLICK_WALL) rgb_schlick_wall(d_nm, ci, a, rgb);
+    else if constexpr (MODE == SBX_RGB_SCHLICK_TWO_BEAM) rgb_two_beam(d_nm, ci, a, rgb);
 }
 
 // RgbColor::to_u8_tuple (interference.rs:73-79): round(255 x), alpha 255
@@ -315,10 +338,11 @@ __device__ __forceinline__ uint32_t shade_px(T h, T href, float href_u, float co
                                __saturatef(t.z * rgb.intensity));
     } else {
         const float ci = fabsf(nc - R) * rsqrt_approx(len2);
-        const double d_nm = ((double)h + (double)href) * 1e9;
+        using DN = typename Dnm<MODE>::type;
+        const DN d_nm = ((DN)h + (DN)href) * (DN)1e9;
         float c[3];
         rgb_eval<MODE>(d_nm, ci, rgb, c);
-        return pack_rgba8(c);
+        return pack_rgba8_fast(c[0], c[1], c[2]);
     }
 }
 

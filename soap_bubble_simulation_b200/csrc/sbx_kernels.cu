@@ -804,6 +804,7 @@ static cudaError_t launch_march_mode(const StepArgs<T> &a, dim3 grid, dim3 block
     case SBX_RGB_EXACT3: k_march<T, VEC, SBX_RGB_EXACT3, TFE, STRICT><<<grid, block, 0, st>>>(a); break;
     case SBX_RGB_EXACT3_LINEAR: k_march<T, VEC, SBX_RGB_EXACT3_LINEAR, TFE, STRICT><<<grid, block, 0, st>>>(a); break;
     case SBX_RGB_SCHLICK_WALL: k_march<T, VEC, SBX_RGB_SCHLICK_WALL, TFE, STRICT><<<grid, block, 0, st>>>(a); break;
+    case SBX_RGB_SCHLICK_TWO_BEAM: k_march<T, VEC, SBX_RGB_SCHLICK_TWO_BEAM, TFE, STRICT><<<grid, block, 0, st>>>(a); break;
     default: return cudaErrorInvalidValue;
     }
     return cudaGetLastError();
@@ -882,6 +883,7 @@ cudaError_t launch_step(StepArgs<T> a, int batch, bool tfe, bool strict, bool ha
         case SBX_RGB_EXACT3: SBX_POLES(SBX_RGB_EXACT3); break;
         case SBX_RGB_EXACT3_LINEAR: SBX_POLES(SBX_RGB_EXACT3_LINEAR); break;
         case SBX_RGB_SCHLICK_WALL: SBX_POLES(SBX_RGB_SCHLICK_WALL); break;
+        case SBX_RGB_SCHLICK_TWO_BEAM: SBX_POLES(SBX_RGB_SCHLICK_TWO_BEAM); break;
         default: return cudaErrorInvalidValue;
         }
 #undef SBX_POLES
@@ -930,6 +932,7 @@ cudaError_t launch_shade(StepArgs<T> a, int batch, int band_rows_req, cudaStream
     case SBX_RGB_EXACT3: SBX_SHADE(SBX_RGB_EXACT3); break;
     case SBX_RGB_EXACT3_LINEAR: SBX_SHADE(SBX_RGB_EXACT3_LINEAR); break;
     case SBX_RGB_SCHLICK_WALL: SBX_SHADE(SBX_RGB_SCHLICK_WALL); break;
+    case SBX_RGB_SCHLICK_TWO_BEAM: SBX_SHADE(SBX_RGB_SCHLICK_TWO_BEAM); break;
     default: return cudaErrorInvalidValue;
     }
 #undef SBX_SHADE
@@ -957,6 +960,7 @@ cudaError_t launch_wgsl(WgslArgs a, int batch, int band_rows_req, cudaStream_t s
     case SBX_RGB_EXACT3: SBX_WGSL(SBX_RGB_EXACT3); break;
     case SBX_RGB_EXACT3_LINEAR: SBX_WGSL(SBX_RGB_EXACT3_LINEAR); break;
     case SBX_RGB_SCHLICK_WALL: SBX_WGSL(SBX_RGB_SCHLICK_WALL); break;
+    case SBX_RGB_SCHLICK_TWO_BEAM: SBX_WGSL(SBX_RGB_SCHLICK_TWO_BEAM); break;
     default: return cudaErrorInvalidValue;
     }
 #undef SBX_WGSL

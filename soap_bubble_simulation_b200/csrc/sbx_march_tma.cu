@@ -472,6 +472,7 @@ static cudaError_t launch_tma_mode(const StepArgs<T> &a, dim3 grid, dim3 block, 
     case SBX_RGB_EXACT3: return launch_one<T, SBX_RGB_EXACT3, TFE>(a, grid, block, smem, st);
     case SBX_RGB_EXACT3_LINEAR: return launch_one<T, SBX_RGB_EXACT3_LINEAR, TFE>(a, grid, block, smem, st);
     case SBX_RGB_SCHLICK_WALL: return launch_one<T, SBX_RGB_SCHLICK_WALL, TFE>(a, grid, block, smem, st);
+    case SBX_RGB_SCHLICK_TWO_BEAM: return launch_one<T, SBX_RGB_SCHLICK_TWO_BEAM, TFE>(a, grid, block, smem, st);
     default: return cudaErrorInvalidValue;
     }
 }

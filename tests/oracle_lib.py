@@ -100,6 +100,7 @@ def lib() -> C.CDLL:
         "orc_color_lut_2d": (None, [C.POINTER(Interference), d, d, i, i, dp]),
         "orc_interference_batch": (None, [C.POINTER(Interference), p, p, C.c_size_t, i, p]),
         "orc_schlick_wall_rgb": (None, [f, f, f, C.POINTER(C.c_float)]),
+        "orc_schlick_two_beam_rgb": (None, [f, f, f, C.POINTER(C.c_float)]),
         "orc_thin_film_interference": (None, [f, f, f, f, C.POINTER(C.c_float)]),
         "orc_generate_interference_lut": (None, [f, f, p]),
         "orc_generate_lut_spectral": (None, [f, f, p, i, i, i, f, p]),
@@ -295,6 +296,12 @@ def thin_film_interference(d_nm, cos_theta, n=1.33, intensity=1.0):
 def schlick_wall_rgb(d_nm, cos_i, n=1.33):
     o = (C.c_float * 3)()
     lib().orc_schlick_wall_rgb(d_nm, cos_i, n, o)
+    return tuple(o)
+
+
+def schlick_two_beam_rgb(d_nm, cos_i, n=1.33):
+    o = (C.c_float * 3)()
+    lib().orc_schlick_two_beam_rgb(d_nm, cos_i, n, o)
     return tuple(o)
 
 

@@ -558,3 +558,34 @@ def test_caustic_map_consumer_matches_oracle(S):
     d.upload(synthetic_field(nt, nphi) * 1e6)
     ref = O.caustic_map(O.caustic_params(grid_width=nphi, grid_height=nt), (synthetic_field(nt, nphi) * 1e6).astype(np.float32))
     assert np.abs(d.caustic_map()[0] - ref).max() <= 1e-4 * np.abs(ref).max()
+
+
+def test_two_beam_schlick_documented_model(S):
+    """SBX_RGB_SCHLICK_TWO_BEAM: the model README/north_star describe (docs/key-insights.md:288-309); checked
+    against the restated formula, fused and shade-only, float and RGBA8 output, f32 and f64 storage."""
+    nt, nphi = 48, 128
+    f = synthetic_field(nt, nphi, h0_nm=450.0, noise_nm=60.0).astype(np.float32)
+    view = S.View(mode=S.RGB_SCHLICK_TWO_BEAM, format=S.OUT_RGB_F32)
+    cos = _oracle_view_cos(nt, nphi, 0.025, view.cam_pos)
+    ref = np.empty((nt, nphi, 3))
+    for i in range(nt):
+        for j in range(nphi):
+            ref[i, j] = O.schlick_two_beam_rgb(float(f[i, j] * np.float32(1e9)), float(np.float32(cos[i, j])), 1.33)
+    ref = np.clip(ref, 0.0, 1.0)
+    for prec in (S.PREC_F32, S.PREC_F64):
+        sim = make_sim(S, nt, nphi, prec, h_ref=0.0)
+        sim.upload(f)
+        sim.shade(view)
+        rgb = sim.download_rgb(S.OUT_RGB_F32)[0]
+        assert np.abs(rgb - ref).max() <= 1e-4
+        sim.shade(S.View(mode=S.RGB_SCHLICK_TWO_BEAM, format=S.OUT_RGBA8))
+        px = sim.download_rgb()[0]
+        assert np.abs(px[..., :3].astype(int) - np.floor(ref * 255 + 0.5)).max() <= 1
+    # fused through the TMA kernel: colour of the stepped field equals shade-only of the same field
+    sim = make_sim(S, nt, nphi, S.PREC_F32, h_ref=0.0)
+    sim.upload(f)
+    v8 = S.View(mode=S.RGB_SCHLICK_TWO_BEAM, format=S.OUT_RGBA8)
+    sim.step_fused(1e-4, v8, 2)
+    fused = sim.download_rgb()[0]
+    sim.shade(v8)
+    assert np.abs(fused.astype(int) - sim.download_rgb()[0].astype(int)).max() <= 1
