@@ -925,7 +925,7 @@ static int32_t step_wgsl_sem(sbx_drainage *h, double dt, const RgbArgs &rgb)
     a.radius_view = h->wp.bubble_radius;
     a.rgb = rgb;
     int n = 0;
-    CU(launch_wgsl(a, h->batch, h->band_rows, h->stream, &n));
+    CU(launch_wgsl(a, h->batch, h->band_rows, h->use_tma, h->stream, &n));
     if (rgb.mode != SBX_RGB_NONE && (h->row_begin == 0 || h->row_end == h->num_theta)) {
         // frozen pole rows still need their colour: shade them from the (unchanged) pole values
         StepArgs<float> s;

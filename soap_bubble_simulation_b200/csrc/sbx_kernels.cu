@@ -313,17 +313,16 @@ __global__ void __launch_bounds__(256) k_shade(const StepArgs<T> a)
     }
 }
 
-// f32 -> RGBA8 streaming variant of k_shade: four rows per trip with all four 16-byte loads issued before the
-// first use, so that every thread keeps 64 B in flight (the plain loop above has one dependent load per row).
+// f32 -> RGBA8 streaming variant of k_shade: two rows per trip with both 16-byte loads issued before the first
+// use and running pointers instead of per-row index arithmetic (the plain loop above has one dependent load per
+// row; four rows per trip ran into tex_throttle, profiles/r01_k_shade_rgba8.txt).
 template <int MODE>
-__global__ void __launch_bounds__(256) k_shade_rgba8(const StepArgs<float> a)
+__global__ void __launch_bounds__(256, 6) k_shade_rgba8(const StepArgs<float> a)
 {
     const int N = a.num_phi;
     const int j0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
     if (j0 >= N) return;
     const int b = blockIdx.z;
-    const float *__restrict__ in = a.in + (long long)b * a.bubble_stride;
-    uint32_t *__restrict__ out = reinterpret_cast<uint32_t *>(a.rgb.out) + (long long)b * a.rgb_bubble_stride;
     const BubbleParam<float> bp = a.bub[b];
     const float4 ca = __ldg(reinterpret_cast<const float4 *>(a.rgb.colA + j0));
     const float colA[4] = {ca.x, ca.y, ca.z, ca.w};
@@ -331,27 +330,31 @@ __global__ void __launch_bounds__(256) k_shade_rgba8(const StepArgs<float> a)
     const float href_u = bp.h_ref * a.rgb.nm_over_max;
     const int l0 = a.l_first + blockIdx.y * a.band_rows;
     const int l1 = min(l0 + a.band_rows - 1, a.l_last);
-    for (int l = l0; l <= l1; l += 4) {
-        float4 h[4];
-        float2 sc[4];
+    const float *__restrict__ in_p = a.in + (long long)b * a.bubble_stride + (long long)l0 * N + j0;
+    uint32_t *__restrict__ out_p = reinterpret_cast<uint32_t *>(a.rgb.out) + (long long)b * a.rgb_bubble_stride +
+                                   (long long)(l0 - 1) * N + j0;
+    const float2 *__restrict__ sc_p = a.rowSC + a.row_begin + (l0 - 1);
+    auto shade_row = [&](const float4 &h, const float2 &sc, uint32_t *dst) {
+        const float ccy = sc.y * a.rgb.cam_y;
+        const float hv[4] = {h.x, h.y, h.z, h.w};
+        uint32_t px[4];
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const int lr = min(l + r, l1);
-            h[r] = __ldg(reinterpret_cast<const float4 *>(in + (long long)lr * N + j0));
-            sc[r] = __ldg(a.rowSC + a.row_begin + (lr - 1));
-        }
-#pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            if (l + r > l1) break;
-            const float ccy = sc[r].y * a.rgb.cam_y;
-            const float hv[4] = {h[r].x, h[r].y, h[r].z, h[r].w};
-            uint32_t px[4];
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-                px[k] = shade_px<MODE>(hv[k], bp.h_ref, href_u, colA[k], sc[r].x, ccy, bp.radius, camR2, a.rgb);
-            *reinterpret_cast<uint4 *>(out + (long long)(l + r - 1) * N + j0) = make_uint4(px[0], px[1], px[2], px[3]);
-        }
+        for (int k = 0; k < 4; ++k)
+            px[k] = shade_px<MODE>(hv[k], bp.h_ref, href_u, colA[k], sc.x, ccy, bp.radius, camR2, a.rgb);
+        *reinterpret_cast<uint4 *>(dst) = make_uint4(px[0], px[1], px[2], px[3]);
+    };
+    int left = l1 - l0 + 1;
+    for (; left >= 2; left -= 2) {
+        const float4 h0 = __ldg(reinterpret_cast<const float4 *>(in_p));
+        const float4 h1 = __ldg(reinterpret_cast<const float4 *>(in_p + N));
+        const float2 s0 = __ldg(sc_p), s1 = __ldg(sc_p + 1);
+        shade_row(h0, s0, out_p);
+        shade_row(h1, s1, out_p + N);
+        in_p += 2 * (long long)N;
+        out_p += 2 * (long long)N;
+        sc_p += 2;
     }
+    if (left) shade_row(__ldg(reinterpret_cast<const float4 *>(in_p)), __ldg(sc_p), out_p);
 }
 
 // ------------------------------------------------------------------ WGSL-semantics dispatch
@@ -942,11 +945,15 @@ cudaError_t launch_shade(StepArgs<T> a, int batch, int band_rows_req, cudaStream
 template cudaError_t launch_shade<float>(StepArgs<float>, int, int, cudaStream_t, int *);
 template cudaError_t launch_shade<double>(StepArgs<double>, int, int, cudaStream_t, int *);
 
-cudaError_t launch_wgsl(WgslArgs a, int batch, int band_rows_req, cudaStream_t st, int *launches)
+cudaError_t launch_wgsl(WgslArgs a, int batch, int band_rows_req, bool use_tma, cudaStream_t st, int *launches)
 {
     const bool vec_ok = (a.num_phi % 4) == 0;
     const int rows = a.l_last - a.l_first + 1;
     if (rows <= 0) return cudaSuccess;
+    if (use_tma && wgsl_tma_supported(a)) {
+        ++*launches;
+        return launch_wgsl_tma(a, batch, band_rows_req, st);
+    }
     dim3 grid, block;
     int band_rows;
     march_geometry(a.num_phi, vec_ok ? 4 : 1, rows, batch, band_rows_req, grid, block, band_rows);

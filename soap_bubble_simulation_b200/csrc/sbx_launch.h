@@ -26,7 +26,10 @@ cudaError_t launch_tfe_pass(T *buf, long long bubble_stride, int num_phi, int ro
 template <typename T>
 cudaError_t launch_shade(StepArgs<T> a, int batch, int band_rows_req, cudaStream_t st, int *launches);
 
-cudaError_t launch_wgsl(WgslArgs a, int batch, int band_rows_req, cudaStream_t st, int *launches);
+cudaError_t launch_wgsl(WgslArgs a, int batch, int band_rows_req, bool use_tma, cudaStream_t st, int *launches);
+// TMA-staged ring variant (sbx_wgsl_tma.cu): num_phi % 4 == 0, RGBA8 or no colour
+bool wgsl_tma_supported(const WgslArgs &a);
+cudaError_t launch_wgsl_tma(WgslArgs a, int batch, int band_rows_req, cudaStream_t st);
 
 template <typename TD, typename TS>
 cudaError_t launch_convert_in(TD *dst, const TS *src, long long n, long long bubble_stride, const double *href, cudaStream_t st);
