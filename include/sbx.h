@@ -240,6 +240,17 @@ int32_t sbx_caustic_params_default(sbx_caustic_params *p);
  * on the device (SBX_PTR_CAUSTICS).  grid_width/grid_height in p are overridden by the handle's grid. */
 int32_t sbx_drainage_caustics(sbx_drainage *h, const sbx_caustic_params *p, float *host_out);
 
+/* sample_thickness_at_uv / thickness_gradient_uv of the branched-flow ray marcher
+ * (src/render/shaders/branched_flow_compute.wgsl:187-210), generalised from its hard-coded 128x64 grid to the
+ * handle's grid: nearest-texel thickness (metres, f32) of bubble `bubble` at n uv positions (u = phi/2pi,
+ * v = theta/pi; host array of n x 2 floats) and its central-difference gradient with eps = 0.01 in uv space.
+ * out_h (n floats) and out_grad (n x 2 floats) are host arrays; either may be NULL.  Whole-sphere handles only. */
+int32_t sbx_drainage_sample_uv(sbx_drainage *h, int32_t bubble, const float *uv, size_t n, float *out_h, float *out_grad);
+
+/* sample_thickness(normal) of the same shader (branched_flow_compute.wgsl:110-116, 294-300): thickness * scale at the
+ * texel each unit normal (host array of n x 3 floats) points at.  out_h = n floats on the host. */
+int32_t sbx_drainage_sample_normal(sbx_drainage *h, int32_t bubble, const float *normals, size_t n, float scale, float *out_h);
+
 /* ---------------------------------------------------------------- interference LUT / calculator */
 /* generate_interference_lut(refractive_index, intensity) -> 256x64 RGBA8
  * (src/render/interference_lut.rs:18-41), built on `device`. */

@@ -830,3 +830,45 @@ void orc_caustic_map(const orc_caustic_params *p, const float *t, float *out)
         }
     }
 }
+
+/* ================================================================== branched-flow sampling side (f32) */
+
+static float sample_uv(const float *t, int W, int H, float u, float v)
+{ /* branched_flow_compute.wgsl:187-192 */
+    float cu = u < 0.f ? 0.f : (u > 1.f ? 1.f : u), cv = v < 0.f ? 0.f : (v > 1.f ? 1.f : v);
+    uint32_t x = (uint32_t)(cu * (float)(W - 1)), y = (uint32_t)(cv * (float)(H - 1));
+    return t[(size_t)y * (size_t)W + (size_t)x];
+}
+
+void orc_sample_thickness_uv(const float *t, int W, int H, const float *uv, size_t n, float *out_h, float *out_grad)
+{
+    const float eps = 0.01f;
+    for (size_t i = 0; i < n; ++i) {
+        const float u = uv[2 * i], v = uv[2 * i + 1];
+        if (out_h) out_h[i] = sample_uv(t, W, H, u, v);
+        if (out_grad) { /* :196-210 */
+            const float h_right = sample_uv(t, W, H, u + eps, v), h_left = sample_uv(t, W, H, u - eps, v);
+            const float h_up = sample_uv(t, W, H, u, v + eps), h_down = sample_uv(t, W, H, u, v - eps);
+            out_grad[2 * i] = (h_right - h_left) / (2.0f * eps);
+            out_grad[2 * i + 1] = (h_up - h_down) / (2.0f * eps);
+        }
+    }
+}
+
+void orc_sample_thickness_normal(const float *t, int W, int H, const float *nrm, size_t n, float scale, float *out_h,
+                                 float *out_uv)
+{
+    const float PI_F = 3.14159265359f; /* branched_flow_compute.wgsl PI constant */
+    for (size_t i = 0; i < n; ++i) {
+        const float nx = nrm[3 * i], ny = nrm[3 * i + 1], nz = nrm[3 * i + 2];
+        const float phi = atan2f(nz, nx);
+        const float cy = ny < -1.f ? -1.f : (ny > 1.f ? 1.f : ny);
+        const float theta = acosf(cy);
+        const float u = (phi + PI_F) / (2.0f * PI_F), v = theta / PI_F;
+        uint32_t x = (uint32_t)(u * (float)(W - 1)), y = (uint32_t)(v * (float)(H - 1));
+        if (x > (uint32_t)(W - 1)) x = (uint32_t)(W - 1); /* u can round to 1 + 1 ulp; the shader would read OOB */
+        if (y > (uint32_t)(H - 1)) y = (uint32_t)(H - 1);
+        out_h[i] = t[(size_t)y * (size_t)W + x] * scale;
+        if (out_uv) { out_uv[2 * i] = u; out_uv[2 * i + 1] = v; }
+    }
+}

@@ -181,6 +181,18 @@ void orc_caustic_params_default(orc_caustic_params *p); /* src/render/caustics.r
  * thickness field (phi wrapped, theta clamped, :29-92) -> focusing x branch x refraction factors (:95-112) */
 void orc_caustic_map(const orc_caustic_params *p, const float *thickness, float *out);
 
+/* branched_flow_compute.wgsl:187-210, generalised from the hard-coded 128x64 grid: nearest-texel thickness at a
+ * uv position (u = phi/2pi, v = theta/pi; clamp, truncating index) and its central-difference gradient with
+ * eps = 0.01 in uv space.  out_grad = n x 2 floats (may be NULL). */
+void orc_sample_thickness_uv(const float *thickness, int width, int height, const float *uv, size_t n, float *out_h,
+                             float *out_grad);
+
+/* branched_flow_compute.wgsl:110-116 + 294-300: thickness * scale at the texel a unit normal points at
+ * (phi = atan2(n.z, n.x), theta = acos(n.y); u = (phi + pi)/2pi, v = theta/pi; truncating index, no clamp needed).
+ * out_uv (n x 2, may be NULL) returns the f32 uv the index came from, so a test can spot texel-boundary ties. */
+void orc_sample_thickness_normal(const float *thickness, int width, int height, const float *normals, size_t n,
+                                 float scale, float *out_h, float *out_uv);
+
 #ifdef __cplusplus
 }
 #endif

@@ -112,6 +112,8 @@ _SIGS = {
     "sbx_drainage_launch_count": [C.c_void_p, C.POINTER(C.c_int64)],
     "sbx_caustic_params_default": [C.POINTER(CausticParamsC)],
     "sbx_drainage_caustics": [C.c_void_p, C.POINTER(CausticParamsC), C.c_void_p],
+    "sbx_drainage_sample_uv": [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p],
+    "sbx_drainage_sample_normal": [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_float, C.c_void_p],
     "sbx_lut_build": [C.c_float, C.c_float, C.c_void_p, C.c_int32],
     "sbx_lut_build_spectral": [C.c_float, C.c_float, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                C.c_float, C.c_void_p, C.c_int32],

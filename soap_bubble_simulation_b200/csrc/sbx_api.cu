@@ -1345,6 +1345,56 @@ extern "C" int32_t sbx_drainage_caustics(sbx_drainage *h, const sbx_caustic_para
     return SBX_OK;
 }
 
+extern "C" int32_t sbx_drainage_sample_uv(sbx_drainage *h, int32_t bubble, const float *uv, size_t n, float *out_h, float *out_grad)
+{
+    CHECK_H(h);
+    if (!uv) return fail(SBX_ERR_INVALID, "uv is null");
+    if (bubble < 0 || bubble >= h->batch) return fail(SBX_ERR_INVALID, "bubble %d out of range", bubble);
+    if (h->rows_local != h->num_theta) return fail(SBX_ERR_UNSUPPORTED, "uv sampling needs a whole-sphere handle");
+    if (n == 0) return SBX_OK;
+    float *duv = nullptr, *dh = nullptr, *dg = nullptr;
+    cudaError_t e = cudaMalloc(&duv, n * 8);
+    if (e == cudaSuccess && out_h) e = cudaMalloc(&dh, n * 4);
+    if (e == cudaSuccess && out_grad) e = cudaMalloc(&dg, n * 8);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(duv, uv, n * 8, cudaMemcpyHostToDevice, h->stream);
+    const size_t off = (size_t)bubble * h->bubble_stride + h->num_phi;
+    if (e == cudaSuccess) {
+        if (h->f64) e = launch_sample_uv<double>(tbuf<double>(h, h->cur) + off, h->num_phi, h->num_theta, 0.f, duv, n, dh, dg, h->stream);
+        else e = launch_sample_uv<float>(tbuf<float>(h, h->cur) + off, h->num_phi, h->num_theta, (float)h->b_href[bubble], duv, n, dh, dg, h->stream);
+        h->launches++;
+    }
+    if (e == cudaSuccess && dh) e = cudaMemcpyAsync(out_h, dh, n * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess && dg) e = cudaMemcpyAsync(out_grad, dg, n * 8, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(duv); cudaFree(dh); cudaFree(dg);
+    if (e != cudaSuccess) return fail(SBX_ERR_CUDA, "uv sampling failed: %s", cudaGetErrorString(e));
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_sample_normal(sbx_drainage *h, int32_t bubble, const float *normals, size_t n, float scale, float *out_h)
+{
+    CHECK_H(h);
+    if (!normals || !out_h) return fail(SBX_ERR_INVALID, "normals/out_h is null");
+    if (bubble < 0 || bubble >= h->batch) return fail(SBX_ERR_INVALID, "bubble %d out of range", bubble);
+    if (h->rows_local != h->num_theta) return fail(SBX_ERR_UNSUPPORTED, "normal sampling needs a whole-sphere handle");
+    if (n == 0) return SBX_OK;
+    float *dn = nullptr, *dh = nullptr;
+    cudaError_t e = cudaMalloc(&dn, n * 12);
+    if (e == cudaSuccess) e = cudaMalloc(&dh, n * 4);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(dn, normals, n * 12, cudaMemcpyHostToDevice, h->stream);
+    const size_t off = (size_t)bubble * h->bubble_stride + h->num_phi;
+    if (e == cudaSuccess) {
+        if (h->f64) e = launch_sample_normal<double>(tbuf<double>(h, h->cur) + off, h->num_phi, h->num_theta, 0.f, dn, n, scale, dh, h->stream);
+        else e = launch_sample_normal<float>(tbuf<float>(h, h->cur) + off, h->num_phi, h->num_theta, (float)h->b_href[bubble], dn, n, scale, dh, h->stream);
+        h->launches++;
+    }
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out_h, dh, n * 4, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(dn); cudaFree(dh);
+    if (e != cudaSuccess) return fail(SBX_ERR_CUDA, "normal sampling failed: %s", cudaGetErrorString(e));
+    return SBX_OK;
+}
+
 // ------------------------------------------------------------------ LUT / calculator entry points
 static int32_t pick_device(int32_t device)
 {

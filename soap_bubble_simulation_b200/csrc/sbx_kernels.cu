@@ -778,6 +778,61 @@ cudaError_t launch_caustics(const T *buf, long long bubble_stride, float *out, i
 template cudaError_t launch_caustics<float>(const float *, long long, float *, int, int, int, int, int, const double *, const sbx_caustic_params &, cudaStream_t);
 template cudaError_t launch_caustics<double>(const double *, long long, float *, int, int, int, int, int, const double *, const sbx_caustic_params &, cudaStream_t);
 
+// branched_flow_compute.wgsl:187-210 for n query points
+template <typename T>
+__global__ void k_sample_uv(const T *field /* first owned row of the bubble */, int W, int H, float href, const float *uv,
+                            size_t n, float *out_h, float *out_grad)
+{
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    auto S = [&](float u, float v) {
+        const float cu = fminf(fmaxf(u, 0.f), 1.f), cv = fminf(fmaxf(v, 0.f), 1.f);
+        const unsigned x = (unsigned)__fmul_rn(cu, (float)(W - 1)), y = (unsigned)__fmul_rn(cv, (float)(H - 1));
+        return (float)field[(size_t)y * W + x] + href;
+    };
+    const float eps = 0.01f;
+    const float u = uv[2 * i], v = uv[2 * i + 1];
+    if (out_h) out_h[i] = S(u, v);
+    if (out_grad) {
+        out_grad[2 * i] = __fdiv_rn(__fsub_rn(S(__fadd_rn(u, eps), v), S(__fsub_rn(u, eps), v)), __fmul_rn(2.0f, eps));
+        out_grad[2 * i + 1] = __fdiv_rn(__fsub_rn(S(u, __fadd_rn(v, eps)), S(u, __fsub_rn(v, eps))), __fmul_rn(2.0f, eps));
+    }
+}
+
+template <typename T>
+__global__ void k_sample_normal(const T *field, int W, int H, float href, const float *nrm, size_t n, float scale, float *out_h)
+{ // branched_flow_compute.wgsl:110-116, 294-300
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n) return;
+    const float PI_F = 3.14159265359f;
+    const float phi = atan2f(nrm[3 * i + 2], nrm[3 * i]);
+    const float theta = acosf(fminf(fmaxf(nrm[3 * i + 1], -1.f), 1.f));
+    const float u = __fdiv_rn(__fadd_rn(phi, PI_F), __fmul_rn(2.0f, PI_F)), v = __fdiv_rn(theta, PI_F);
+    const unsigned x = min((unsigned)__fmul_rn(u, (float)(W - 1)), (unsigned)(W - 1));
+    const unsigned y = min((unsigned)__fmul_rn(v, (float)(H - 1)), (unsigned)(H - 1));
+    out_h[i] = __fmul_rn((float)field[(size_t)y * W + x] + href, scale);
+}
+
+template <typename T>
+cudaError_t launch_sample_normal(const T *field, int W, int H, float href, const float *nrm, size_t n, float scale,
+                                 float *out_h, cudaStream_t st)
+{
+    k_sample_normal<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(field, W, H, href, nrm, n, scale, out_h);
+    return cudaGetLastError();
+}
+template cudaError_t launch_sample_normal<float>(const float *, int, int, float, const float *, size_t, float, float *, cudaStream_t);
+template cudaError_t launch_sample_normal<double>(const double *, int, int, float, const float *, size_t, float, float *, cudaStream_t);
+
+template <typename T>
+cudaError_t launch_sample_uv(const T *field, int W, int H, float href, const float *uv, size_t n, float *out_h,
+                             float *out_grad, cudaStream_t st)
+{
+    k_sample_uv<T><<<(unsigned)((n + 255) / 256), 256, 0, st>>>(field, W, H, href, uv, n, out_h, out_grad);
+    return cudaGetLastError();
+}
+template cudaError_t launch_sample_uv<float>(const float *, int, int, float, const float *, size_t, float *, float *, cudaStream_t);
+template cudaError_t launch_sample_uv<double>(const double *, int, int, float, const float *, size_t, float *, float *, cudaStream_t);
+
 // per-column view term A_j = cos(phi_j) cam_x + sin(phi_j) cam_z, evaluated in f64
 __global__ void k_col_view(float *colA, int num_phi, double cam_x, double cam_z)
 {

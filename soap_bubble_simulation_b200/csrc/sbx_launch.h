@@ -54,6 +54,12 @@ cudaError_t launch_lut_shade_points(cudaTextureObject_t lut, float inv_max_nm, f
 template <typename T>
 cudaError_t launch_caustics(const T *buf, long long bubble_stride, float *out, int num_phi, int num_theta, int row_begin,
                             int rows_local, int batch, const double *href, const sbx_caustic_params &p, cudaStream_t st);
+template <typename T>
+cudaError_t launch_sample_uv(const T *field, int W, int H, float href, const float *uv, size_t n, float *out_h,
+                             float *out_grad, cudaStream_t st);
+template <typename T>
+cudaError_t launch_sample_normal(const T *field, int W, int H, float href, const float *nrm, size_t n, float scale,
+                                 float *out_h, cudaStream_t st);
 cudaError_t launch_col_view(float *colA, int num_phi, double cam_x, double cam_z, cudaStream_t st);
 
 }  // namespace sbx

@@ -231,6 +231,23 @@ class _DeviceField:
         L.check(L.lib().sbx_drainage_caustics(self._h, C.byref(p), out.ctypes.data))
         return out
 
+    def sample_uv(self, uv, bubble: int = 0):
+        """sample_thickness_at_uv / thickness_gradient_uv (branched_flow_compute.wgsl:187-210) at (n, 2) uv positions:
+        returns (thickness (n,) f32 in metres, gradient (n, 2) f32 per unit uv)."""
+        q = np.ascontiguousarray(uv, dtype=np.float32).reshape(-1, 2)
+        hh = np.empty(len(q), np.float32)
+        gg = np.empty((len(q), 2), np.float32)
+        L.check(L.lib().sbx_drainage_sample_uv(self._h, bubble, q.ctypes.data, len(q), hh.ctypes.data, gg.ctypes.data))
+        return hh, gg
+
+    def sample_normal(self, normals, scale: float = 1.0, bubble: int = 0):
+        """sample_thickness(normal) (branched_flow_compute.wgsl:110-116, 294-300): thickness * scale at the texel each
+        of the (n, 3) unit normals points at."""
+        q = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+        hh = np.empty(len(q), np.float32)
+        L.check(L.lib().sbx_drainage_sample_normal(self._h, bubble, q.ctypes.data, len(q), float(scale), hh.ctypes.data))
+        return hh
+
     def attach_comm(self, comm) -> None:
         L.check(L.lib().sbx_drainage_attach_comm(self._h, comm._c))
         self._comm = comm

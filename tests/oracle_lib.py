@@ -111,6 +111,8 @@ def lib() -> C.CDLL:
         "orc_view_cos": (d, [d, d, d, dp]),
         "orc_caustic_params_default": (None, [C.POINTER(CausticParams)]),
         "orc_caustic_map": (None, [C.POINTER(CausticParams), p, p]),
+        "orc_sample_thickness_uv": (None, [p, i, i, p, C.c_size_t, p, p]),
+        "orc_sample_thickness_normal": (None, [p, i, i, p, C.c_size_t, C.c_float, p, p]),
         "orc_shade_field": (None, [p, i, i, i, i, d, dp, d, p, i, i, f, f, i, p, i]),
     }
     for name, (res, args) in sig.items():
@@ -362,3 +364,21 @@ def caustic_map(p: CausticParams, thickness: np.ndarray) -> np.ndarray:
     out = np.empty_like(t)
     lib().orc_caustic_map(C.byref(p), t.ctypes.data, out.ctypes.data)
     return out
+
+
+def sample_thickness_uv(thickness: np.ndarray, uv: np.ndarray):
+    t = np.ascontiguousarray(thickness, dtype=np.float32)
+    q = np.ascontiguousarray(uv, dtype=np.float32).reshape(-1, 2)
+    h = np.empty(len(q), np.float32)
+    g = np.empty((len(q), 2), np.float32)
+    lib().orc_sample_thickness_uv(t.ctypes.data, t.shape[1], t.shape[0], q.ctypes.data, len(q), h.ctypes.data, g.ctypes.data)
+    return h, g
+
+
+def sample_thickness_normal(thickness: np.ndarray, normals: np.ndarray, scale: float = 1.0):
+    t = np.ascontiguousarray(thickness, dtype=np.float32)
+    q = np.ascontiguousarray(normals, dtype=np.float32).reshape(-1, 3)
+    h = np.empty(len(q), np.float32)
+    uv = np.empty((len(q), 2), np.float32)
+    lib().orc_sample_thickness_normal(t.ctypes.data, t.shape[1], t.shape[0], q.ctypes.data, len(q), scale, h.ctypes.data, uv.ctypes.data)
+    return h, uv

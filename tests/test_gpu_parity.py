@@ -589,3 +589,46 @@ def test_two_beam_schlick_documented_model(S):
     fused = sim.download_rgb()[0]
     sim.shade(v8)
     assert np.abs(fused.astype(int) - sim.download_rgb()[0].astype(int)).max() <= 1
+
+
+def test_branched_flow_sampling_side_matches_oracle(S):
+    """f2: nearest-texel thickness and eps = 0.01 central-difference gradient at uv positions
+    (branched_flow_compute.wgsl:187-210), on the reference's 128x64 grid and on a larger one."""
+    rng = np.random.default_rng(9)
+    for w, h in ((128, 64), (1024, 512)):
+        f = (synthetic_field(h, w, noise_nm=30.0)).astype(np.float32)
+        sim = S.GPUDrainageSimulator(500e-9, w, h)
+        sim.upload(f)
+        uv = np.concatenate([rng.uniform(-0.05, 1.05, (4000, 2)), [[0, 0], [1, 1], [0.5, 0.0], [0.999999, 0.5]]]).astype(np.float32)
+        gh, gg = sim.sample_uv(uv)
+        rh, rg = O.sample_thickness_uv(f, uv)
+        assert np.array_equal(gh, rh)
+        assert np.array_equal(gg, rg)
+        # sample_thickness(normal): libm and CUDA atan2f/acosf differ by an ulp or two, which can move a sample sitting
+        # on a texel boundary to the neighbouring texel; everywhere else the values are identical
+        nrm = rng.normal(size=(4000, 3)).astype(np.float32)
+        nrm /= np.linalg.norm(nrm, axis=1, keepdims=True)
+        nrm = np.concatenate([nrm, [[0, 1, 0], [0, -1, 0], [1, 0, 0], [-1, 0, 1e-9]]]).astype(np.float32)
+        gn = sim.sample_normal(nrm, scale=2.5)
+        rn, ruv = O.sample_thickness_normal(f, nrm, 2.5)
+        fx, fy = ruv[:, 0] * np.float32(w - 1), ruv[:, 1] * np.float32(h - 1)
+        tie = (np.abs(fx - np.round(fx)) < 1e-3) | (np.abs(fy - np.round(fy)) < 1e-3)
+        assert np.array_equal(gn[~tie], rn[~tie])
+        assert tie.mean() < 0.02
+
+
+def test_many_strips_fall_back_to_the_pole_kernel(S):
+    """More than 128 strips per ring: the pole rows are not folded into the TMA kernel (the strips could not all be
+    co-resident) and k_poles finishes them; results are the same."""
+    nt, nphi = 6, 129 * 1024
+    f = synthetic_field(nt, nphi).astype(np.float32)
+    sim = make_sim(S, nt, nphi, S.PREC_F32, h_ref=0.0)
+    ora = O.OracleDrainage(nt, nphi)
+    sim.upload(f)
+    ora.data[:] = f.astype(np.float64)
+    dt = 0.25 * dt_max(nt, nphi)
+    sim.step(dt, 2)
+    ora.step(dt, 2)
+    got = sim.download()[0]
+    assert np.abs(got / ora.data - 1).max() <= 1e-5
+    assert np.all(got[0] == got[0, 0]) and np.all(got[-1] == got[-1, 0])
