@@ -153,6 +153,10 @@ struct sbx_drainage {
     int peer_up_rows = 0;
     unsigned long long epoch = 0;
     int band_rows = 0;
+    bool use_resident = true;            // SBX_NO_RESIDENT=1: always use the streaming kernels
+    std::vector<FrontTable> res_tabs;    // per-step TFE tables of one resident launch (host)
+    FrontTable *res_tabs_dev = nullptr;
+    size_t res_tabs_cap = 0;
     int64_t launches = 0;
 };
 
@@ -167,6 +171,7 @@ static void free_all(sbx_drainage *h)
         if (h->buf[i]) cudaFree(h->buf[i]);
         if (h->conc[i]) cudaFree(h->conc[i]);
     }
+    cudaFree(h->res_tabs_dev);
     cudaFree(h->coefS);
     cudaFree(h->coefF);
     cudaFree(h->rowSC);
@@ -396,6 +401,7 @@ extern "C" int32_t sbx_drainage_create(const sbx_drainage_cfg *cfg, int32_t devi
     h->href_zero = std::all_of(h->b_href.begin(), h->b_href.end(), [](double v) { return v == 0.0; });
     if (const char *s = getenv("SBX_BAND_ROWS")) h->band_rows = atoi(s);
     if (const char *s = getenv("SBX_NO_TMA")) h->use_tma = atoi(s) == 0;
+    if (const char *s = getenv("SBX_NO_RESIDENT")) h->use_resident = atoi(s) == 0;
 
 #define CU_H(expr)                                                                     \
     do {                                                                               \
@@ -901,9 +907,8 @@ static int32_t step_cpu_sem(sbx_drainage *h, double dt, const RgbArgs &rgb)
     return halo_exchange(h);
 }
 
-static int32_t step_wgsl_sem(sbx_drainage *h, double dt, const RgbArgs &rgb)
+static void fill_wgsl_args(sbx_drainage *h, WgslArgs &a, const RgbArgs &rgb)
 {
-    WgslArgs a;
     memset(&a, 0, sizeof a);
     a.h_in = tbuf<float>(h, h->cur);
     a.h_out = tbuf<float>(h, 1 - h->cur);
@@ -924,6 +929,12 @@ static int32_t step_wgsl_sem(sbx_drainage *h, double dt, const RgbArgs &rgb)
     a.delta_phi = 2.0f * PI_F / (float)h->wp.grid_width;     // drainage.wgsl:93
     a.radius_view = h->wp.bubble_radius;
     a.rgb = rgb;
+}
+
+static int32_t step_wgsl_sem(sbx_drainage *h, double dt, const RgbArgs &rgb)
+{
+    WgslArgs a;
+    fill_wgsl_args(h, a, rgb);
     int n = 0;
     CU(launch_wgsl(a, h->batch, h->band_rows, h->use_tma, h->stream, &n));
     if (rgb.mode != SBX_RGB_NONE && (h->row_begin == 0 || h->row_end == h->num_theta)) {
@@ -940,6 +951,69 @@ static int32_t step_wgsl_sem(sbx_drainage *h, double dt, const RgbArgs &rgb)
     return halo_exchange(h);
 }
 
+// Small whole-sphere grids: take `nsteps` colourless steps inside one launch with the field resident in shared
+// memory (sbx_resident.cu).  Returns the number of steps taken (0: not applicable, the caller streams them).
+static bool resident_possible(const sbx_drainage *h)
+{
+    return h->use_resident && !h->comm && !h->peer_enabled && h->row_begin == 0 && h->rows_local == h->num_theta;
+}
+
+template <typename T>
+static int32_t steps_resident(sbx_drainage *h, double dt, int nsteps, int *taken)
+{
+    *taken = 0;
+    RgbArgs none;
+    memset(&none, 0, sizeof none);
+    StepArgs<T> a;
+    fill_step_args<T>(h, a, dt, none);
+    if (!resident_possible(h) || nsteps < 2 || resident_cluster<T>(a, h->batch, h->strict) == 0) return SBX_OK;
+    constexpr int kChunk = 8192;  // steps per launch (bounds the TFE table upload)
+    while (nsteps > 0) {
+        const int n = std::min(nsteps, kChunk);
+        const FrontTable *tabs = nullptr;
+        if (h->tfe_enabled) {
+            h->res_tabs.resize((size_t)n);
+            for (int s = 0; s < n; ++s) {  // the host state machine, one step at a time (drainage.rs:387-391)
+                tfe_advance(h, dt);
+                tfe_table(h, h->res_tabs[(size_t)s]);
+                h->time += dt;
+            }
+            if (h->res_tabs_cap < (size_t)n) {
+                CU(cudaStreamSynchronize(h->stream));
+                cudaFree(h->res_tabs_dev);
+                h->res_tabs_dev = nullptr;
+                h->res_tabs_cap = 0;
+                CU(cudaMalloc(&h->res_tabs_dev, (size_t)kChunk * sizeof(FrontTable)));
+                h->res_tabs_cap = kChunk;
+            }
+            CU(cudaMemcpyAsync(h->res_tabs_dev, h->res_tabs.data(), (size_t)n * sizeof(FrontTable), cudaMemcpyHostToDevice, h->stream));
+            tabs = h->res_tabs_dev;
+        } else {
+            for (int s = 0; s < n; ++s) h->time += dt;
+        }
+        CU(launch_resident<T>(a, h->batch, h->strict, tabs, n, h->stream));
+        h->launches++;
+        *taken += n;
+        nsteps -= n;
+    }
+    return SBX_OK;
+}
+
+static int32_t steps_resident_wgsl(sbx_drainage *h, double dt, int nsteps, int *taken)
+{
+    *taken = 0;
+    RgbArgs none;
+    memset(&none, 0, sizeof none);
+    WgslArgs a;
+    fill_wgsl_args(h, a, none);
+    if (!resident_possible(h) || nsteps < 2 || resident_cluster_wgsl(a, h->batch) == 0) return SBX_OK;
+    CU(launch_resident_wgsl(a, h->batch, nsteps, h->stream));  // in place on the current buffers
+    for (int s = 0; s < nsteps; ++s) h->time += dt;             // gpu_drainage.rs:368
+    h->launches++;
+    *taken = nsteps;
+    return SBX_OK;
+}
+
 static int32_t do_steps(sbx_drainage *h, double dt, int32_t nsteps, const sbx_view *view)
 {
     if (nsteps < 0) return fail(SBX_ERR_INVALID, "nsteps < 0");
@@ -948,6 +1022,15 @@ static int32_t do_steps(sbx_drainage *h, double dt, int32_t nsteps, const sbx_vi
     RgbArgs rgb;
     rc = prepare_rgb(h, view, rgb);
     if (rc != SBX_OK) return rc;
+    // only the last step's colour frame is observable: the steps before it may run without the colour stage
+    const int plain = rgb.mode == SBX_RGB_NONE ? nsteps : nsteps - 1;
+    if (plain >= 2) {
+        int taken = 0;
+        rc = h->wgsl ? steps_resident_wgsl(h, dt, plain, &taken)
+                     : (h->f64 ? steps_resident<double>(h, dt, plain, &taken) : steps_resident<float>(h, dt, plain, &taken));
+        if (rc != SBX_OK) return rc;
+        nsteps -= taken;
+    }
     for (int s = 0; s < nsteps; ++s) {
         rc = h->wgsl ? step_wgsl_sem(h, dt, rgb) : (h->f64 ? step_cpu_sem<double>(h, dt, rgb) : step_cpu_sem<float>(h, dt, rgb));
         if (rc != SBX_OK) return rc;

@@ -19,6 +19,16 @@ bool march_tma_folds_poles(const StepArgs<T> &a);
 template <typename T>
 cudaError_t launch_march_tma(StepArgs<T> a, int batch, bool tfe, int band_rows_req, cudaStream_t st, int *pole_slots);
 
+// shared-memory-resident multi-step kernels for small whole-sphere grids (sbx_resident.cu): cluster width that
+// would be used, 0 = not applicable
+template <typename T>
+int resident_cluster(const StepArgs<T> &a, int batch, bool strict);
+template <typename T>
+cudaError_t launch_resident(StepArgs<T> a, int batch, bool strict, const FrontTable *tables_dev, int nsteps,
+                            cudaStream_t st);
+int resident_cluster_wgsl(const WgslArgs &a, int batch);
+cudaError_t launch_resident_wgsl(WgslArgs a, int batch, int nsteps, cudaStream_t st);
+
 template <typename T>
 cudaError_t launch_tfe_pass(T *buf, long long bubble_stride, int num_phi, int row_begin, int rows_local,
                             int batch, const FrontTable &ft, double factor, cudaStream_t st, int *launches);
