@@ -77,15 +77,37 @@ def single(name, nt, nphi, prec, mode, steps, bpc, h_ref=0.0, note="", semantics
 which = sys.argv[1:] or ["c1", "c2", "c3", "c4", "c5", "modes"]
 
 if "c1" in which:
-    # config 1: config/default.json, 128x256, 1000 steps (launch-bound: 2 kernels of ~3 us per step)
+    # config 1: config/default.json, 128x256, 1000 steps.  A multi-step call keeps the field resident in shared memory
+    # (sbx_resident.cu); one step per call streams through HBM and is launch-bound.
+    def loop(f):
+        def run(n):
+            for _ in range(n):
+                f()
+        return run
+
     sim = S.DrainageSimulator(S.SimulationConfig.default())
     sim.set_stream(stream.cuda_stream)
     ms = timed(lambda n: sim.step(1e-3, n), 1000, warm=50)
-    report("C1 128x256 default.json drainage (f32 offset storage, TFE on), per step", 126 * 256, 8, ms, "launch-bound")
+    report("C1 128x256 default.json drainage (f32 offset storage, TFE on), 1000 steps per call", 126 * 256, 8, ms,
+           "shared-memory resident: no HBM traffic inside the call; exchange-latency-bound")
+    ms = timed(loop(lambda: sim.step(1e-3, 1)), 1000, warm=50)
+    report("C1 128x256 drainage, one step per call", 126 * 256, 8, ms, "launch-bound")
     view = S.View()
-    ms = timed(lambda n: sim.step_fused(1e-3, view, n), 1000, warm=50)
-    report("C1 128x256 fused drainage + LUT interference, per step", 126 * 256, 12, ms, "launch-bound")
+    ms = timed(loop(lambda: sim.step_fused(1e-3, view, 1)), 1000, warm=50)
+    report("C1 128x256 fused drainage + LUT interference, one frame per step", 126 * 256, 12, ms, "launch-bound")
+    ms = timed(loop(lambda: sim.step_fused(1e-3, view, 10)), 100, warm=10) / 10.0
+    report("C1 128x256 fused, 10 steps per frame (9 resident + 1 fused), per step", 126 * 256, 12, ms, "")
     sim.close()
+    sim = S.DrainageSimulator(S.SimulationConfig.default(), precision=S.PREC_F64_STRICT)
+    sim.set_stream(stream.cuda_stream)
+    ms = timed(lambda n: sim.step(1e-3, n), 1000, warm=50)
+    report("C1 128x256 f64 STRICT (bit-identical to the reference), 1000 steps per call", 126 * 256, 16, ms, "resident")
+    sim.close()
+    g = S.GPUDrainageSimulator(500e-9, 128, 64)
+    g.set_stream(stream.cuda_stream)
+    ms = timed(lambda n: g.dispatch(n), 1000, warm=50)
+    report("reference GPU grid 128x64 WGSL semantics, 1000 dispatches per call", 62 * 128, 16, ms, "resident")
+    g.close()
 
 if "c2" in which:
     single("C2 2048x4096 f32 fused LUT->RGBA8", 2048, 4096, S.PREC_F32, S.RGB_LUT, 400, 12, note="64 MiB working set: L2-resident")

@@ -145,6 +145,28 @@ def test_resident_batch_of_independent_bubbles(S):
         assert np.abs(got[i] / ora.data - 1).max() < 1e-12, i
 
 
+@pytest.mark.parametrize("prec_name", ["PREC_F32", "PREC_F64"])
+def test_resident_result_does_not_depend_on_cluster_width(S, prec_name):
+    """The batch size picks the cluster width (16, 8, 4, 2, 1 CTAs per bubble).  Cell arithmetic and the order of the
+    pole sums do not depend on it, so every bubble of every batch equals the lone bubble bit for bit."""
+    nt, nphi = 48, 64
+    prec = getattr(S, prec_name)
+    f = synthetic_field(nt, nphi).astype(np.float32).astype(np.float64)
+    dt = 0.25 * dt_max(nt, nphi)
+    ref = None
+    for nb in (1, 12, 20, 40, 100):
+        sim = make_sim(S, nt, nphi, prec, h_ref=0.0 if prec == S.PREC_F32 else None, batch=nb)
+        sim.upload(np.broadcast_to(f, (nb, nt, nphi)).copy())
+        l0 = launches(sim)
+        sim.step(dt, 50)
+        assert launches(sim) - l0 == 1
+        got = sim.download()
+        if ref is None:
+            ref = got[0].copy()
+        for b in range(nb):
+            assert np.array_equal(got[b], ref), (nb, b)
+
+
 @pytest.mark.parametrize("marangoni", [False, True])
 @pytest.mark.parametrize("w,h", [(128, 64), (50, 37), (256, 128)])
 def test_wgsl_resident_matches_f32_oracle(S, w, h, marangoni, monkeypatch):
