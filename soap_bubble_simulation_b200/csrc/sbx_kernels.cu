@@ -18,6 +18,17 @@
 
 namespace sbx {
 
+int device_sm_count()
+{
+    static int n = 0;
+    if (n == 0) {
+        int dev = 0;
+        cudaGetDevice(&dev);
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0) n = 148;
+    }
+    return n;
+}
+
 // ------------------------------------------------------------------ colour output helpers
 template <int MODE, int VEC>
 __device__ __forceinline__ void emit_rgb(const typename Dnm<MODE>::type *d_nm, const float *ci, const RgbArgs &rgb,

@@ -5,6 +5,26 @@
 
 namespace sbx {
 
+// Rows per latitude band for the marching kernels.  Large grids run many waves of CTAs and the band height does not
+// matter (24 rows measured flat at 8192 x 16384); when the whole launch is only a few waves, a band height that leaves
+// the last wave half empty costs its full time -- 2048 x 4096 at 24 rows is 344 CTAs on 592 slots, at 14 rows 588:
+// +30 %.  Cost model: waves x (band rows + ring fill / halo overhead).
+inline int auto_band_rows(int rows, long long ctas_per_band, int slots, int dflt)
+{
+    if (rows <= 0) return 1;
+    if (slots <= 0 || ctas_per_band * ((rows + dflt - 1) / dflt) >= 4LL * slots) return dflt < rows ? dflt : rows;
+    int best = dflt < rows ? dflt : rows;
+    double best_cost = 1e300;
+    for (int b = 6; b <= 64 && b <= rows; ++b) {
+        const long long bands = (rows + b - 1) / b;
+        const long long waves = (ctas_per_band * bands + slots - 1) / slots;
+        const double cost = (double)waves * (b + 4.0);
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = b; }
+    }
+    return best;
+}
+int device_sm_count();
+
 // one drainage step in CPU semantics: marching stencil (+ fused colour) then the pole rows.
 // `launches` is incremented once per kernel launched.
 template <typename T>

@@ -475,7 +475,8 @@ cudaError_t launch_march_tma(StepArgs<T> a, int batch, bool tfe, int band_rows_r
     const int consumers = tma_consumers<T>(a.num_phi);
     const int strip = consumers * VEC;
     const int gx = (a.num_phi + strip - 1) / strip;
-    int band_rows = band_rows_req > 0 ? band_rows_req : 24;  // multiple of the 3-row ring stage; measured best at 8192x16384
+    int band_rows = band_rows_req > 0 ? band_rows_req
+                                      : auto_band_rows(rows, (long long)gx * batch, device_sm_count() * MinBlocks<T>::value, 24);
     if (band_rows > rows) band_rows = rows;
     const int gy = (rows + band_rows - 1) / band_rows;
     a.band_rows = band_rows;

@@ -272,7 +272,7 @@ cudaError_t launch_wgsl_tma(WgslArgs a, int batch, int band_rows_req, cudaStream
     while (consumers > 32 && consumers * 2 >= a.num_phi) consumers >>= 1;
     const int strip = consumers * 4;
     const int gx = (a.num_phi + strip - 1) / strip;
-    int band_rows = band_rows_req > 0 ? band_rows_req : 24;
+    int band_rows = band_rows_req > 0 ? band_rows_req : auto_band_rows(rows, (long long)gx * batch, device_sm_count() * 3, 24);
     if (band_rows > rows) band_rows = rows;
     const int gy = (rows + band_rows - 1) / band_rows;
     a.band_rows = band_rows;
