@@ -419,7 +419,8 @@ static cudaError_t launch_one(const StepArgs<T> &a, dim3 grid, dim3 block, size_
     attr[0].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = attr;
     // PDL pays when the grid has several waves (measured: +1 % at 8192x16384, -10 % at the single-wave 2048x4096)
-    cfg.numAttrs = (use_pdl() && (size_t)grid.x * grid.y * grid.z >= 1184) ? 1 : 0;
+    static const size_t pdl_min = [] { const char *e = getenv("SBX_PDL_MIN_CTAS"); return e ? (size_t)atoll(e) : (size_t)500; }();
+    cfg.numAttrs = (use_pdl() && (size_t)grid.x * grid.y * grid.z >= pdl_min) ? 1 : 0;
     return cudaLaunchKernelEx(&cfg, k_march_tma<T, MODE, TFE>, a);
 }
 
