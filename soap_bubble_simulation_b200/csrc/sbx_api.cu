@@ -867,7 +867,7 @@ static int32_t step_cpu_sem(sbx_drainage *h, double dt, const RgbArgs &rgb)
             fill_step_args<T>(h, s, dt, rgb);
             s.l_first = 1;
             s.l_last = h->rows_local;
-            CU(launch_shade<T>(s, h->batch, h->band_rows, h->stream, &n));
+            CU(launch_shade<T>(s, h->batch, h->band_rows, h->stream, &n, h->use_tma));
         }
     } else {
         a.fronts = ft;
@@ -1065,7 +1065,7 @@ extern "C" int32_t sbx_drainage_shade(sbx_drainage *h, const sbx_view *view)
         StepArgs<double> s;
         fill_step_args<double>(h, s, 0.0, rgb);
         s.l_first = 1; s.l_last = h->rows_local;
-        CU(launch_shade<double>(s, h->batch, h->band_rows, h->stream, &n));
+        CU(launch_shade<double>(s, h->batch, h->band_rows, h->stream, &n, h->use_tma));
     } else {
         StepArgs<float> s;
         fill_step_args<float>(h, s, 0.0, rgb);
@@ -1073,7 +1073,7 @@ extern "C" int32_t sbx_drainage_shade(sbx_drainage *h, const sbx_view *view)
         if (h->wgsl) {
             // WGSL handles carry radius in params, h_ref = 0; BubbleParam was filled from them at create
         }
-        CU(launch_shade<float>(s, h->batch, h->band_rows, h->stream, &n));
+        CU(launch_shade<float>(s, h->batch, h->band_rows, h->stream, &n, h->use_tma));
     }
     h->launches += n;
     return SBX_OK;

@@ -980,12 +980,16 @@ template cudaError_t launch_tfe_pass<float>(float *, long long, int, int, int, i
 template cudaError_t launch_tfe_pass<double>(double *, long long, int, int, int, int, const FrontTable &, double, cudaStream_t, int *);
 
 template <typename T>
-cudaError_t launch_shade(StepArgs<T> a, int batch, int band_rows_req, cudaStream_t st, int *launches)
+cudaError_t launch_shade(StepArgs<T> a, int batch, int band_rows_req, cudaStream_t st, int *launches, bool use_tma)
 {
     constexpr int VECW = 16 / (int)sizeof(T);
     const bool vec_ok = (a.num_phi % VECW) == 0;
     const int rows = a.l_last - a.l_first + 1;
     if (rows <= 0) return cudaSuccess;
+    if (use_tma && rows >= 8 && shade_tma_supported<T>(a)) {
+        ++*launches;
+        return launch_shade_tma<T>(a, batch, band_rows_req, st);
+    }
     dim3 grid, block;
     int band_rows;
     march_geometry(a.num_phi, vec_ok ? VECW : 1, rows, batch, band_rows_req, grid, block, band_rows);
@@ -1008,8 +1012,8 @@ cudaError_t launch_shade(StepArgs<T> a, int batch, int band_rows_req, cudaStream
     ++*launches;
     return cudaGetLastError();
 }
-template cudaError_t launch_shade<float>(StepArgs<float>, int, int, cudaStream_t, int *);
-template cudaError_t launch_shade<double>(StepArgs<double>, int, int, cudaStream_t, int *);
+template cudaError_t launch_shade<float>(StepArgs<float>, int, int, cudaStream_t, int *, bool);
+template cudaError_t launch_shade<double>(StepArgs<double>, int, int, cudaStream_t, int *, bool);
 
 cudaError_t launch_wgsl(WgslArgs a, int batch, int band_rows_req, bool use_tma, cudaStream_t st, int *launches)
 {

@@ -54,7 +54,12 @@ cudaError_t launch_tfe_pass(T *buf, long long bubble_stride, int num_phi, int ro
                             int batch, const FrontTable &ft, double factor, cudaStream_t st, int *launches);
 
 template <typename T>
-cudaError_t launch_shade(StepArgs<T> a, int batch, int band_rows_req, cudaStream_t st, int *launches);
+cudaError_t launch_shade(StepArgs<T> a, int batch, int band_rows_req, cudaStream_t st, int *launches, bool use_tma = false);
+// TMA-staged ring variant (sbx_shade_tma.cu): whole 16-byte packets per row, RGBA8 output
+template <typename T>
+bool shade_tma_supported(const StepArgs<T> &a);
+template <typename T>
+cudaError_t launch_shade_tma(StepArgs<T> a, int batch, int band_rows_req, cudaStream_t st);
 
 cudaError_t launch_wgsl(WgslArgs a, int batch, int band_rows_req, bool use_tma, cudaStream_t st, int *launches);
 // TMA-staged ring variant (sbx_wgsl_tma.cu): num_phi % 4 == 0, RGBA8 or no colour

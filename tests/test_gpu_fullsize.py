@@ -96,6 +96,34 @@ def test_tma_and_direct_kernels_agree_c2(S, monkeypatch):
     assert np.abs(out[0][1].astype(int) - out[1][1].astype(int)).max() <= 1
 
 
+@pytest.mark.parametrize("prec_name", ["PREC_F32", "PREC_F64"])
+@pytest.mark.parametrize("mode_name", ["RGB_LUT", "RGB_SCHLICK_TWO_BEAM", "RGB_EXACT3"])
+def test_shade_tma_ring_equals_direct_kernel(S, monkeypatch, prec_name, mode_name):
+    """sbx_drainage_shade on the TMA ring (sbx_shade_tma.cu) and the direct-load kernel run the same colour stage on
+    the same values: identical RGBA8 frames, ragged band heights and a partial last strip included."""
+    nt, nphi = 203, 4096 + 512
+    f = synthetic_field(nt, nphi, h0_nm=650.0, noise_nm=80.0, dtype=np.float32)
+    view = S.View(mode=getattr(S, mode_name), format=S.OUT_RGBA8, intensity=2.0)
+    frames = []
+    for no_tma in ("0", "1"):
+        monkeypatch.setenv("SBX_NO_TMA", no_tma)
+        sim = S.DrainageSimulator(S.SimulationConfig.default(), precision=getattr(S, prec_name), num_theta=nt, num_phi=nphi,
+                                  h_ref=0.0 if prec_name == "PREC_F32" else None)
+        sim.upload(f)
+        sim.shade(view)
+        frames.append(sim.download_rgb()[0])
+    assert frames[0].shape == (nt, nphi, 4)
+    if prec_name == "PREC_F32":
+        assert np.array_equal(frames[0], frames[1])
+    else:
+        # the f64 direct kernel forms the thickness in nm and rounds the channels with its own helpers: same colour
+        # up to a rounding tie
+        d = np.abs(frames[0].astype(int) - frames[1].astype(int))
+        print(f"\n[shade f64 {mode_name}] max {d.max()} LSB, {np.count_nonzero(d)} of {d.size} channels differ")
+        assert d.max() <= 1 and np.count_nonzero(d) <= 0.01 * d.size
+    assert frames[0][..., :3].std() > 1.0  # a real picture, not a constant
+
+
 def test_band_rows_do_not_change_results(S, monkeypatch):
     nt, nphi = 1024, 2048
     f = synthetic_field(nt, nphi, dtype=np.float32)
