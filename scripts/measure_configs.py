@@ -182,7 +182,8 @@ if "f2" in which or "c3" in which:
             L.check(L.lib().sbx_drainage_caustics(sim._h, C.byref(cp), None))
 
     ms = timed(caus, 50)
-    report("f2 caustic map (9-point stencil consumer) of 8192x16384", 8192 * 16384, 8, ms, "first version: direct loads")
+    report("f2 caustic map (9-point stencil consumer) of 8192x16384", 8192 * 16384, 8, ms,
+           "direct loads" if os.environ.get("SBX_NO_TMA") == "1" else "TMA ring")
     sim.close()
 
 print("\n| config | ms/step | Gcell/s | B/cell | GB/s | % of measured HBM peak | note |")

@@ -1417,9 +1417,9 @@ extern "C" int32_t sbx_drainage_caustics(sbx_drainage *h, const sbx_caustic_para
     q.grid_height = (uint32_t)h->num_theta;
     const double *href = h->href_zero ? nullptr : h->href_dev;
     if (h->f64) CU(launch_caustics<double>(tbuf<double>(h, h->cur), h->bubble_stride, h->caustic_buf, h->num_phi, h->num_theta,
-                                           h->row_begin, h->rows_local, h->batch, href, q, h->stream));
+                                           h->row_begin, h->rows_local, h->batch, href, q, h->stream, h->use_tma));
     else CU(launch_caustics<float>(tbuf<float>(h, h->cur), h->bubble_stride, h->caustic_buf, h->num_phi, h->num_theta,
-                                   h->row_begin, h->rows_local, h->batch, href, q, h->stream));
+                                   h->row_begin, h->rows_local, h->batch, href, q, h->stream, h->use_tma));
     h->launches++;
     if (host_out) {
         CU(cudaMemcpyAsync(host_out, h->caustic_buf, cells * sizeof(float), cudaMemcpyDeviceToHost, h->stream));

@@ -347,4 +347,29 @@ __device__ __forceinline__ uint32_t shade_px(T h, T href, float href_u, float co
 }
 
 
+// ------------------------------------------------------------------ caustic map (thickness-buffer consumer, row f2)
+// caustics_compute.wgsl::main (src/render/shaders/caustics_compute.wgsl:29-126): 9-point stencil on the thickness
+// buffer, phi wrapped, theta clamped at the poles (ghost rows supply the neighbours of a latitude band).
+__device__ __forceinline__ float caustic_intensity(float center, float left, float right, float up, float down,
+                                                   float ul, float ur, float dl, float dr, const sbx_caustic_params &p)
+{
+    // h = 1: the divisions by 2h, h^2 and 4h^2 are exact scalings (caustics_compute.wgsl:46-92)
+    const float gx = (right - left) * 0.5f, gy = (down - up) * 0.5f;
+    const float lr = left + right, ud = up + down;
+    const float laplacian = ((lr + up) + down) - 4.0f * center;
+    const float d2x = lr - 2.0f * center, d2y = ud - 2.0f * center;
+    const float dxy = (((dr - dl) - ur) + ul) * 0.25f;
+    const float hessian_det = __fsub_rn(__fmul_rn(d2x, d2y), __fmul_rn(dxy, dxy));
+    const float curvature_factor = -laplacian * p.focal_length;                                   // :95-112
+    const float focusing = rcp_approx(fmaxf(fabsf(1.0f - curvature_factor), 0.01f));
+    const float branch_factor = hessian_det < -p.branch_threshold ? 1.5f : 1.0f;
+    const float grad_mag = sqrt_approx(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)));
+    const float refraction_factor = fmaf(grad_mag, 0.5f, 1.0f);
+    float intensity = focusing * branch_factor * refraction_factor;
+    intensity = ex2_approx(lg2_approx(intensity) * p.caustic_sharpness);  // pow(x, sharpness), x >= 0.005
+    intensity *= p.caustic_intensity;
+    return fminf(fmaxf(intensity, 0.f), 10.f);
+}
+
+
 }  // namespace sbx

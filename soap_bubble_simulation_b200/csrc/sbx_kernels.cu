@@ -715,29 +715,6 @@ cudaError_t launch_lut_shade_points(cudaTextureObject_t lut, float inv_max_nm, f
     return cudaGetLastError();
 }
 
-// caustics_compute.wgsl::main (src/render/shaders/caustics_compute.wgsl:29-126): 9-point stencil on the thickness
-// buffer, phi wrapped, theta clamped at the poles (ghost rows supply the neighbours of a latitude band).
-__device__ __forceinline__ float caustic_intensity(float center, float left, float right, float up, float down,
-                                                   float ul, float ur, float dl, float dr, const sbx_caustic_params &p)
-{
-    // h = 1: the divisions by 2h, h^2 and 4h^2 are exact scalings (caustics_compute.wgsl:46-92)
-    const float gx = (right - left) * 0.5f, gy = (down - up) * 0.5f;
-    const float lr = left + right, ud = up + down;
-    const float laplacian = ((lr + up) + down) - 4.0f * center;
-    const float d2x = lr - 2.0f * center, d2y = ud - 2.0f * center;
-    const float dxy = (((dr - dl) - ur) + ul) * 0.25f;
-    const float hessian_det = __fsub_rn(__fmul_rn(d2x, d2y), __fmul_rn(dxy, dxy));
-    const float curvature_factor = -laplacian * p.focal_length;                                   // :95-112
-    const float focusing = rcp_approx(fmaxf(fabsf(1.0f - curvature_factor), 0.01f));
-    const float branch_factor = hessian_det < -p.branch_threshold ? 1.5f : 1.0f;
-    const float grad_mag = sqrt_approx(__fadd_rn(__fmul_rn(gx, gx), __fmul_rn(gy, gy)));
-    const float refraction_factor = fmaf(grad_mag, 0.5f, 1.0f);
-    float intensity = focusing * branch_factor * refraction_factor;
-    intensity = ex2_approx(lg2_approx(intensity) * p.caustic_sharpness);  // pow(x, sharpness), x >= 0.005
-    intensity *= p.caustic_intensity;
-    return fminf(fmaxf(intensity, 0.f), 10.f);
-}
-
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256) k_caustics(const T *buf, long long bubble_stride, float *out, int num_phi,
                                                   int num_theta, int row_begin, int rows_local, const double *href,
@@ -776,18 +753,21 @@ __global__ void __launch_bounds__(256) k_caustics(const T *buf, long long bubble
 
 template <typename T>
 cudaError_t launch_caustics(const T *buf, long long bubble_stride, float *out, int num_phi, int num_theta, int row_begin,
-                            int rows_local, int batch, const double *href, const sbx_caustic_params &p, cudaStream_t st)
+                            int rows_local, int batch, const double *href, const sbx_caustic_params &p, cudaStream_t st,
+                            bool use_tma)
 {
     constexpr int VECW = 16 / (int)sizeof(T);
     const bool vec_ok = num_phi % VECW == 0;
+    if (use_tma && vec_ok && num_phi >= 32 * VECW && rows_local >= 8)
+        return launch_caustics_tma<T>(buf, bubble_stride, out, num_phi, num_theta, row_begin, rows_local, batch, href, p, st);
     const int packets = vec_ok ? num_phi / VECW : num_phi;
     const dim3 block(64, 4), grid((unsigned)((packets + 63) / 64), (unsigned)((rows_local + 3) / 4), (unsigned)batch);
     if (vec_ok) k_caustics<T, VECW><<<grid, block, 0, st>>>(buf, bubble_stride, out, num_phi, num_theta, row_begin, rows_local, href, p);
     else k_caustics<T, 1><<<grid, block, 0, st>>>(buf, bubble_stride, out, num_phi, num_theta, row_begin, rows_local, href, p);
     return cudaGetLastError();
 }
-template cudaError_t launch_caustics<float>(const float *, long long, float *, int, int, int, int, int, const double *, const sbx_caustic_params &, cudaStream_t);
-template cudaError_t launch_caustics<double>(const double *, long long, float *, int, int, int, int, int, const double *, const sbx_caustic_params &, cudaStream_t);
+template cudaError_t launch_caustics<float>(const float *, long long, float *, int, int, int, int, int, const double *, const sbx_caustic_params &, cudaStream_t, bool);
+template cudaError_t launch_caustics<double>(const double *, long long, float *, int, int, int, int, int, const double *, const sbx_caustic_params &, cudaStream_t, bool);
 
 // branched_flow_compute.wgsl:187-210 for n query points
 template <typename T>

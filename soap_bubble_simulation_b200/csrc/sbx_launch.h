@@ -88,7 +88,11 @@ cudaError_t launch_lut_shade_points(cudaTextureObject_t lut, float inv_max_nm, f
                                     const float *cos_theta, size_t n, float *rgb, cudaStream_t st);
 template <typename T>
 cudaError_t launch_caustics(const T *buf, long long bubble_stride, float *out, int num_phi, int num_theta, int row_begin,
-                            int rows_local, int batch, const double *href, const sbx_caustic_params &p, cudaStream_t st);
+                            int rows_local, int batch, const double *href, const sbx_caustic_params &p, cudaStream_t st,
+                            bool use_tma = false);
+template <typename T>
+cudaError_t launch_caustics_tma(const T *buf, long long bubble_stride, float *out, int num_phi, int num_theta, int row_begin,
+                                int rows_local, int batch, const double *href, const sbx_caustic_params &p, cudaStream_t st);
 template <typename T>
 cudaError_t launch_sample_uv(const T *field, int W, int H, float href, const float *uv, size_t n, float *out_h,
                              float *out_grad, cudaStream_t st);

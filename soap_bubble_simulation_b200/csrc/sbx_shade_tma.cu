@@ -173,4 +173,141 @@ cudaError_t launch_shade_tma(StepArgs<T> a, int batch, int band_rows_req, cudaSt
 template cudaError_t launch_shade_tma<float>(StepArgs<float>, int, int, cudaStream_t);
 template cudaError_t launch_shade_tma<double>(StepArgs<double>, int, int, cudaStream_t);
 
+// ------------------------------------------------------------------ caustic map on the ring (row f2)
+// caustics_compute.wgsl:29-126: a 9-point stencil of the thickness buffer, phi wrapped, theta clamped at the poles.
+// One row per ring slot (strip + a 16-byte halo each side, wrapped across the seam as in sbx_march_tma.cu); an output
+// row reads slots l-1, l, l+1 and hands slot l-1 back.  The rows above the first / below the last pole row are the
+// pole rows themselves (clamp), rows beyond a latitude band are the neighbours' ghost rows.
+namespace {
+constexpr int kCSlots = 8;
+}
+
+template <typename T>
+__global__ void __launch_bounds__(288, 4)
+k_caustics_tma(const T *buf, long long bubble_stride, float *out, int N, int NT, int row_begin, int rows_local,
+               const double *href, sbx_caustic_params p, int band_rows)
+{
+    constexpr int VEC = 16 / (int)sizeof(T);
+    constexpr int HALO = VEC;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    const int C = blockDim.x - 32;
+    const int strip = VEC * C;
+    const int c0 = blockIdx.x * strip;
+    const int w = min(strip, N - c0);
+    const int rowf = strip + 2 * HALO;
+    T *ring = reinterpret_cast<T *>(smem_raw);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kCSlots * rowf * sizeof(T));
+    uint64_t *empty = full + kCSlots;
+    const int b = blockIdx.z;
+    const T *in = buf + (long long)b * bubble_stride;
+    const int l0 = 1 + blockIdx.y * band_rows;
+    const int l1 = min(l0 + band_rows - 1, rows_local);
+    if (l0 > l1) return;
+    const int nout = l1 - l0 + 1, nload = nout + 2;
+    const int nwarps_c = C >> 5;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kCSlots; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], nwarps_c);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    __syncthreads();
+
+    if (threadIdx.x >= C) {
+        if (threadIdx.x == C) {
+            const bool wrapL = c0 == 0, wrapR = c0 + w >= N;
+            const uint32_t main_elems = (uint32_t)w + (wrapL ? 0 : HALO) + (wrapR ? 0 : HALO);
+            const uint32_t row_bytes = ((uint32_t)w + 2 * HALO) * (uint32_t)sizeof(T);
+            for (int r = 0; r < nload; ++r) {
+                const int s = r % kCSlots;
+                if (r >= kCSlots) mbar_wait(&empty[s], (uint32_t)(((r / kCSlots) - 1) & 1));
+                int lr = l0 - 1 + r;                      // local row (0 = ghost above, rows_local + 1 = ghost below)
+                const int g = row_begin + lr - 1;         // its global row
+                if (g < 0) lr += 1;                       // clamp(y - 1, 0, height - 1)
+                if (g > NT - 1) lr -= 1;                  // clamp(y + 1, 0, height - 1)
+                mbar_expect_tx(&full[s], row_bytes);
+                const T *grow_ptr = in + (long long)lr * N;
+                T *dst = ring + (size_t)s * rowf;
+                tma_bulk_g2s(dst + (wrapL ? HALO : 0), grow_ptr + c0 - (wrapL ? 0 : HALO), main_elems * (uint32_t)sizeof(T), &full[s]);
+                if (wrapL) tma_bulk_g2s(dst, grow_ptr + (N - HALO), 16u, &full[s]);
+                if (wrapR) tma_bulk_g2s(dst + HALO + w, grow_ptr, 16u, &full[s]);
+            }
+        }
+        return;
+    }
+
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int jloc = tid * VEC;
+    const bool active = jloc < w;
+    const int soff = HALO + (active ? jloc : 0);
+    const float hr = href ? (float)href[b] : 0.f;
+    float *dst = out + ((long long)b * rows_local + (l0 - 1)) * N + c0 + (active ? jloc : 0);
+
+    auto load_row = [&](float (&r)[VEC + 2], int slot) {
+        const T *src = ring + (size_t)slot * rowf + soff;
+        if constexpr (VEC == 4) {
+            const float4 q = *reinterpret_cast<const float4 *>(src);
+            r[1] = q.x + hr; r[2] = q.y + hr; r[3] = q.z + hr; r[4] = q.w + hr;
+        } else {
+            const double2 q = *reinterpret_cast<const double2 *>(src);
+            r[1] = (float)q.x + hr; r[2] = (float)q.y + hr;
+        }
+        r[0] = (float)src[-1] + hr;
+        r[VEC + 1] = (float)src[VEC] + hr;
+    };
+
+    float up[VEC + 2], cur[VEC + 2], dn[VEC + 2];
+    mbar_wait(&full[0], 0);
+    load_row(up, 0);
+    mbar_wait(&full[1 % kCSlots], 0);
+    load_row(cur, 1);
+#pragma unroll 1
+    for (int i = 0; i < nout; ++i, dst += N) {
+        const int rl = i + 2, s = rl % kCSlots;
+        mbar_wait(&full[s], (uint32_t)((rl / kCSlots) & 1));
+        load_row(dn, s);
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[i % kCSlots]);  // row i (the `up` row) is in registers everywhere in this warp
+        if (active) {
+            float o[VEC];
+#pragma unroll
+            for (int j = 0; j < VEC; ++j)
+                o[j] = caustic_intensity(cur[1 + j], cur[j], cur[2 + j], up[1 + j], dn[1 + j], up[j], up[2 + j], dn[j], dn[2 + j], p);
+            if constexpr (VEC == 4) *reinterpret_cast<float4 *>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+            else *reinterpret_cast<float2 *>(dst) = make_float2(o[0], o[1]);
+        }
+#pragma unroll
+        for (int j = 0; j < VEC + 2; ++j) { up[j] = cur[j]; cur[j] = dn[j]; }
+    }
+}
+
+template <typename T>
+cudaError_t launch_caustics_tma(const T *buf, long long bubble_stride, float *out, int num_phi, int num_theta, int row_begin,
+                                int rows_local, int batch, const double *href, const sbx_caustic_params &p, cudaStream_t st)
+{
+    constexpr int VEC = 16 / (int)sizeof(T);
+    int consumers = 256;
+    while (consumers > 32 && consumers * VEC / 2 >= num_phi) consumers >>= 1;
+    const int strip = consumers * VEC;
+    const int gx = (num_phi + strip - 1) / strip;
+    int band_rows = auto_band_rows(rows_local, (long long)gx * batch, device_sm_count() * 4, 32);
+    const dim3 grid((unsigned)gx, (unsigned)((rows_local + band_rows - 1) / band_rows), (unsigned)batch), block((unsigned)(consumers + 32));
+    const size_t smem = (size_t)kCSlots * (strip + 2 * VEC) * sizeof(T) + 2 * kCSlots * sizeof(uint64_t);
+    static bool configured[64] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !configured[dev]) {
+        cudaError_t e = cudaFuncSetAttribute(k_caustics_tma<T>, cudaFuncAttributePreferredSharedMemoryCarveout, (int)cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        configured[dev] = true;
+    }
+    k_caustics_tma<T><<<grid, block, smem, st>>>(buf, bubble_stride, out, num_phi, num_theta, row_begin, rows_local, href, p, band_rows);
+    return cudaGetLastError();
+}
+template cudaError_t launch_caustics_tma<float>(const float *, long long, float *, int, int, int, int, int, const double *, const sbx_caustic_params &, cudaStream_t);
+template cudaError_t launch_caustics_tma<double>(const double *, long long, float *, int, int, int, int, int, const double *, const sbx_caustic_params &, cudaStream_t);
+
 }  // namespace sbx

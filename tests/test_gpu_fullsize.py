@@ -124,6 +124,26 @@ def test_shade_tma_ring_equals_direct_kernel(S, monkeypatch, prec_name, mode_nam
     assert frames[0][..., :3].std() > 1.0  # a real picture, not a constant
 
 
+@pytest.mark.parametrize("prec_name", ["PREC_F32", "PREC_F64"])
+def test_caustics_tma_ring_equals_direct_kernel(S, monkeypatch, prec_name):
+    """f2: the caustic map on the TMA ring and with direct loads is the same function of the same nine values: identical
+    floats, pole clamp, seam wrap and a partial last strip included."""
+    nt, nphi = 203, 4096 + 512
+    f = (synthetic_field(nt, nphi, noise_nm=40.0) * 1e6).astype(np.float32)
+    maps = []
+    for no_tma in ("0", "1"):
+        monkeypatch.setenv("SBX_NO_TMA", no_tma)
+        sim = S.DrainageSimulator(S.SimulationConfig.default(), precision=getattr(S, prec_name), num_theta=nt, num_phi=nphi,
+                                  h_ref=0.0 if prec_name == "PREC_F32" else None)
+        sim.upload(f)
+        maps.append(sim.caustic_map(focal_length=0.7, branch_threshold=1e-4)[0])
+    assert maps[0].shape == (nt, nphi)
+    assert np.array_equal(maps[0], maps[1])
+    assert maps[0].std() > 1e-3
+    ref = O.caustic_map(O.caustic_params(grid_width=nphi, grid_height=nt, focal_length=0.7, branch_threshold=1e-4), f)
+    assert np.abs(maps[0] - ref).max() <= 1e-5 * max(1.0, np.abs(ref).max())
+
+
 def test_band_rows_do_not_change_results(S, monkeypatch):
     nt, nphi = 1024, 2048
     f = synthetic_field(nt, nphi, dtype=np.float32)
