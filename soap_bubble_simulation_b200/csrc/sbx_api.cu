@@ -711,7 +711,7 @@ static int32_t prepare_rgb(sbx_drainage *h, const sbx_view *v, RgbArgs &r)
     r.r0 = (float)(((v->n_film - 1.0) / (v->n_film + 1.0)) * ((v->n_film - 1.0) / (v->n_film + 1.0)));
     r.omr0 = 1.0f - r.r0;
     const double wl[3] = {650.0, 532.0, 450.0};  // interference.rs:26-30
-    for (int k = 0; k < 3; ++k) { r.two_n_over_wl[k] = 2.0 * v->n_film / wl[k]; r.inv_wl_f[k] = (float)(1.0 / wl[k]); }
+    for (int k = 0; k < 3; ++k) { r.two_n_over_wl[k] = 2.0 * v->n_film / wl[k]; r.inv_wl_f[k] = (float)(1.0 / wl[k]); r.two_pi_over_wl_f[k] = (float)(2.0 * M_PI / wl[k]); }
     return SBX_OK;
 }
 

@@ -257,20 +257,17 @@ __device__ __forceinline__ void rgb_schlick_wall(double d_nm, float ci, const Rg
 // Low finesse, so f32 cycles and the SFU sine on the reduced argument are ample for the 1e-4 colour tolerance.
 __device__ __forceinline__ void rgb_two_beam(float d_nm, float ci, const RgbArgs &a, float rgb[3])
 {
+    // I_k = 4 F (1 + cos(2 pi OPD / lambda_k + pi)) / 2 = 2 F (1 - cos(2 pi OPD / lambda_k)), docs/key-insights.md:288-309.
+    // The SFU cosine takes its argument in revolutions and drops the integer part itself, so no explicit range
+    // reduction is needed: the phase (< 80 rad) carries 5e-6 rad of fp32 rounding -- as in the f32 reference shader --
+    // which is < 2e-5 of colour even at grazing incidence (tolerance 1e-4).
     const float s2 = (1.f - ci * ci) * a.inv_n2;
     const float ct = sqrt_approx(fmaxf(1.f - s2, 0.f));
     const float opd = a.two_n * d_nm * ct;
     const float m = 1.f - ci, m2 = m * m;
-    const float fres4 = 4.f * fmaf(a.omr0, m2 * m2 * m, a.r0);
+    const float f2 = 2.f * fmaf(a.omr0, m2 * m2 * m, a.r0);
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const float cyc = opd * a.inv_wl_f[k];
-        // round-to-nearest by the 1.5*2^23 magic add (FADD pipe) instead of FRND, which shares the SFU port with
-        // the sine; cyc stays far below 2^22
-        const float r = __fsub_rn(__fadd_rn(cyc, 12582912.f), 12582912.f);
-        const float s = __sinf(3.14159265358979f * (cyc - r));
-        rgb[k] = clamp01(s * s * fres4);
-    }
+    for (int k = 0; k < 3; ++k) rgb[k] = __saturatef(fmaf(-f2, __cosf(opd * a.two_pi_over_wl_f[k]), f2));
 }
 
 // bubble.wgsl:425-439 through the texture unit: linear filter, clamp-to-edge, normalised coordinates,

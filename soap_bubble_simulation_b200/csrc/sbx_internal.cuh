@@ -47,7 +47,8 @@ struct RgbArgs {
     float inv_max_nm;  // 1 / LUT max thickness
     float nm_over_max; // 1e9 / LUT max thickness: metres -> LUT u coordinate
     cudaTextureObject_t lut;
-    float inv_wl_f[3];        // 1/lambda_k in f32 (two-beam model)
+    float inv_wl_f[3];        // 1/lambda_k in f32
+    float two_pi_over_wl_f[3];  // 2 pi / lambda_k in f32 (two-beam model)
     float two_n, r0, omr0;    // 2n, Schlick R0 = ((n-1)/(n+1))^2, 1 - R0
     double inv_n2_d;          // 1/n^2 in f64 for the phase
     double two_n_over_wl[3];  // 2 n / lambda_k at 650, 532, 450 nm (interference.rs:26-30)
