@@ -32,6 +32,23 @@ sim.step_fused(5e-3, view, 130)
 assert sim.active_tfe_count() >= 1
 sim.download()
 sim.close()
+# shared-memory-resident multi-step path: strict / fast, fronts active, batch (cluster per bubble), then consumers
+for prec in (S.PREC_F32, S.PREC_F64_STRICT):
+    sim = S.DrainageSimulator(S.SimulationConfig.default(), precision=prec, num_theta=64, num_phi=256, batch=3)
+    sim.step(5e-3, 160)
+    assert sim.active_tfe_count() >= 1
+    sim.caustic_map()
+    sim.sample_uv(np.random.default_rng(0).uniform(0, 1, (64, 2)))
+    sim.sample_normal(np.array([[0.0, 1.0, 0.0], [1.0, 0.0, 0.0]]))
+    sim.download()
+    sim.close()
+sim = S.DrainageSimulator(S.SimulationConfig.default(), precision=S.PREC_F32, num_theta=37, num_phi=50)
+sim.step(1e-3, 40)  # ragged: scalar st.async pushes
+sim.close()
+g = S.GPUDrainageSimulator(500e-9, 128, 64)
+g.dispatch(50)      # WGSL resident
+g.download_concentration()
+g.close()
 g = S.GPUDrainageSimulator(500e-9, 256, 64)
 g.set_marangoni_enabled(True)
 g.dispatch(3, view)
