@@ -17,7 +17,7 @@ constexpr int kSRowsPerStage = 2;  // theta rows per stage
 }  // namespace
 
 template <typename T, int MODE>
-__global__ void __launch_bounds__(288, 4) k_shade_tma(const StepArgs<T> a)
+__global__ void __launch_bounds__(288, 5) k_shade_tma(const StepArgs<T> a)
 {
     constexpr int VEC = 16 / (int)sizeof(T);
     extern __shared__ __align__(128) unsigned char smem_raw[];
