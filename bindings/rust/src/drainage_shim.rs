@@ -62,6 +62,9 @@ impl DrainageSimulator {
         Self { h, mirror: RefCell::new(mirror), stale: Cell::new(true) }
     }
     pub fn step(&mut self, dt: f64) { check(unsafe { sbx_drainage_step(self.h, dt, 1) }); self.stale.set(true); }
+    /// n applications of `step(dt)` in one call.  On grids that fit in shared memory (the default 128 x 256 does) the
+    /// library takes all n steps inside one kernel launch: ~1.8 us per step instead of ~14 us.
+    pub fn step_many(&mut self, dt: f64, n: usize) { check(unsafe { sbx_drainage_step(self.h, dt, n as i32) }); self.stale.set(true); }
     pub fn get_thickness(&self, theta: f64, phi: f64) -> f64 {
         let mut out = 0.0;
         check(unsafe { sbx_drainage_get_thickness(self.h, 0, theta, phi, &mut out) });
@@ -94,6 +97,82 @@ impl DrainageSimulator {
 }
 
 impl Drop for DrainageSimulator { fn drop(&mut self) { unsafe { sbx_drainage_destroy(self.h) }; } }
+
+/// GPUDrainageSimulator (src/render/gpu_drainage.rs:81-491) over libsbx: the same methods without the wgpu
+/// `device` / `queue` / `encoder` arguments.  Buffers are CUDA device pointers (`current_thickness_buffer`), valid until
+/// the next step.
+pub struct GPUDrainageSimulator {
+    h: *mut sbx_drainage,
+    params: sbx_drainage_params,
+    grid_width: u32,
+    grid_height: u32,
+    current_time: f32,
+    pub enabled: bool,          // gpu_drainage.rs:107 (false by default)
+    pub time_scale: f32,        // :109 (100.0)
+    pub steps_per_frame: u32,   // :111 (10)
+    pub marangoni_enabled: bool,
+}
+
+impl GPUDrainageSimulator {
+    pub fn new(initial_thickness: f32, grid_width: u32, grid_height: u32) -> Self {
+        let mut cfg = unsafe { std::mem::zeroed::<sbx_drainage_cfg>() };
+        check(unsafe { sbx_drainage_cfg_default(&mut cfg) });
+        cfg.semantics = SBX_SEM_WGSL;
+        cfg.num_phi = grid_width as i32;
+        cfg.num_theta = grid_height as i32;
+        cfg.h0_m = initial_thickness as f64;
+        let mut h = std::ptr::null_mut();
+        check(unsafe { sbx_drainage_create(&cfg, 0, &mut h) });
+        let mut params = cfg.wgsl;
+        check(unsafe { sbx_drainage_params_get(h, &mut params) });
+        Self { h, params, grid_width, grid_height, current_time: 0.0, enabled: false, time_scale: 100.0,
+               steps_per_frame: 10, marangoni_enabled: false }
+    }
+    /// gpu_drainage.rs:337-370: `steps_per_frame` dispatches of drainage_step, one library call (resident in shared
+    /// memory on the reference's 128 x 64 grid: 0.8 us per dispatch).
+    pub fn step(&mut self, dt: f32) {
+        if !self.enabled { return; }
+        check(unsafe { sbx_drainage_step(self.h, self.params.dt as f64, self.steps_per_frame as i32) });
+        self.current_time += dt * self.time_scale;
+    }
+    pub fn update_params(&mut self, params: sbx_drainage_params) {
+        self.params = params;
+        check(unsafe { sbx_drainage_update_params(self.h, &self.params) });
+    }
+    pub fn set_dt(&mut self, dt: f32) { self.params.dt = dt; self.push(); }
+    pub fn set_physics(&mut self, viscosity: f32, density: f32, gravity: f32, diffusion: f32) {
+        self.params.viscosity = viscosity; self.params.density = density;
+        self.params.gravity = gravity; self.params.diffusion_coeff = diffusion; self.push();
+    }
+    pub fn set_bubble_radius(&mut self, radius: f32) { self.params.bubble_radius = radius; self.push(); }
+    pub fn reset(&mut self, initial_thickness: f32) {
+        check(unsafe { sbx_drainage_reset(self.h, initial_thickness as f64) });
+        self.current_time = 0.0;
+    }
+    pub fn set_marangoni_enabled(&mut self, enabled: bool) {
+        self.marangoni_enabled = enabled; self.params.marangoni_enabled = enabled as u32; self.push();
+    }
+    pub fn set_marangoni_params(&mut self, gamma_air: f32, gamma_reduction: f32, surfactant_diffusion: f32, marangoni_coeff: f32) {
+        self.params.gamma_air = gamma_air; self.params.gamma_reduction = gamma_reduction;
+        self.params.surfactant_diffusion = surfactant_diffusion; self.params.marangoni_coeff = marangoni_coeff; self.push();
+    }
+    pub fn concentration_buffer(&self) -> *mut std::os::raw::c_void { self.ptr(SBX_PTR_CONCENTRATION) }
+    pub fn current_buffer(&self) -> *mut std::os::raw::c_void { self.ptr(SBX_PTR_THICKNESS) }
+    pub fn current_thickness_buffer(&self) -> *mut std::os::raw::c_void { self.ptr(SBX_PTR_THICKNESS) }
+    pub fn current_time(&self) -> f32 { self.current_time }
+    pub fn grid_size(&self) -> (u32, u32) { (self.grid_width, self.grid_height) }
+    pub fn params(&self) -> &sbx_drainage_params { &self.params }
+    /// CausticRenderer::compute (caustics.rs:441-457) on the latest thickness buffer; the map stays on the device.
+    pub fn compute_caustics(&mut self, p: &sbx_caustic_params) { check(unsafe { sbx_drainage_caustics(self.h, p, std::ptr::null_mut()) }); }
+    fn push(&mut self) { check(unsafe { sbx_drainage_update_params(self.h, &self.params) }); }
+    fn ptr(&self, kind: i32) -> *mut std::os::raw::c_void {
+        let mut p = std::ptr::null_mut();
+        check(unsafe { sbx_drainage_device_ptr(self.h, kind, &mut p) });
+        p
+    }
+}
+
+impl Drop for GPUDrainageSimulator { fn drop(&mut self) { unsafe { sbx_drainage_destroy(self.h) }; } }
 
 /// generate_interference_lut (interference_lut.rs:18-41)
 pub const LUT_THICKNESS_SAMPLES: u32 = 256;

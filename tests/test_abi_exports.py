@@ -29,6 +29,21 @@ def test_python_binding_covers_the_header():
     assert sorted(_lib.EXPORTED_SYMBOLS) == declared_symbols()
 
 
+def test_rust_binding_source_covers_the_header():
+    """bindings/rust/src/sbx_sys.rs (source only: no rustc in this image) declares every entry point of the header
+    with the same number of arguments."""
+    with open(os.path.join(ROOT, "bindings", "rust", "src", "sbx_sys.rs")) as f:
+        rs = f.read()
+    rust = {m.group(1): m.group(2) for m in re.finditer(r"pub fn (sbx_[a-z0-9_]+)\s*\(([^)]*)\)", rs, flags=re.S)}
+    assert sorted(rust) == declared_symbols()
+    with open(os.path.join(ROOT, "include", "sbx.h")) as f:
+        src = re.sub(r"/\*.*?\*/", "", f.read(), flags=re.S)
+    for name, args in re.findall(r"\b(sbx_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src, flags=re.S):
+        n_c = 0 if args.strip() == "void" else args.count(",") + 1
+        n_rs = 0 if not rust[name].strip() else rust[name].count(",") + 1
+        assert n_c == n_rs, (name, n_c, n_rs)
+
+
 def test_struct_layouts_match_the_reference_pod():
     """DrainageParams is a 64-byte #[repr(C)] POD (gpu_drainage.rs:10-44; pipeline.rs has the same style of
     size/offset checks for BubbleUniform at :2918-2948)."""
