@@ -86,6 +86,27 @@ public:
     DrainageSimulator &operator=(const DrainageSimulator &) = delete;
 
     void step(double dt) { check(sbx_drainage_step(h_, dt, 1)); stale_ = true; }                    // :298-392
+    // n applications of step(dt) in one call: on grids that fit in shared memory (the default 128 x 256 does) all n
+    // steps run inside one kernel launch
+    void step(double dt, int n) { check(sbx_drainage_step(h_, dt, n)); stale_ = true; }
+    // thickness-buffer consumers of the frame (pipeline.rs:1808-1818): caustic map (caustics_compute.wgsl:29-126) and
+    // the branched-flow shader's thickness sampling (branched_flow_compute.wgsl:187-210), both on the latest buffer
+    std::vector<float> caustic_map(const sbx_caustic_params *p = nullptr)
+    {
+        sbx_caustic_params q;
+        check(sbx_caustic_params_default(&q));
+        if (p) q = *p;
+        std::vector<float> out(mirror_.num_theta() * mirror_.num_phi());
+        check(sbx_drainage_caustics(h_, &q, out.data()));
+        return out;
+    }
+    void sample_uv(const std::vector<float> &uv, std::vector<float> &h, std::vector<float> &grad) const
+    {
+        const size_t n = uv.size() / 2;
+        h.resize(n);
+        grad.resize(2 * n);
+        check(sbx_drainage_sample_uv(h_, 0, uv.data(), n, h.data(), grad.data()));
+    }
     void step_fused(double dt, const sbx_view &v) { check(sbx_drainage_step_fused(h_, dt, 1, &v)); stale_ = true; }
     double get_thickness(double theta, double phi) const                                            // :516-552
     {

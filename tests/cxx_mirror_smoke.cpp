@@ -2,6 +2,7 @@
 // the reference's own unit tests (drainage.rs:636-719, interference.rs:649-686) through it.
 #include <cmath>
 #include <cstdio>
+#include <vector>
 
 #include "../include/sbx.hpp"
 
@@ -40,6 +41,18 @@ int main()
     g.enabled = true;
     g.step(1.0f / 60.0f);
     if (std::fabs(g.current_time() - 100.0 / 60.0) > 1e-5) return 12;
+    // one multi-step call equals the same number of single steps (both paths in f32 offset storage: pole means may
+    // differ in the last bit of their f64 sums, nothing else)
+    sbx::DrainageSimulator a(cfg), b(cfg);
+    a.step(cfg.dt, 50);
+    for (int i = 0; i < 50; ++i) b.step(cfg.dt);
+    if (std::fabs(a.current_time() - b.current_time()) > 0.0) return 13;
+    if (std::fabs(a.get_thickness(0.7, 1.3) / b.get_thickness(0.7, 1.3) - 1.0) > 1e-6) return 14;
+    const std::vector<float> cm = a.caustic_map();
+    if (cm.size() != 128u * 256u || !(std::fabs(cm[5000] - 2.0f) < 1e-3f)) return 15;  // flat film: intensity 2.0
+    std::vector<float> hh, gg;
+    a.sample_uv({0.25f, 0.5f, 0.75f, 0.1f}, hh, gg);
+    if (hh.size() != 2 || !(hh[0] > 400e-9f && hh[0] < 500.1e-9f)) return 16;
     std::printf("CXX_MIRROR_GPU_OK\n");
     return 0;
 }
