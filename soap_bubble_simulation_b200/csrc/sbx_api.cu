@@ -127,6 +127,11 @@ struct sbx_drainage {
     // time + TFE state machine (drainage.rs:237-255)
     double time = 0.0;
     std::vector<sbx_tfe_front> fronts;
+    // phi intervals of a front depend only on its centre and width, which never change after the spawn: cached so
+    // that the per-step table costs a row interval per front (the resident path builds thousands of tables per call)
+    struct ColCache { double phi_center, width; FrontCells c; };
+    mutable ColCache col_cache[kMaxFronts + 1];
+    mutable int col_cache_n = 0, col_cache_next = 0;
     double tfe_ratio = 0.85;
     bool tfe_enabled = true;
     double next_spawn = 0.5, spawn_interval = 2.0;
@@ -154,9 +159,10 @@ struct sbx_drainage {
     unsigned long long epoch = 0;
     int band_rows = 0;
     bool use_resident = true;            // SBX_NO_RESIDENT=1: always use the streaming kernels
-    std::vector<FrontTable> res_tabs;    // per-step TFE tables of one resident launch (host)
-    FrontTable *res_tabs_dev = nullptr;
-    size_t res_tabs_cap = 0;
+    FrontTable *res_tabs_host[2] = {nullptr, nullptr};  // pinned: per-step TFE tables of a resident launch
+    FrontTable *res_tabs_dev[2] = {nullptr, nullptr};
+    cudaEvent_t res_tabs_ev[2] = {nullptr, nullptr};
+    int res_slot = 0;
     int64_t launches = 0;
 };
 
@@ -171,7 +177,11 @@ static void free_all(sbx_drainage *h)
         if (h->buf[i]) cudaFree(h->buf[i]);
         if (h->conc[i]) cudaFree(h->conc[i]);
     }
-    cudaFree(h->res_tabs_dev);
+    for (int i = 0; i < 2; ++i) {
+        if (h->res_tabs_host[i]) cudaFreeHost(h->res_tabs_host[i]);
+        cudaFree(h->res_tabs_dev[i]);
+        if (h->res_tabs_ev[i]) cudaEventDestroy(h->res_tabs_ev[i]);
+    }
     cudaFree(h->coefS);
     cudaFree(h->coefF);
     cudaFree(h->rowSC);
@@ -654,16 +664,32 @@ static void tfe_table(const sbx_drainage *h, FrontTable &ft)
         auto Prow = [&](long i) { const double th = (double)i * dth; return !(fabs(th - M_PI_2) > f.extent); };
         exact_interval(Prow, (long)ceil((M_PI_2 - f.extent) / dth), (long)floor((M_PI_2 + f.extent) / dth),
                        (long)min_idx, (long)max_idx, c.row_lo, c.row_hi);
-        const double hw = f.width / 2.0;
-        auto Pdir = [&](long j) { const double d = fabs((double)j * dph - f.phi_center); return !(d > M_PI) && d < hw; };
-        auto Pwrap = [&](long j) { const double d = fabs((double)j * dph - f.phi_center); return d > M_PI && (2.0 * M_PI - d) < hw; };
-        exact_interval(Pdir, (long)ceil((f.phi_center - hw) / dph), (long)floor((f.phi_center + hw) / dph), 0, NP - 1,
-                       c.c0_lo, c.c0_hi);
-        c.c1_lo = 1; c.c1_hi = 0;
-        if (f.phi_center - hw < 0.0)
-            exact_interval(Pwrap, (long)ceil((f.phi_center + 2.0 * M_PI - hw) / dph), NP - 1, 0, NP - 1, c.c1_lo, c.c1_hi);
-        else if (f.phi_center + hw > 2.0 * M_PI)
-            exact_interval(Pwrap, 0, (long)floor((f.phi_center - 2.0 * M_PI + hw) / dph), 0, NP - 1, c.c1_lo, c.c1_hi);
+        const sbx_drainage::ColCache *hit = nullptr;
+        for (int i = 0; i < h->col_cache_n; ++i)
+            if (h->col_cache[i].phi_center == f.phi_center && h->col_cache[i].width == f.width) { hit = &h->col_cache[i]; break; }
+        if (!hit) {
+            FrontCells cc;
+            memset(&cc, 0, sizeof cc);
+            const double hw = f.width / 2.0;
+            auto Pdir = [&](long j) { const double d = fabs((double)j * dph - f.phi_center); return !(d > M_PI) && d < hw; };
+            auto Pwrap = [&](long j) { const double d = fabs((double)j * dph - f.phi_center); return d > M_PI && (2.0 * M_PI - d) < hw; };
+            exact_interval(Pdir, (long)ceil((f.phi_center - hw) / dph), (long)floor((f.phi_center + hw) / dph), 0, NP - 1,
+                           cc.c0_lo, cc.c0_hi);
+            cc.c1_lo = 1; cc.c1_hi = 0;
+            if (f.phi_center - hw < 0.0)
+                exact_interval(Pwrap, (long)ceil((f.phi_center + 2.0 * M_PI - hw) / dph), NP - 1, 0, NP - 1, cc.c1_lo, cc.c1_hi);
+            else if (f.phi_center + hw > 2.0 * M_PI)
+                exact_interval(Pwrap, 0, (long)floor((f.phi_center - 2.0 * M_PI + hw) / dph), 0, NP - 1, cc.c1_lo, cc.c1_hi);
+            sbx_drainage::ColCache &slot = h->col_cache[h->col_cache_next];
+            h->col_cache_next = (h->col_cache_next + 1) % (kMaxFronts + 1);
+            h->col_cache_n = std::min(h->col_cache_n + 1, kMaxFronts + 1);
+            slot.phi_center = f.phi_center;
+            slot.width = f.width;
+            slot.c = cc;
+            hit = &slot;
+        }
+        c.c0_lo = hit->c.c0_lo; c.c0_hi = hit->c.c0_hi;
+        c.c1_lo = hit->c.c1_lo; c.c1_hi = hit->c.c1_hi;
     }
 }
 
@@ -958,6 +984,8 @@ static bool resident_possible(const sbx_drainage *h)
     return h->use_resident && !h->comm && !h->peer_enabled && h->row_begin == 0 && h->rows_local == h->num_theta;
 }
 
+constexpr int kResidentChunk = 1024;
+
 template <typename T>
 static int32_t steps_resident(sbx_drainage *h, double dt, int nsteps, int *taken)
 {
@@ -967,27 +995,46 @@ static int32_t steps_resident(sbx_drainage *h, double dt, int nsteps, int *taken
     StepArgs<T> a;
     fill_step_args<T>(h, a, dt, none);
     if (!resident_possible(h) || nsteps < 2 || resident_cluster<T>(a, h->batch, h->strict) == 0) return SBX_OK;
-    constexpr int kChunk = 8192;  // steps per launch (bounds the TFE table upload)
+    // Steps per launch.  The host state machine of chunk k + 1 (0.14 us per step) runs while the kernel of chunk k does:
+    // two pinned host / device table buffers alternate, an event per buffer says when its upload has been consumed.
+    constexpr int kChunk = kResidentChunk;
+    if (h->tfe_enabled && !h->res_tabs_host[0]) {
+        for (int i = 0; i < 2; ++i) {
+            CU(cudaMallocHost(&h->res_tabs_host[i], (size_t)kChunk * sizeof(FrontTable)));
+            CU(cudaMalloc(&h->res_tabs_dev[i], (size_t)kChunk * sizeof(FrontTable)));
+            CU(cudaEventCreateWithFlags(&h->res_tabs_ev[i], cudaEventDisableTiming));
+        }
+    }
     while (nsteps > 0) {
         const int n = std::min(nsteps, kChunk);
         const FrontTable *tabs = nullptr;
         if (h->tfe_enabled) {
-            h->res_tabs.resize((size_t)n);
+            const int slot = h->res_slot;
+            h->res_slot ^= 1;
+            CU(cudaEventSynchronize(h->res_tabs_ev[slot]));  // the upload that last used this host buffer is done
+            FrontTable *host = h->res_tabs_host[slot];
             for (int s = 0; s < n; ++s) {  // the host state machine, one step at a time (drainage.rs:387-391)
                 tfe_advance(h, dt);
-                tfe_table(h, h->res_tabs[(size_t)s]);
+                tfe_table(h, host[s]);
                 h->time += dt;
+                FrontTable &t = host[s];
+                t.rows_changed = t.cols_changed = 1;
+                if (s > 0 && host[s - 1].count == t.count) {
+                    const FrontTable &p = host[s - 1];
+                    int rows = p.row_min != t.row_min || p.row_max != t.row_max, cols = 0;
+                    for (int k = 0; k < t.count; ++k) {
+                        rows |= p.f[k].row_lo != t.f[k].row_lo || p.f[k].row_hi != t.f[k].row_hi;
+                        cols |= p.f[k].c0_lo != t.f[k].c0_lo || p.f[k].c0_hi != t.f[k].c0_hi || p.f[k].c1_lo != t.f[k].c1_lo ||
+                                p.f[k].c1_hi != t.f[k].c1_hi;
+                    }
+                    t.rows_changed = rows;
+                    t.cols_changed = cols;
+                }
             }
-            if (h->res_tabs_cap < (size_t)n) {
-                CU(cudaStreamSynchronize(h->stream));
-                cudaFree(h->res_tabs_dev);
-                h->res_tabs_dev = nullptr;
-                h->res_tabs_cap = 0;
-                CU(cudaMalloc(&h->res_tabs_dev, (size_t)kChunk * sizeof(FrontTable)));
-                h->res_tabs_cap = kChunk;
-            }
-            CU(cudaMemcpyAsync(h->res_tabs_dev, h->res_tabs.data(), (size_t)n * sizeof(FrontTable), cudaMemcpyHostToDevice, h->stream));
-            tabs = h->res_tabs_dev;
+            // stream order keeps the device buffer safe: this copy runs after the kernel that read it two chunks ago
+            CU(cudaMemcpyAsync(h->res_tabs_dev[slot], host, (size_t)n * sizeof(FrontTable), cudaMemcpyHostToDevice, h->stream));
+            CU(cudaEventRecord(h->res_tabs_ev[slot], h->stream));
+            tabs = h->res_tabs_dev[slot];
         } else {
             for (int s = 0; s < n; ++s) h->time += dt;
         }

@@ -23,6 +23,9 @@ struct FrontTable {
     int count;
     int row_min, row_max;  // union row range the reference iterates (drainage.rs:425-440)
     FrontCells f[kMaxFronts];
+    // resident multi-step kernel only: do the row / column intervals differ from the previous step's table?  (Row
+    // intervals move every few hundred steps per front, column intervals only when a front is born or dies.)
+    int rows_changed, cols_changed;
 };
 
 // per-bubble constants (foam batches may vary radius and reference thickness per bubble)

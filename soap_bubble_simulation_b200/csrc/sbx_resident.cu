@@ -214,8 +214,8 @@ k_resident(const StepArgs<T> a, const FrontTable *__restrict__ tables, int nstep
     using RowC = typename std::conditional<STRICT, double4, ResRow<T>>::type;
     RowC *rowc = reinterpret_cast<RowC *>(res_align16(nxt + slab));
     FrontTable *ft = reinterpret_cast<FrontTable *>(rowc + rows_max);  // ring of three: ft[s % 3] = fronts of step s
-    unsigned *rowmask = reinterpret_cast<unsigned *>(ft + 3);          // rowmask[(s & 1) * rows_max + owned row]
-    unsigned *colmask = rowmask + 2 * rows_max;                        // colmask[(s & 1) * N + column]
+    unsigned *rowmask = reinterpret_cast<unsigned *>(ft + 3);          // two halves of rows_max: fronts covering each owned row
+    unsigned *colmask = rowmask + 2 * rows_max;                        // two halves of N: fronts covering each column
     uint64_t *bars = reinterpret_cast<uint64_t *>(res_align16(colmask + (tables != nullptr ? 2 * N : 0)));
 
     T *field = const_cast<T *>(a.in) + (long long)b * a.bubble_stride + N;  // global row 0
@@ -295,6 +295,7 @@ k_resident(const StepArgs<T> a, const FrontTable *__restrict__ tables, int nstep
 
     constexpr int kRunUnroll = STRICT ? 4 : 2;  // the strict update is a chain of IEEE divisions: overlap them
     int i_cur = 0;  // s % 3
+    int rm_buf = 0, cm_buf = 0;  // which half of rowmask / colmask holds the current step's masks
 #ifdef SBX_RES_PROFILE
     long long p_wait = 0, p_b = 0, p_a = 0, p_sync = 0;
 #endif
@@ -303,7 +304,8 @@ k_resident(const StepArgs<T> a, const FrontTable *__restrict__ tables, int nstep
         RES_T(c0);
         const int i_next = i_cur == 2 ? 0 : i_cur + 1, i_pre = i_next == 2 ? 0 : i_next + 1;
         const FrontTable &ftc = ft[i_cur];
-        const unsigned *rmc = rowmask + (s & 1) * rows_max, *cmc = colmask + (s & 1) * N;
+        const unsigned *rmc = rowmask + rm_buf * rows_max, *cmc = colmask + cm_buf * N;
+        int rm_next = rm_buf, cm_next = cm_buf;
         const bool prefetch = tfe && s + 2 < nsteps;
         if (prefetch && tid < kTabWords)
             cp_async4(reinterpret_cast<int *>(ft + i_pre) + tid, reinterpret_cast<const int *>(tables + s + 2) + tid);
@@ -325,8 +327,8 @@ k_resident(const StepArgs<T> a, const FrontTable *__restrict__ tables, int nstep
                     double m = 0.0;
                     if (lane == 0) {
                         double sum = 0.0;
-#pragma unroll 1
-                        for (int j = 0; j < N; ++j) sum = __dadd_rn(sum, (double)ring[j]);
+#pragma unroll 8
+                        for (int j = 0; j < N; ++j) sum = __dadd_rn(sum, (double)ring[j]);  // loads run ahead of the add chain
                         m = __ddiv_rn(sum, (double)N);
                     }
                     avg = (T)__shfl_sync(0xffffffffu, m, 0);
@@ -426,20 +428,31 @@ k_resident(const StepArgs<T> a, const FrontTable *__restrict__ tables, int nstep
                 }
             }
             if (tfe && s + 1 < nsteps && ft[i_next].count > 0) {
-                // row and column masks of the next step's fronts (its table landed during the previous
-                // step); off the path the neighbours wait on
-                unsigned *rmn = rowmask + ((s + 1) & 1) * rows_max, *cmn = colmask + ((s + 1) & 1) * N;
+                // row and column masks of the next step's fronts (its table landed during the previous step), rebuilt
+                // only when the host flagged a change, into the half nobody reads during this step
+                if (ft[i_next].rows_changed) {
+                    unsigned *rmn = rowmask + (rm_buf ^ 1) * rows_max;
 #pragma unroll 1
-                for (int l = tid; l < Rb; l += n_a) rmn[l] = res_row_mask(ft[i_next], g0 + l);
+                    for (int l = tid; l < Rb; l += n_a) rmn[l] = res_row_mask(ft[i_next], g0 + l);
+                }
+                if (ft[i_next].cols_changed) {
+                    unsigned *cmn = colmask + (cm_buf ^ 1) * N;
 #pragma unroll 1
-                for (int j = tid; j < N; j += n_a) cmn[j] = res_col_mask(ft[i_next], j);
+                    for (int j = tid; j < N; j += n_a) cmn[j] = res_col_mask(ft[i_next], j);
+                }
             }
             if (prefetch) cp_async_wait_all();
             RES_T(c3);
             RES_ACC(p_b, c1, c2); RES_ACC(p_a, c2, c3);
         }
+        if (tfe && s + 1 < nsteps && ft[i_next].count > 0) {  // uniform: every thread flips together
+            if (ft[i_next].rows_changed) rm_next = rm_buf ^ 1;
+            if (ft[i_next].cols_changed) cm_next = cm_buf ^ 1;
+        }
         RES_T(c4);
         __syncthreads();
+        rm_buf = rm_next;
+        cm_buf = cm_next;
         T *t = cur; cur = nxt; nxt = t;
         i_cur = i_next;
         RES_T(c5);
