@@ -6,13 +6,13 @@
 namespace sbx {
 
 // Rows per latitude band for the marching kernels.  Large grids run many waves of CTAs and the band height does not
-// matter (24 rows measured flat at 8192 x 16384); when the whole launch is only a few waves, a band height that leaves
+// matter (24 rows measured flat at 8192 x 16384); when the whole launch is only a few waves (< 16), a band height that leaves
 // the last wave half empty costs its full time -- 2048 x 4096 at 24 rows is 344 CTAs on 592 slots, at 14 rows 588:
 // +30 %.  Cost model: waves x (band rows + ring fill / halo overhead).
 inline int auto_band_rows(int rows, long long ctas_per_band, int slots, int dflt)
 {
     if (rows <= 0) return 1;
-    if (slots <= 0 || ctas_per_band * ((rows + dflt - 1) / dflt) >= 4LL * slots) return dflt < rows ? dflt : rows;
+    if (slots <= 0 || ctas_per_band * ((rows + dflt - 1) / dflt) >= 16LL * slots) return dflt < rows ? dflt : rows;
     int best = dflt < rows ? dflt : rows;
     double best_cost = 1e300;
     for (int b = 6; b <= 64 && b <= rows; ++b) {

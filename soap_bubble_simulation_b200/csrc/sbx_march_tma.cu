@@ -476,15 +476,23 @@ cudaError_t launch_march_tma(StepArgs<T> a, int batch, bool tfe, int band_rows_r
     const int consumers = tma_consumers<T>(a.num_phi);
     const int strip = consumers * VEC;
     const int gx = (a.num_phi + strip - 1) / strip;
-    int band_rows = band_rows_req > 0 ? band_rows_req
-                                      : auto_band_rows(rows, (long long)gx * batch, device_sm_count() * MinBlocks<T>::value, 24);
+    const size_t smem = march_tma_smem_bytes(consumers);
+    // resident CTAs per SM of this launch shape (narrow strips have smaller CTAs and more of them fit), asked once
+    static int occ_cache[9] = {0};  // by consumers / 32
+    int &occ = occ_cache[consumers / 32];
+    if (occ == 0) {
+        int nb = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_march_tma<T, SBX_RGB_LUT, false>, consumers + 32, smem) != cudaSuccess || nb <= 0)
+            nb = MinBlocks<T>::value;
+        occ = nb;
+    }
+    int band_rows = band_rows_req > 0 ? band_rows_req : auto_band_rows(rows, (long long)gx * batch, device_sm_count() * occ, 24);
     if (band_rows > rows) band_rows = rows;
     const int gy = (rows + band_rows - 1) / band_rows;
     a.band_rows = band_rows;
     a.pole_slots = gx;
     *pole_slots = gx;
     const dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)batch), block((unsigned)(consumers + 32));
-    const size_t smem = march_tma_smem_bytes(consumers);
     return tfe ? launch_tma_mode<T, true>(a, grid, block, smem, st) : launch_tma_mode<T, false>(a, grid, block, smem, st);
 }
 
