@@ -647,9 +647,7 @@ k_resident_wgsl(const WgslArgs a, int nsteps, unsigned magic, int rows_max)
 }
 
 // ------------------------------------------------------------------ host side
-template <typename K>
-static void cluster_config(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *attr, K kernel, int C, int batch, size_t smem,
-                           cudaStream_t st)
+static void cluster_config(cudaLaunchConfig_t &cfg, cudaLaunchAttribute *attr, int C, int batch, size_t smem, cudaStream_t st)
 {
     cfg = cudaLaunchConfig_t{};
     cfg.gridDim = dim3((unsigned)C, (unsigned)batch, 1);
@@ -681,7 +679,7 @@ static int max_cluster_width()
         int n = 0;
         if (cudaFuncSetAttribute(k_resident_probe, cudaFuncAttributeNonPortableClusterSizeAllowed, 1) == cudaSuccess &&
             cudaFuncSetAttribute(k_resident_probe, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kResSmemMax) == cudaSuccess) {
-            cluster_config(cfg, attr, k_resident_probe, 16, 1, kResSmemMax, nullptr);
+            cluster_config(cfg, attr, 16, 1, kResSmemMax, nullptr);
             if (cudaOccupancyMaxActiveClusters(&n, k_resident_probe, &cfg) == cudaSuccess && n >= 1) width = 16;
         }
         cudaGetLastError();
@@ -735,7 +733,7 @@ static cudaError_t launch_cluster(K kernel, int C, int batch, size_t smem, cudaS
     }
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[1];
-    cluster_config(cfg, attr, kernel, C, batch, smem, st);
+    cluster_config(cfg, attr, C, batch, smem, st);
     return cudaLaunchKernelEx(&cfg, kernel, args...);
 }
 
