@@ -21,6 +21,7 @@ namespace {
 
 constexpr int kStages = 3;        // ring depth
 constexpr int kRowsPerStage = 3;  // theta rows per stage == the unroll of the three-row register window
+constexpr int kMaxBandRows = 64;  // rows a CTA marches at most (their coefficients are staged in shared memory)
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
 {
@@ -76,6 +77,10 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
     constexpr int HALO = VEC;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double warp_part[8];
+    // per-row coefficients {A+B, A-B, E, G} and {sin, cos} of this band, staged once: a row then costs two LDS
+    // instead of two global loads on the critical path of its first instruction
+    __shared__ __align__(16) T s_coef[kMaxBandRows][4];
+    __shared__ float2 s_sc[kMaxBandRows];
     const int C = blockDim.x - 32;  // consumer threads
     const int N = a.num_phi;
     const int strip_w_max = VEC * C;
@@ -143,6 +148,18 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
     // ---------------------------------------------------------------- consumers
     const int tid = threadIdx.x;
     const int lane = tid & 31;
+    // stage the band's row coefficients while the producer's first copies are in flight
+    for (int r = tid; r < l1 - l0 + 1; r += C) {
+        const long long g = a.row_begin + l0 - 1 + (long long)r;
+        if constexpr (VEC == 4) {
+            *reinterpret_cast<float4 *>(&s_coef[r][0]) = __ldg(reinterpret_cast<const float4 *>(a.coefF + 4 * g));
+        } else {
+            *reinterpret_cast<double2 *>(&s_coef[r][0]) = __ldg(reinterpret_cast<const double2 *>(a.coefF + 4 * g));
+            *reinterpret_cast<double2 *>(&s_coef[r][2]) = __ldg(reinterpret_cast<const double2 *>(a.coefF + 4 * g) + 1);
+        }
+        s_sc[r] = __ldg(a.rowSC + g);
+    }
+    bar_consumers(C);
     const int jloc = tid * VEC;  // column offset inside the strip
     const bool active = jloc < w;
     const int jc = c0 + (active ? jloc : 0);
@@ -203,8 +220,8 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
     T *out_p = out + (long long)l0 * N + jc;
     uint32_t *rgb_p = reinterpret_cast<uint32_t *>(a.rgb.out) + (long long)b * a.rgb_bubble_stride +
                       (long long)(l0 - 1) * N + jc;
-    const T *cf_p = a.coefF + 4 * (long long)(a.row_begin + l0 - 1);
-    const float2 *sc_p = a.rowSC + (a.row_begin + l0 - 1);
+    const T *cf_p = &s_coef[0][0];
+    const float2 *sc_p = s_sc;
     int grow = a.row_begin + l0 - 1;
     const int ring_top = 1, ring_bot = a.num_theta - 2;
     const bool has_ring = (grow <= ring_top && ring_top <= a.row_begin + l1 - 1) ||
@@ -213,11 +230,11 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
     auto compute_row = [&](const RowT &up, const RowT &cur, const RowT &dn) {
         T cApB, cAmB, cE, cG;  // {A+B, A-B, E, G}
         if constexpr (VEC == 4) {
-            const float4 cf = __ldg(reinterpret_cast<const float4 *>(cf_p));
+            const float4 cf = *reinterpret_cast<const float4 *>(cf_p);
             cApB = cf.x; cAmB = cf.y; cE = cf.z; cG = cf.w;
         } else {
-            const double2 c01 = __ldg(reinterpret_cast<const double2 *>(cf_p));
-            const double2 c23 = __ldg(reinterpret_cast<const double2 *>(cf_p) + 1);
+            const double2 c01 = *reinterpret_cast<const double2 *>(cf_p);
+            const double2 c23 = *(reinterpret_cast<const double2 *>(cf_p) + 1);
             cApB = c01.x; cAmB = c01.y; cE = c23.x; cG = c23.y;
         }
         Vec<T, VEC> nw;
@@ -276,7 +293,7 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
                 }
             }
             if constexpr (MODE != SBX_RGB_NONE) {
-                const float2 sc = __ldg(sc_p);
+                const float2 sc = *sc_p;
                 const float ccy = sc.y * a.rgb.cam_y;
                 uint32_t px[VEC];
 #pragma unroll
@@ -488,6 +505,7 @@ cudaError_t launch_march_tma(StepArgs<T> a, int batch, bool tfe, int band_rows_r
     }
     int band_rows = band_rows_req > 0 ? band_rows_req : auto_band_rows(rows, (long long)gx * batch, device_sm_count() * occ, 24);
     if (band_rows > rows) band_rows = rows;
+    if (band_rows > kMaxBandRows) band_rows = kMaxBandRows;
     const int gy = (rows + band_rows - 1) / band_rows;
     a.band_rows = band_rows;
     a.pole_slots = gx;
