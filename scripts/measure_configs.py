@@ -129,6 +129,10 @@ if "modes" in which:
     single("C3 WGSL semantics (h + concentration), no Marangoni", 8192, 16384, S.PREC_F32, S.RGB_NONE, 50, 16, semantics="wgsl")
     single("C3 WGSL semantics + Marangoni + LUT->RGBA8", 8192, 16384, S.PREC_F32, S.RGB_LUT, 50, 20, semantics="wgsl", marangoni=True)
 
+if "wgsl" in which:
+    single("C3 WGSL semantics (h + concentration), no Marangoni", 8192, 16384, S.PREC_F32, S.RGB_NONE, 50, 16, semantics="wgsl")
+    single("C3 WGSL semantics + Marangoni + LUT->RGBA8", 8192, 16384, S.PREC_F32, S.RGB_LUT, 50, 20, semantics="wgsl", marangoni=True)
+
 if "c4" in which:
     # config 4: foam of independent bubbles, 256x512 each; per-bubble h0 and radius, offset storage
     for B in (512, 4096):

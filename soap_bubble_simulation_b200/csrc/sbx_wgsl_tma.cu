@@ -18,6 +18,7 @@ namespace {
 constexpr int kWStages = 2;        // two fields double the bytes per stage, so two stages keep 4 CTAs per SM
 constexpr int kWRowsPerStage = 3;  // == unroll of the register window
 constexpr int kWHalo = 4;
+constexpr int kWMaxBandRows = 64;  // rows a CTA marches at most (their coefficients are staged in shared memory)
 
 struct RowW {
     float v[4];
@@ -30,6 +31,9 @@ template <int MODE>
 __global__ void __launch_bounds__(288, 3) k_wgsl_tma(const WgslArgs a)
 {
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    // per-row {sin, cot, 1/sin^2, 1/sin} and {sin, cos} of this band, staged once (see sbx_march_tma.cu)
+    __shared__ float4 s_rw[kWMaxBandRows];
+    __shared__ float2 s_sc[kWMaxBandRows];
     const int C = blockDim.x - 32;
     const int N = a.num_phi;
     const int strip_w_max = 4 * C;
@@ -93,6 +97,11 @@ __global__ void __launch_bounds__(288, 3) k_wgsl_tma(const WgslArgs a)
     // ---------------------------------------------------------------- consumers
     const int tid = threadIdx.x;
     const int lane = tid & 31;
+    for (int r = tid; r < l1 - l0 + 1; r += C) {
+        s_rw[r] = __ldg(reinterpret_cast<const float4 *>(a.rowW) + (a.row_begin + l0 - 1 + r));
+        s_sc[r] = __ldg(a.rowSC + (a.row_begin + l0 - 1 + r));
+    }
+    asm volatile("bar.sync 1, %0;" ::"r"(C) : "memory");
     const int jloc = tid * 4;
     const bool active = jloc < w;
     const int jc = c0 + (active ? jloc : 0);
@@ -149,11 +158,11 @@ __global__ void __launch_bounds__(288, 3) k_wgsl_tma(const WgslArgs a)
     float *cout_p = cout + (long long)l0 * N + jc;
     uint32_t *rgb_p = reinterpret_cast<uint32_t *>(a.rgb.out) + (long long)b * a.rgb_bubble_stride +
                       (long long)(l0 - 1) * N + jc;
-    const float4 *rw_p = reinterpret_cast<const float4 *>(a.rowW) + (a.row_begin + l0 - 1);
-    const float2 *sc_p = a.rowSC + (a.row_begin + l0 - 1);
+    const float4 *rw_p = s_rw;
+    const float2 *sc_p = s_sc;
 
     auto compute_row = [&](const RowW &hu, const RowW &hc, const RowW &hd, const RowW &cu, const RowW &cc, const RowW &cd) {
-        const float4 rw = __ldg(rw_p);  // {sin, cos/sin_safe, 1/sin_safe^2, 1/sin_safe}, drainage.wgsl:92-101
+        const float4 rw = *rw_p;  // {sin, cos/sin_safe, 1/sin_safe^2, 1/sin_safe}, drainage.wgsl:92-101
         const float sin_theta = rw.x, cot = rw.y, inv_sin2 = rw.z, inv_sin = rw.w;
         float hn[4], cn[4];
 #pragma unroll
@@ -195,7 +204,7 @@ __global__ void __launch_bounds__(288, 3) k_wgsl_tma(const WgslArgs a)
             *reinterpret_cast<float4 *>(hout_p) = make_float4(hn[0], hn[1], hn[2], hn[3]);
             *reinterpret_cast<float4 *>(cout_p) = make_float4(cn[0], cn[1], cn[2], cn[3]);
             if constexpr (MODE != SBX_RGB_NONE) {
-                const float2 sc = __ldg(sc_p);
+                const float2 sc = *sc_p;
                 const float ccy = sc.y * a.rgb.cam_y;
                 uint32_t px[4];
 #pragma unroll
@@ -274,6 +283,7 @@ cudaError_t launch_wgsl_tma(WgslArgs a, int batch, int band_rows_req, cudaStream
     const int gx = (a.num_phi + strip - 1) / strip;
     int band_rows = band_rows_req > 0 ? band_rows_req : auto_band_rows(rows, (long long)gx * batch, device_sm_count() * 3, 24);
     if (band_rows > rows) band_rows = rows;
+    if (band_rows > kWMaxBandRows) band_rows = kWMaxBandRows;
     const int gy = (rows + band_rows - 1) / band_rows;
     a.band_rows = band_rows;
     const dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)batch), block((unsigned)(consumers + 32));
