@@ -14,6 +14,7 @@ namespace sbx {
 namespace {
 constexpr int kSStages = 4;        // ring depth
 constexpr int kSRowsPerStage = 2;  // theta rows per stage
+constexpr int kSMaxBandRows = 64;  // rows a CTA shades at most
 }  // namespace
 
 template <typename T, int MODE>
@@ -21,6 +22,7 @@ __global__ void __launch_bounds__(288, 5) k_shade_tma(const StepArgs<T> a)
 {
     constexpr int VEC = 16 / (int)sizeof(T);
     extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ float2 s_sc[kSMaxBandRows];  // {sin, cos} of the band's rows, staged once
     const int C = blockDim.x - 32;  // consumer threads
     const int N = a.num_phi;
     const int strip = VEC * C;
@@ -78,7 +80,9 @@ __global__ void __launch_bounds__(288, 5) k_shade_tma(const StepArgs<T> a)
     const float camR2 = a.rgb.cam2 + Rv * Rv;
     const float href_u = (float)href * a.rgb.nm_over_max;
     uint32_t *rgb_p = reinterpret_cast<uint32_t *>(a.rgb.out) + (long long)b * a.rgb_bubble_stride + (long long)(l0 - 1) * N + jc;
-    const float2 *sc_p = a.rowSC + (a.row_begin + l0 - 1);
+    for (int r = tid; r < rows; r += C) s_sc[r] = __ldg(a.rowSC + (a.row_begin + l0 - 1 + r));
+    bar_consumers(C);
+    const float2 *sc_p = s_sc;
     const T *my = ring + (active ? jloc : 0);
 
     for (int c = 0; c < nchunks; ++c) {
@@ -105,7 +109,7 @@ __global__ void __launch_bounds__(288, 5) k_shade_tma(const StepArgs<T> a)
         for (int r = 0; r < kSRowsPerStage; ++r) {
             if (r < nr) {
                 if (active) {
-                    const float2 sc = __ldg(sc_p);
+                    const float2 sc = *sc_p;
                     const float ccy = sc.y * a.rgb.cam_y;
                     uint32_t px[VEC];
 #pragma unroll
@@ -158,6 +162,7 @@ cudaError_t launch_shade_tma(StepArgs<T> a, int batch, int band_rows_req, cudaSt
     const int gx = (a.num_phi + strip - 1) / strip;
     int band_rows = band_rows_req > 0 ? band_rows_req : auto_band_rows(rows, (long long)gx * batch, device_sm_count() * 4, 24);
     if (band_rows > rows) band_rows = rows;
+    if (band_rows > kSMaxBandRows) band_rows = kSMaxBandRows;
     a.band_rows = band_rows;
     const dim3 grid((unsigned)gx, (unsigned)((rows + band_rows - 1) / band_rows), (unsigned)batch), block((unsigned)(consumers + 32));
     const size_t smem = (size_t)kSStages * kSRowsPerStage * strip * sizeof(T) + 2 * kSStages * sizeof(uint64_t);
