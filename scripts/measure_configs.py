@@ -129,6 +129,9 @@ if "modes" in which:
     single("C3 WGSL semantics (h + concentration), no Marangoni", 8192, 16384, S.PREC_F32, S.RGB_NONE, 50, 16, semantics="wgsl")
     single("C3 WGSL semantics + Marangoni + LUT->RGBA8", 8192, 16384, S.PREC_F32, S.RGB_LUT, 50, 20, semantics="wgsl", marangoni=True)
 
+if "exact3" in which:
+    single("C3 f32 fused EXACT3 (3-lambda exact Fresnel + gamma)->RGBA8", 8192, 16384, S.PREC_F32, S.RGB_EXACT3, 30, 12)
+
 if "wgsl" in which:
     single("C3 WGSL semantics (h + concentration), no Marangoni", 8192, 16384, S.PREC_F32, S.RGB_NONE, 50, 16, semantics="wgsl")
     single("C3 WGSL semantics + Marangoni + LUT->RGBA8", 8192, 16384, S.PREC_F32, S.RGB_LUT, 50, 20, semantics="wgsl", marangoni=True)
