@@ -32,6 +32,20 @@ pub struct sbx_view { pub cam_pos: [f64; 3], pub n_film: f64, pub intensity: f32
 #[derive(Debug, Clone, Copy)]
 pub struct sbx_tfe_front { pub phi_center: f64, pub extent: f64, pub width: f64, pub velocity: f64 }
 
+/// One headless frame: Camera (camera.rs:49-60) + the BubbleUniform fields the fragment shader's shading path reads
+#[repr(C)]
+#[derive(Debug, Clone, Copy)]
+pub struct sbx_frame_params {
+    pub width: u32, pub height: u32,
+    pub cam_distance: f32, pub cam_yaw: f32, pub cam_pitch: f32, pub cam_fov_rad: f32,
+    pub radius: f32, pub base_thickness_nm: f32,
+    pub film_time: f32, pub swirl_intensity: f32, pub drainage_speed: f32, pub pattern_scale: f32,
+    pub interference_intensity: f32, pub base_alpha: f32, pub edge_alpha: f32,
+    pub edge_smoothing_mode: u32,
+    pub background: [f32; 3],
+    pub lut_max_nm: f32,
+}
+
 /// CausticParams, src/render/caustics.rs:19-79 (64-byte POD)
 #[repr(C)]
 #[derive(Debug, Clone, Copy)]
@@ -116,6 +130,13 @@ extern "C" {
                                       out_h: *mut f32) -> i32;
     pub fn sbx_lut_build_spectral(refractive_index: f32, intensity: f32, wavelengths_nm: *const f32, n_lambda: i32, t: i32,
                                   a: i32, max_nm: f32, out: *mut u8, device: i32) -> i32;
+    pub fn sbx_frame_params_default(p: *mut sbx_frame_params) -> i32;
+    pub fn sbx_render_bubble_frame(p: *const sbx_frame_params, lut_rgba: *const u8, t: i32, a: i32, rgba_out: *mut u8,
+                                   device: i32) -> i32;
+    pub fn sbx_drainage_render_frame(h: *mut sbx_drainage, bubble: i32, p: *const sbx_frame_params, n_film: f64,
+                                     rgba_out: *mut u8) -> i32;
+    pub fn sbx_export_frame_png(path: *const std::os::raw::c_char, width: u32, height: u32, rgba: *const u8,
+                                len: usize) -> i32;
     pub fn sbx_lut_shade_points(lut_rgba: *const u8, t: i32, a: i32, max_nm: f32, d_nm: *const f32, cos_theta: *const f32,
                                 n: usize, intensity: f32, rgb_out: *mut f32, device: i32) -> i32;
     pub fn sbx_interference_terms(n_film: f64, d_nm: *const f64, cos_i: *const f64, n: usize, wavelength_nm: f64,

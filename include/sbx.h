@@ -37,7 +37,8 @@ typedef enum {
     SBX_ERR_CUDA = -2,        /* CUDA runtime error, or no device */
     SBX_ERR_NOMEM = -3,
     SBX_ERR_UNSUPPORTED = -4, /* valid request this build does not implement */
-    SBX_ERR_COMM = -5         /* NCCL / peer-memory failure */
+    SBX_ERR_COMM = -5,        /* NCCL / peer-memory failure */
+    SBX_ERR_IO = -6           /* file could not be written (ExportError::SaveError, image_export.rs:11) */
 } sbx_status;
 
 /* Which reference implementation the step reproduces. */
@@ -250,6 +251,42 @@ int32_t sbx_drainage_sample_uv(sbx_drainage *h, int32_t bubble, const float *uv,
 /* sample_thickness(normal) of the same shader (branched_flow_compute.wgsl:110-116, 294-300): thickness * scale at the
  * texel each unit normal (host array of n x 3 floats) points at.  out_h = n floats on the host. */
 int32_t sbx_drainage_sample_normal(sbx_drainage *h, int32_t bubble, const float *normals, size_t n, float scale, float *out_h);
+
+/* ---------------------------------------------------------------- headless bubble frame + PNG export (rows f3/f4) */
+/* What one frame of HeadlessRenderPipeline shows (src/render/headless.rs:27-39): its Camera (camera.rs:49-60) and the
+ * BubbleUniform fields the fragment shader's shading path reads (pipeline.rs:20-112; bubble.wgsl:12-57). */
+typedef struct {
+    uint32_t width, height;                       /* HeadlessRenderPipeline::new(width, height), headless.rs:50 */
+    float cam_distance, cam_yaw, cam_pitch;       /* 0.2, 0, 0.3 (camera.rs:49-60); target = origin */
+    float cam_fov_rad;                            /* 45 deg vertical; aspect = width / height */
+    float radius;                                 /* sphere radius in metres, 0.025 */
+    float base_thickness_nm;                      /* 500 */
+    float film_time, swirl_intensity, drainage_speed, pattern_scale; /* 0, 1, 0.5, 1 */
+    float interference_intensity;                 /* 4 */
+    float base_alpha, edge_alpha;                 /* 0.3, 0.6 */
+    uint32_t edge_smoothing_mode;                 /* 0 linear, 1 smoothstep (default), 2 power */
+    float background[3];                          /* clear colour (0.1, 0.1, 0.15), linear */
+    float lut_max_nm;                             /* LUT_MAX_THICKNESS_NM = 2000 (interference_lut.rs:13) */
+} sbx_frame_params;
+int32_t sbx_frame_params_default(sbx_frame_params *p);
+/* HeadlessRenderPipeline::render_to_buffer (headless.rs:437-512) for the bubble: bubble.wgsl::fs_main (:487-541)
+ * evaluated per pixel on `device` -- procedural simplex/FBM film thickness (:200-229), |view . normal|, LUT fetch
+ * (linear, clamp-to-edge sampler) x interference_intensity (:425-439), black film below 30 nm (:517-519), edge
+ * alpha (:501-513) -- alpha-blended over the background into an Rgba8UnormSrgb target.  The rasterised mesh is an
+ * analytic ray-sphere hit here.  lut_rgba: host, A rows of T RGBA8 texels ([angle][thickness]); rgba_out: host,
+ * width*height*4 bytes, row 0 at the top, alpha 255. */
+int32_t sbx_render_bubble_frame(const sbx_frame_params *p, const uint8_t *lut_rgba, int32_t T, int32_t A,
+                                uint8_t *rgba_out, int32_t device);
+/* The same frame with the film thickness taken from bubble `bubble` of a drainage handle instead of the procedural
+ * noise: the latest thickness field blended at (theta, phi) of the surface normal like get_thickness
+ * (drainage.rs:516-552), coloured through the handle's LUT (built for n_film on first use; sbx_drainage_set_lut
+ * overrides it).  p->base_thickness_nm and the film-dynamics fields are ignored.  Whole-sphere handles only. */
+int32_t sbx_drainage_render_frame(sbx_drainage *h, int32_t bubble, const sbx_frame_params *p, double n_film,
+                                  uint8_t *rgba_out);
+/* export_frame(path, width, height, data) (src/export/image_export.rs:42-76): RGBA8 -> PNG file (host only, zlib).
+ * SBX_ERR_INVALID for zero dimensions (ExportError::InvalidDimensions) or len != width*height*4
+ * (ExportError::BufferCreation); SBX_ERR_IO when the file cannot be written (ExportError::SaveError). */
+int32_t sbx_export_frame_png(const char *path, uint32_t width, uint32_t height, const uint8_t *rgba, size_t len);
 
 /* ---------------------------------------------------------------- interference LUT / calculator */
 /* generate_interference_lut(refractive_index, intensity) -> 256x64 RGBA8

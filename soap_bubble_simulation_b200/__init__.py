@@ -7,6 +7,8 @@ from .config import (BubbleParameters, ConfigError, EnvironmentParameters, Fluid
                      SimulationConfig)
 from .drainage import DrainageSimulator, ThicknessField, View, camera_position
 from .gpu_drainage import DrainageParams, GPUDrainageSimulator
+from .headless import (BubbleUniform, Camera, ExportError, HeadlessRenderPipeline, export_frame,
+                       render_drainage_frame)
 from .interference import (LUT_ANGLE_SAMPLES, LUT_MAX_THICKNESS_NM, LUT_THICKNESS_SAMPLES,
                            FresnelCoefficients, InterferenceCalculator, RgbColor,
                            generate_interference_lut, generate_spectral_lut, thin_film_interference)

@@ -14,6 +14,7 @@ LIB_PATH = os.path.join(_HERE, "csrc", "libsbx.so")
 
 # enums (include/sbx.h)
 SBX_OK = 0
+ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_COMM, ERR_IO = -1, -2, -3, -4, -5, -6
 SEM_CPU, SEM_WGSL = 0, 1
 PREC_F32, PREC_F64, PREC_F64_STRICT = 0, 1, 2
 F32, F64 = 0, 1
@@ -47,6 +48,16 @@ class CausticParamsC(C.Structure):
                 ("light_dir_z", C.c_float), ("light_intensity", C.c_float), ("focal_length", C.c_float),
                 ("caustic_intensity", C.c_float), ("caustic_sharpness", C.c_float), ("branch_threshold", C.c_float),
                 ("ground_y", C.c_float), ("bubble_radius", C.c_float), ("time", C.c_float), ("_padding", C.c_uint32)]
+
+
+class FrameParamsC(C.Structure):
+    """sbx_frame_params: Camera (camera.rs:49-60) + the BubbleUniform fields bubble.wgsl::fs_main's shading reads."""
+    _fields_ = [("width", C.c_uint32), ("height", C.c_uint32), ("cam_distance", C.c_float), ("cam_yaw", C.c_float),
+                ("cam_pitch", C.c_float), ("cam_fov_rad", C.c_float), ("radius", C.c_float),
+                ("base_thickness_nm", C.c_float), ("film_time", C.c_float), ("swirl_intensity", C.c_float),
+                ("drainage_speed", C.c_float), ("pattern_scale", C.c_float), ("interference_intensity", C.c_float),
+                ("base_alpha", C.c_float), ("edge_alpha", C.c_float), ("edge_smoothing_mode", C.c_uint32),
+                ("background", C.c_float * 3), ("lut_max_nm", C.c_float)]
 
 
 class DrainageCfgC(C.Structure):
@@ -114,6 +125,10 @@ _SIGS = {
     "sbx_drainage_caustics": [C.c_void_p, C.POINTER(CausticParamsC), C.c_void_p],
     "sbx_drainage_sample_uv": [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p],
     "sbx_drainage_sample_normal": [C.c_void_p, C.c_int32, C.c_void_p, C.c_size_t, C.c_float, C.c_void_p],
+    "sbx_frame_params_default": [C.POINTER(FrameParamsC)],
+    "sbx_render_bubble_frame": [C.POINTER(FrameParamsC), C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_int32],
+    "sbx_drainage_render_frame": [C.c_void_p, C.c_int32, C.POINTER(FrameParamsC), C.c_double, C.c_void_p],
+    "sbx_export_frame_png": [C.c_char_p, C.c_uint32, C.c_uint32, C.c_void_p, C.c_size_t],
     "sbx_lut_build": [C.c_float, C.c_float, C.c_void_p, C.c_int32],
     "sbx_lut_build_spectral": [C.c_float, C.c_float, C.c_void_p, C.c_int32, C.c_int32, C.c_int32,
                                C.c_float, C.c_void_p, C.c_int32],

@@ -10,6 +10,8 @@
 #include <string>
 #include <vector>
 
+#include <zlib.h>
+
 #include "sbx_comm.h"
 #include "sbx_launch.h"
 
@@ -1593,6 +1595,192 @@ extern "C" int32_t sbx_lut_shade_points(const uint8_t *lut_rgba, int32_t T, int3
     if (tex) cudaDestroyTextureObject(tex);
     if (arr) cudaFreeArray(arr);
     if (e != cudaSuccess) return fail(SBX_ERR_CUDA, "LUT shading failed: %s", cudaGetErrorString(e));
+    return SBX_OK;
+}
+
+// ------------------------------------------------------------------ headless bubble frame + PNG export (rows f3/f4)
+extern "C" int32_t sbx_frame_params_default(sbx_frame_params *p)
+{
+    if (!p) return fail(SBX_ERR_INVALID, "p is null");
+    memset(p, 0, sizeof *p);
+    p->width = p->height = 256;       // tests/screenshot_tests.rs: 256 x 256 frames
+    p->cam_distance = 0.2f;           // Camera::new, camera.rs:49-60
+    p->cam_yaw = 0.0f;
+    p->cam_pitch = 0.3f;
+    p->cam_fov_rad = 45.0f * (float)(M_PI / 180.0);
+    p->radius = 0.025f;
+    p->base_thickness_nm = 500.0f;    // BubbleUniform::default, pipeline.rs:69-112
+    p->film_time = 0.0f;
+    p->swirl_intensity = 1.0f;
+    p->drainage_speed = 0.5f;
+    p->pattern_scale = 1.0f;
+    p->interference_intensity = 4.0f;
+    p->base_alpha = 0.3f;
+    p->edge_alpha = 0.6f;
+    p->edge_smoothing_mode = 1;
+    p->background[0] = 0.1f; p->background[1] = 0.1f; p->background[2] = 0.15f;
+    p->lut_max_nm = 2000.0f;
+    return SBX_OK;
+}
+
+static int32_t frame_args_from(const sbx_frame_params *p, FrameArgs &a)
+{
+    if (!p) return fail(SBX_ERR_INVALID, "frame params are null");
+    if (p->width == 0 || p->height == 0 || p->width > 16384 || p->height > 16384)
+        return fail(SBX_ERR_INVALID, "Invalid dimensions: %ux%u", p->width, p->height);
+    if (!(p->radius > 0.f) || !(p->cam_distance > p->radius)) return fail(SBX_ERR_INVALID, "camera must be outside the bubble");
+    if (!(p->lut_max_nm > 0.f) || !(p->cam_fov_rad > 0.f) || p->edge_smoothing_mode > 2u)
+        return fail(SBX_ERR_INVALID, "bad frame parameters");
+    memset(&a, 0, sizeof a);
+    a.width = (int)p->width;
+    a.height = (int)p->height;
+    // Camera::position (camera.rs:63-68), Mat4::look_at_rh(position, origin, Y), perspective_rh(fov, aspect)
+    const float d = p->cam_distance, cp = cosf(p->cam_pitch), sp = sinf(p->cam_pitch);
+    const float cam[3] = {d * cp * sinf(p->cam_yaw), d * sp, d * cp * cosf(p->cam_yaw)};
+    const float cl = sqrtf(cam[0] * cam[0] + cam[1] * cam[1] + cam[2] * cam[2]);
+    const float f[3] = {-cam[0] / cl, -cam[1] / cl, -cam[2] / cl};
+    float r[3] = {f[1] * 0.f - f[2] * 1.f, f[2] * 0.f - f[0] * 0.f, f[0] * 1.f - f[1] * 0.f};  // cross(f, Y)
+    const float rl = sqrtf(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]);
+    if (!(rl > 0.f)) return fail(SBX_ERR_INVALID, "camera looks along the up axis");
+    for (int k = 0; k < 3; ++k) r[k] /= rl;
+    const float u[3] = {r[1] * f[2] - r[2] * f[1], r[2] * f[0] - r[0] * f[2], r[0] * f[1] - r[1] * f[0]};  // cross(r, f)
+    for (int k = 0; k < 3; ++k) { a.cam[k] = cam[k]; a.fwd[k] = f[k]; a.right[k] = r[k]; a.up[k] = u[k]; a.bg[k] = p->background[k]; }
+    a.tan_half_y = tanf(0.5f * p->cam_fov_rad);
+    a.tan_half_x = a.tan_half_y * ((float)p->width / (float)p->height);
+    a.radius = p->radius;
+    a.cam2 = cam[0] * cam[0] + cam[1] * cam[1] + cam[2] * cam[2];
+    a.base_nm = p->base_thickness_nm;
+    a.film_time = p->film_time;
+    a.swirl = p->swirl_intensity;
+    a.drainage_speed = p->drainage_speed;
+    a.pattern_scale = p->pattern_scale;
+    a.intensity = p->interference_intensity;
+    a.base_alpha = p->base_alpha;
+    a.edge_alpha = p->edge_alpha;
+    a.edge_mode = (int)p->edge_smoothing_mode;
+    a.inv_max_nm = 1.0f / p->lut_max_nm;
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_render_bubble_frame(const sbx_frame_params *p, const uint8_t *lut_rgba, int32_t T, int32_t A,
+                                           uint8_t *rgba_out, int32_t device)
+{
+    if (!lut_rgba || !rgba_out || T < 2 || A < 2) return fail(SBX_ERR_INVALID, "bad arguments");
+    FrameArgs a;
+    int32_t rc = frame_args_from(p, a);
+    if (rc != SBX_OK) return rc;
+    rc = pick_device(device);
+    if (rc != SBX_OK) return rc;
+    cudaArray_t arr = nullptr;
+    cudaTextureObject_t tex = 0;
+    uint32_t *out = nullptr;
+    const size_t bytes = (size_t)a.width * a.height * 4;
+    cudaChannelFormatDesc ch = cudaCreateChannelDesc<uchar4>();
+    cudaError_t e = cudaMallocArray(&arr, &ch, (size_t)T, (size_t)A);
+    if (e == cudaSuccess) e = cudaMemcpy2DToArray(arr, 0, 0, lut_rgba, (size_t)T * 4, (size_t)T * 4, (size_t)A, cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) {
+        cudaResourceDesc rd{};
+        rd.resType = cudaResourceTypeArray;
+        rd.res.array.array = arr;
+        cudaTextureDesc td{};  // sampler at pipeline.rs:350-359
+        td.addressMode[0] = td.addressMode[1] = cudaAddressModeClamp;
+        td.filterMode = cudaFilterModeLinear;
+        td.readMode = cudaReadModeNormalizedFloat;
+        td.normalizedCoords = 1;
+        e = cudaCreateTextureObject(&tex, &rd, &td, nullptr);
+    }
+    if (e == cudaSuccess) e = cudaMalloc(&out, bytes);
+    a.lut = tex;
+    a.out = out;
+    if (e == cudaSuccess) e = launch_bubble_frame(a, 0);
+    if (e == cudaSuccess) e = cudaMemcpy(rgba_out, out, bytes, cudaMemcpyDeviceToHost);
+    cudaFree(out);
+    if (tex) cudaDestroyTextureObject(tex);
+    if (arr) cudaFreeArray(arr);
+    if (e != cudaSuccess) return fail(SBX_ERR_CUDA, "bubble frame failed: %s", cudaGetErrorString(e));
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_render_frame(sbx_drainage *h, int32_t bubble, const sbx_frame_params *p, double n_film,
+                                             uint8_t *rgba_out)
+{
+    CHECK_H(h);
+    if (!rgba_out) return fail(SBX_ERR_INVALID, "rgba_out is null");
+    if (bubble < 0 || bubble >= h->batch) return fail(SBX_ERR_INVALID, "bubble %d out of range (batch %d)", bubble, h->batch);
+    if (h->row_begin != 0 || h->rows_local != h->num_theta)
+        return fail(SBX_ERR_UNSUPPORTED, "render_frame needs a whole-sphere handle (this one owns rows %d..%d of %d)",
+                    h->row_begin, h->row_end, h->num_theta);
+    if (!(n_film > 0.0)) return fail(SBX_ERR_INVALID, "n_film must be > 0");
+    FrameArgs a;
+    int32_t rc = frame_args_from(p, a);
+    if (rc != SBX_OK) return rc;
+    rc = ensure_lut(h, (float)n_film);
+    if (rc != SBX_OK) return rc;
+    a.inv_max_nm = 1.0f / h->lut_max_nm;
+    a.lut = h->lut_tex;
+    // local row 0 of the buffer is the ghost row: the field starts one row in
+    const char *base = static_cast<const char *>(h->buf[h->cur]);
+    a.field = base + ((size_t)bubble * h->bubble_stride + (size_t)h->num_phi) * h->esz;
+    a.field_f64 = h->f64 ? 1 : 0;
+    a.num_theta = h->num_theta;
+    a.num_phi = h->num_phi;
+    a.h_ref = h->b_href.empty() ? h->h_ref : h->b_href[bubble];
+    const size_t bytes = (size_t)a.width * a.height * 4;
+    uint32_t *out = nullptr;
+    CU(cudaMalloc(&out, bytes));
+    a.out = out;
+    cudaError_t e = launch_bubble_frame(a, h->stream);
+    h->launches++;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rgba_out, out, bytes, cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(out);
+    if (e != cudaSuccess) return fail(SBX_ERR_CUDA, "bubble frame failed: %s", cudaGetErrorString(e));
+    return SBX_OK;
+}
+
+// export_frame (src/export/image_export.rs:42-76): 8-bit RGBA PNG, one IDAT chunk, filter 0 on every scanline.
+static void png_chunk(std::vector<uint8_t> &o, const char type[4], const uint8_t *data, size_t n)
+{
+    const uint32_t len = (uint32_t)n;
+    const uint8_t be[4] = {(uint8_t)(len >> 24), (uint8_t)(len >> 16), (uint8_t)(len >> 8), (uint8_t)len};
+    o.insert(o.end(), be, be + 4);
+    const size_t at = o.size();
+    o.insert(o.end(), type, type + 4);
+    if (n) o.insert(o.end(), data, data + n);
+    const uint32_t crc = (uint32_t)crc32(0L, o.data() + at, (uInt)(n + 4));
+    const uint8_t cb[4] = {(uint8_t)(crc >> 24), (uint8_t)(crc >> 16), (uint8_t)(crc >> 8), (uint8_t)crc};
+    o.insert(o.end(), cb, cb + 4);
+}
+
+extern "C" int32_t sbx_export_frame_png(const char *path, uint32_t width, uint32_t height, const uint8_t *rgba, size_t len)
+{
+    if (!path || !rgba) return fail(SBX_ERR_INVALID, "null argument");
+    if (width == 0 || height == 0) return fail(SBX_ERR_INVALID, "Invalid dimensions: %ux%u", width, height);
+    const size_t expect = (size_t)width * height * 4;
+    if (len != expect || expect > 0x7fffffffull)
+        return fail(SBX_ERR_INVALID, "Data length %zu doesn't match expected %zu (%ux%ux4)", len, expect, width, height);
+    std::vector<uint8_t> raw((size_t)height * ((size_t)width * 4 + 1));
+    for (uint32_t y = 0; y < height; ++y) {
+        uint8_t *row = raw.data() + (size_t)y * ((size_t)width * 4 + 1);
+        row[0] = 0;  // filter type None
+        memcpy(row + 1, rgba + (size_t)y * width * 4, (size_t)width * 4);
+    }
+    uLongf zlen = compressBound((uLong)raw.size());
+    std::vector<uint8_t> z(zlen);
+    if (compress2(z.data(), &zlen, raw.data(), (uLong)raw.size(), 6) != Z_OK) return fail(SBX_ERR_IO, "Failed to save image: deflate failed");
+    std::vector<uint8_t> o;
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    o.insert(o.end(), sig, sig + 8);
+    const uint8_t ihdr[13] = {(uint8_t)(width >> 24), (uint8_t)(width >> 16), (uint8_t)(width >> 8), (uint8_t)width,
+                              (uint8_t)(height >> 24), (uint8_t)(height >> 16), (uint8_t)(height >> 8), (uint8_t)height,
+                              8, 6, 0, 0, 0};  // 8 bits per channel, colour type 6 = RGBA, no interlace
+    png_chunk(o, "IHDR", ihdr, sizeof ihdr);
+    png_chunk(o, "IDAT", z.data(), (size_t)zlen);
+    png_chunk(o, "IEND", nullptr, 0);
+    FILE *f = fopen(path, "wb");
+    if (!f) return fail(SBX_ERR_IO, "Failed to save image: cannot open %s", path);
+    const bool ok = fwrite(o.data(), 1, o.size(), f) == o.size();
+    if (fclose(f) != 0 || !ok) return fail(SBX_ERR_IO, "Failed to save image: write to %s failed", path);
     return SBX_OK;
 }
 

@@ -119,4 +119,23 @@ struct WgslArgs {
     RgbArgs rgb;
 };
 
+// arguments of one headless bubble frame (sbx_frame.cu; rows f3/f4)
+struct FrameArgs {
+    int width, height;
+    float cam[3], fwd[3], right[3], up[3];
+    float tan_half_x, tan_half_y;
+    float radius, cam2;
+    float base_nm, film_time, swirl, drainage_speed, pattern_scale;
+    float intensity, base_alpha, edge_alpha;
+    int edge_mode;
+    float bg[3];
+    float inv_max_nm;
+    cudaTextureObject_t lut;
+    const void *field;  // nullptr: procedural thickness; else [num_theta][num_phi] stored thickness (metres - h_ref)
+    int field_f64;
+    int num_theta, num_phi;
+    double h_ref;
+    uint32_t *out;
+};
+
 }  // namespace sbx

@@ -101,4 +101,7 @@ cudaError_t launch_sample_normal(const T *field, int W, int H, float href, const
                                  float *out_h, cudaStream_t st);
 cudaError_t launch_col_view(float *colA, int num_phi, double cam_x, double cam_z, cudaStream_t st);
 
+// the bubble fragment shader as a compute kernel (sbx_frame.cu): one thread per pixel of a headless frame
+cudaError_t launch_bubble_frame(const FrameArgs &a, cudaStream_t st);
+
 }  // namespace sbx
