@@ -183,3 +183,62 @@ pub fn generate_interference_lut(refractive_index: f32, intensity: f32) -> Vec<u
     check(unsafe { sbx_lut_build(refractive_index, intensity, data.as_mut_ptr(), 0) });
     data
 }
+
+/// HeadlessRenderPipeline for the bubble (src/render/headless.rs:27-552): same public fields and methods; `new` is no
+/// longer async because no wgpu adapter is requested.  The frame is bubble.wgsl::fs_main evaluated per pixel by libsbx.
+pub struct HeadlessRenderPipeline {
+    width: u32, height: u32, lut: Vec<u8>,
+    pub camera: crate::render::camera::Camera,
+    pub bubble_uniform: crate::render::pipeline::BubbleUniform,
+}
+
+impl HeadlessRenderPipeline {
+    pub fn new(width: u32, height: u32) -> Option<Self> {
+        let bubble_uniform = crate::render::pipeline::BubbleUniform::default();
+        let mut ndev = 0;
+        if unsafe { sbx_device_count(&mut ndev) } != 0 || ndev == 0 { return None; }  // "no GPU available": tests skip
+        Some(Self { width, height, lut: generate_interference_lut(bubble_uniform.refractive_index, 1.0),  // headless.rs:143-146
+                    camera: crate::render::camera::Camera::new(width as f32 / height as f32), bubble_uniform })
+    }
+    pub fn render_to_buffer(&mut self) -> Vec<u8> {
+        let b = &self.bubble_uniform;
+        let p = sbx_frame_params {
+            width: self.width, height: self.height,
+            cam_distance: self.camera.distance, cam_yaw: self.camera.yaw, cam_pitch: self.camera.pitch,
+            cam_fov_rad: self.camera.fov, radius: 0.025, base_thickness_nm: b.base_thickness_nm,
+            film_time: b.film_time, swirl_intensity: b.swirl_intensity, drainage_speed: b.drainage_speed,
+            pattern_scale: b.pattern_scale, interference_intensity: b.interference_intensity,
+            base_alpha: b.base_alpha, edge_alpha: b.edge_alpha, edge_smoothing_mode: b.edge_smoothing_mode,
+            background: [b.background_r, b.background_g, b.background_b], lut_max_nm: LUT_MAX_THICKNESS_NM,
+        };
+        let mut pixels = vec![0u8; (self.width * self.height * 4) as usize];
+        check(unsafe { sbx_render_bubble_frame(&p, self.lut.as_ptr(), LUT_THICKNESS_SAMPLES as i32,
+                                               LUT_ANGLE_SAMPLES as i32, pixels.as_mut_ptr(), 0) });
+        pixels
+    }
+    pub fn size(&self) -> (u32, u32) { (self.width, self.height) }
+    pub fn set_thickness(&mut self, thickness_nm: f32) { self.bubble_uniform.base_thickness_nm = thickness_nm; }
+    pub fn set_refractive_index(&mut self, n: f32) { self.bubble_uniform.refractive_index = n; }
+    pub fn orbit_camera(&mut self, delta_x: f32, delta_y: f32) { self.camera.orbit(delta_x, delta_y); }
+    pub fn zoom_camera(&mut self, delta: f32) { self.camera.zoom(delta); }
+    pub fn set_camera_distance(&mut self, distance: f32) { self.camera.distance = distance.clamp(0.05, 10.0); }
+    pub fn set_time(&mut self, time: f32) { self.bubble_uniform.time = time; self.bubble_uniform.film_time = time; }
+}
+
+/// export_frame (src/export/image_export.rs:42-76) with the reference's error enum.
+pub fn export_frame<P: AsRef<std::path::Path>>(path: P, width: u32, height: u32, data: &[u8])
+    -> Result<(), crate::export::ExportError> {
+    use crate::export::ExportError;
+    if width == 0 || height == 0 { return Err(ExportError::InvalidDimensions { width, height }); }
+    let expected_len = (width * height * 4) as usize;
+    if data.len() != expected_len {
+        return Err(ExportError::BufferCreation(format!("Data length {} doesn't match expected {} ({}x{}x4)",
+                                                       data.len(), expected_len, width, height)));
+    }
+    let c = std::ffi::CString::new(path.as_ref().to_string_lossy().as_bytes())
+        .map_err(|e| ExportError::SaveError(e.to_string()))?;
+    match unsafe { sbx_export_frame_png(c.as_ptr(), width, height, data.as_ptr(), data.len()) } {
+        0 => Ok(()),
+        _ => Err(ExportError::SaveError(unsafe { CStr::from_ptr(sbx_last_error()) }.to_string_lossy().into_owned())),
+    }
+}

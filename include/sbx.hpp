@@ -212,6 +212,67 @@ inline std::vector<uint8_t> generate_interference_lut(float refractive_index, fl
     return out;
 }
 
+// ---------------------------------------------------------------- headless frame + PNG export (rows f3/f4)
+// src/render/headless.rs:27-552 (bubble only), src/render/camera.rs:28-105, src/export/image_export.rs:42-76
+struct Camera {
+    float distance = 0.2f, yaw = 0.0f, pitch = 0.3f, fov = 45.0f * float(M_PI / 180.0), aspect = 1.0f;
+    void orbit(float dx, float dy)  // camera.rs:71-78
+    {
+        yaw += dx * 0.01f;
+        pitch += dy * 0.01f;
+        const float max_pitch = float(M_PI) / 2.0f - 0.01f;
+        pitch = std::fmin(std::fmax(pitch, -max_pitch), max_pitch);
+    }
+    void zoom(float delta)  // camera.rs:81-84
+    {
+        distance *= 1.0f - delta * 0.1f;
+        distance = std::fmin(std::fmax(distance, 0.05f), 10.0f);
+    }
+};
+
+class HeadlessRenderPipeline {
+public:
+    Camera camera;
+    sbx_frame_params bubble_uniform{};  // base_thickness_nm, film_time, ... (BubbleUniform::default, pipeline.rs:69-112)
+
+    HeadlessRenderPipeline(uint32_t width, uint32_t height, int32_t device = 0) : device_(device)
+    {
+        check(sbx_frame_params_default(&bubble_uniform));
+        bubble_uniform.width = width;
+        bubble_uniform.height = height;
+        camera.aspect = float(width) / float(height);
+        lut_ = generate_interference_lut(1.33f, 1.0f, device);  // headless.rs:143-146
+    }
+    std::array<uint32_t, 2> size() const { return {bubble_uniform.width, bubble_uniform.height}; }
+    void set_thickness(float nm) { bubble_uniform.base_thickness_nm = nm; }
+    void set_time(float t) { bubble_uniform.film_time = t; }
+    void set_camera_distance(float d) { camera.distance = std::fmin(std::fmax(d, 0.05f), 10.0f); }
+    void orbit_camera(float dx, float dy) { camera.orbit(dx, dy); }
+    void zoom_camera(float delta) { camera.zoom(delta); }
+    std::vector<uint8_t> render_to_buffer()  // headless.rs:437-512
+    {
+        sbx_frame_params p = bubble_uniform;
+        p.cam_distance = camera.distance;
+        p.cam_yaw = camera.yaw;
+        p.cam_pitch = camera.pitch;
+        p.cam_fov_rad = camera.fov;
+        std::vector<uint8_t> out(size_t(p.width) * p.height * 4);
+        check(sbx_render_bubble_frame(&p, lut_.data(), LUT_THICKNESS_SAMPLES, LUT_ANGLE_SAMPLES, out.data(), device_));
+        return out;
+    }
+
+private:
+    int32_t device_;
+    std::vector<uint8_t> lut_;
+};
+
+// export_frame, image_export.rs:42-76 (throws sbx::Error: SBX_ERR_INVALID for InvalidDimensions / BufferCreation,
+// SBX_ERR_IO for SaveError)
+inline void export_frame(const std::string &path, uint32_t width, uint32_t height, const std::vector<uint8_t> &data)
+{
+    check(sbx_export_frame_png(path.c_str(), width, height, data.data(), data.size()));
+}
+
 struct RgbColor {  // interference.rs:43-95
     double red = 0, green = 0, blue = 0;
     static RgbColor make(double r, double g, double b)

@@ -23,7 +23,8 @@ constexpr int kStages = 3;        // ring depth
 constexpr int kRowsPerStage = 3;  // theta rows per stage == the unroll of the three-row register window
 constexpr int kMaxBandRows = 64;
 #ifndef SBX_STORE_HINT
-#define SBX_STORE_HINT 0  // A/B knob: 1 = streaming stores for the RGBA8 frame, 2 = also for h', 3 = 2 + L2 evict_last on band-edge rows
+#define SBX_STORE_HINT 0  // A/B knob, bit mask: 1 = streaming stores for the RGBA8 frame, 2 = for h', 4 = L2 evict_last on the
+                          // band-edge rows a neighbouring band re-reads, 8 = L2 evict_first on the interior rows
 #endif  // rows a CTA marches at most (their coefficients are staged in shared memory)
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
@@ -125,8 +126,11 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
             const bool wrapL = c0 == 0, wrapR = c0 + w >= N;
             const uint32_t main_elems = (uint32_t)w + (wrapL ? 0 : HALO) + (wrapR ? 0 : HALO);
             const uint32_t row_bytes = ((uint32_t)w + 2 * HALO) * (uint32_t)sizeof(T);
-#if SBX_STORE_HINT >= 3
+#if SBX_STORE_HINT & 4
             const uint64_t pol = l2_policy_evict_last();
+#endif
+#if SBX_STORE_HINT & 8
+            const uint64_t pol_first = l2_policy_evict_first();
 #endif
             for (int c = 0; c < nchunks; ++c) {
                 const int s = c % kStages;
@@ -141,11 +145,17 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
                     const T *grow_ptr = in + (long long)(l0 - 1 + r) * N;
                     T *dst = ring + ((size_t)s * kRowsPerStage + (r - r_begin)) * rowf;
                     // ring row layout: [0,HALO) left halo | [HALO, HALO+w) main | [HALO+w, 2 HALO+w) right halo
-#if SBX_STORE_HINT >= 3
+#if SBX_STORE_HINT & 4
                     // the band's two halo rows and its first/last owned rows are read again by the neighbouring band
                     if (r <= 1 || r >= rows_load - 2)
                         tma_bulk_g2s_hint(dst + (wrapL ? HALO : 0), grow_ptr + c0 - (wrapL ? 0 : HALO),
                                           main_elems * (uint32_t)sizeof(T), &full[s], pol);
+                    else
+#endif
+#if SBX_STORE_HINT & 8
+                    if (r > 1 && r < rows_load - 2)  // interior rows are read exactly once
+                        tma_bulk_g2s_hint(dst + (wrapL ? HALO : 0), grow_ptr + c0 - (wrapL ? 0 : HALO),
+                                          main_elems * (uint32_t)sizeof(T), &full[s], pol_first);
                     else
 #endif
                     tma_bulk_g2s(dst + (wrapL ? HALO : 0), grow_ptr + c0 - (wrapL ? 0 : HALO),
@@ -225,7 +235,7 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
         else stage_p += stage_elems;
     };
     auto store_px = [&](uint32_t *dst, const uint32_t *px) {
-#if SBX_STORE_HINT >= 1  // the frame is never read back by the step: streaming (evict-first) stores
+#if SBX_STORE_HINT & 1  // the frame is never read back by the step: streaming (evict-first) stores
         if constexpr (VEC == 4) __stcs(reinterpret_cast<uint4 *>(dst), make_uint4(px[0], px[1], px[2], px[3]));
         else __stcs(reinterpret_cast<uint2 *>(dst), make_uint2(px[0], px[1]));
 #else
@@ -234,7 +244,7 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
 #endif
     };
     auto store_h = [&](T *dst, const Vec<T, VEC> &r) {
-#if SBX_STORE_HINT >= 2
+#if SBX_STORE_HINT & 2
         if constexpr (VEC == 4) __stcs(reinterpret_cast<float4 *>(dst), make_float4(r.v[0], r.v[1], r.v[2], r.v[3]));
         else __stcs(reinterpret_cast<double2 *>(dst), make_double2(r.v[0], r.v[1]));
 #else

@@ -53,6 +53,20 @@ int main()
     std::vector<float> hh, gg;
     a.sample_uv({0.25f, 0.5f, 0.75f, 0.1f}, hh, gg);
     if (hh.size() != 2 || !(hh[0] > 400e-9f && hh[0] < 500.1e-9f)) return 16;
+    sbx::HeadlessRenderPipeline hp(64, 64);                                             // headless.rs:50
+    hp.set_thickness(500.0f);
+    hp.set_time(0.0f);
+    const std::vector<uint8_t> px = hp.render_to_buffer();
+    if (px.size() != 64u * 64u * 4u || px[0] != 89 || px[1] != 89 || px[2] != 108 || px[3] != 255) return 17;  // background
+    const uint8_t *mid = &px[(32u * 64u + 32u) * 4u];
+    if (mid[0] == 89 && mid[1] == 89 && mid[2] == 108) return 18;                       // the bubble covers the centre
+    sbx::export_frame("/tmp/sbx_cxx_mirror.png", 64, 64, px);                           // image_export.rs:84-98
+    try {
+        sbx::export_frame("/tmp/sbx_cxx_mirror.png", 0, 100, {});                       // :100-104
+        return 19;
+    } catch (const sbx::Error &e) {
+        if (e.code != SBX_ERR_INVALID) return 20;
+    }
     std::printf("CXX_MIRROR_GPU_OK\n");
     return 0;
 }

@@ -41,6 +41,14 @@ def _off(a, b, lsb):
     return float(np.count_nonzero((d > lsb).any(axis=-1))) / (a.shape[0] * a.shape[1])
 
 
+def _changed(a, b, lsb=2):
+    """fraction of the bubble's pixels (anything that is not background in either image) that differ by more than `lsb`"""
+    bg = np.array([89, 89, 108])
+    hit = (a[..., :3] != bg).any(axis=-1) | (b[..., :3] != bg).any(axis=-1)
+    d = np.abs(a[..., :3].astype(int) - b[..., :3].astype(int))
+    return float(np.count_nonzero((d > lsb).any(axis=-1) & hit)) / max(int(hit.sum()), 1)
+
+
 @pytest.mark.parametrize("name", sorted(G.SCENES))
 def test_gpu_frame_reproduces_reference_golden(name):
     img = _pipeline(name).render_to_buffer()
@@ -74,7 +82,7 @@ def test_gpu_frame_time_and_size_parameters():
     ref = G.render_bubble(lut, size=200, film_time=3.7)
     assert _off(ref, img[:, 60:260], 2) <= 0.005
     still = S.HeadlessRenderPipeline.new(320, 200).render_to_buffer()
-    assert _off(still, img, 2) > 0.05  # the film pattern moved
+    assert _changed(still, img) > 0.10  # the film pattern moved
 
 
 def test_black_film_and_edge_modes():
@@ -92,7 +100,7 @@ def test_black_film_and_edge_modes():
         p = S.HeadlessRenderPipeline.new(128, 128)
         p.bubble_uniform.edge_smoothing_mode = mode
         other = p.render_to_buffer()
-        assert other.shape == (128, 128, 4) and _off(base, other, 2) > 0.05  # a different alpha ramp
+        assert other.shape == (128, 128, 4) and _changed(base, other) > 0.05  # a different alpha ramp
 
 
 def _bilinear_nm(field, n):
@@ -129,7 +137,7 @@ def test_drainage_field_frame(prec):
     off2 = _off(ref, img, 2)
     assert off2 <= 0.005, f"{100 * off2:.3f} % of pixels off by more than 2 LSB"
     sim.reset(300e-9)  # a different field gives a different picture
-    assert _off(S.render_drainage_frame(sim, 256, 256), img, 2) > 0.2
+    assert _changed(S.render_drainage_frame(sim, 256, 256), img) > 0.2
     sim.close()
 
 
