@@ -67,15 +67,22 @@ template <typename T> __device__ __forceinline__ T tmax(T a, T b);
 template <> __device__ __forceinline__ float tmax<float>(float a, float b) { return fmaxf(a, b); }
 template <> __device__ __forceinline__ double tmax<double>(double a, double b) { return fmax(a, b); }
 
-template <typename T> struct MinBlocks { static constexpr int value = 4; };
-template <> struct MinBlocks<double> { static constexpr int value = 3; };
+#ifndef SBX_TEX_PIPELINE
+#define SBX_TEX_PIPELINE 0  // A/B knob: 1 = the LUT fetch of a row is consumed one row later (f32 LUT mode)
+#endif
+#ifndef SBX_LUT_MIN_BLOCKS
+#define SBX_LUT_MIN_BLOCKS 4
+#endif
+template <typename T, int MODE> struct MinBlocks { static constexpr int value = 4; };
+template <int MODE> struct MinBlocks<double, MODE> { static constexpr int value = 3; };
+template <> struct MinBlocks<float, SBX_RGB_LUT> { static constexpr int value = SBX_LUT_MIN_BLOCKS; };
 
 }  // namespace
 
 // T = float (VEC 4) or double (VEC 2): a thread always owns one 16-byte packet of a row, a strip is 16*C bytes
 // wide plus a 16-byte halo each side, so ring geometry and copy sizes are identical for both types.
 template <typename T, int MODE, bool TFE>
-__global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const StepArgs<T> a)
+__global__ void __launch_bounds__(288, MinBlocks<T, MODE>::value) k_march_tma(const StepArgs<T> a)
 {
     constexpr int VEC = 16 / (int)sizeof(T);
     constexpr int HALO = VEC;
@@ -228,11 +235,18 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
         r.eL = src[-1];
         r.eR = src[VEC];
     };
-    auto release_stage = [&]() {
+    // `bits`: OR of the registers whose loads have not been consumed by an instruction yet (see mbar_arrive_after)
+    auto release_stage = [&](uint32_t bits) {
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[stage]);  // every lane of this warp has read the stage
+        if (lane == 0) mbar_arrive_after(&empty[stage], bits);  // every lane of this warp has read the stage
         if (++stage == kStages) { stage = 0; full_parity ^= 1u; stage_p = ring_t; }
         else stage_p += stage_elems;
+    };
+    auto row_bits = [&](const RowT &r) {
+        uint32_t b = dep_bits(r.eL) | dep_bits(r.eR);
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) b |= dep_bits(r.v[k]);
+        return b;
     };
     auto store_px = [&](uint32_t *dst, const uint32_t *px) {
 #if SBX_STORE_HINT & 1  // the frame is never read back by the step: streaming (evict-first) stores
@@ -262,6 +276,12 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
     const int ring_top = 1, ring_bot = a.num_theta - 2;
     const bool has_ring = (grow <= ring_top && ring_top <= a.row_begin + l1 - 1) ||
                           (grow <= ring_bot && ring_bot <= a.row_begin + l1 - 1);  // block-uniform
+
+    constexpr bool kPipe = SBX_TEX_PIPELINE && MODE == SBX_RGB_LUT && sizeof(T) == 4;
+    float4 tpend[VEC];  // kPipe: the previous row's LUT fetches, not yet packed
+    bool have_pend = false;
+#pragma unroll
+    for (int k = 0; k < VEC; ++k) tpend[k] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     auto compute_row = [&](const RowT &up, const RowT &cur, const RowT &dn) {
         T cApB, cAmB, cE, cG;  // {A+B, A-B, E, G}
@@ -328,7 +348,23 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
                     if (grow == a.peer.push_dn_grow) stv<T, VEC>(reinterpret_cast<T *>(a.peer.dn_ghost) + jc, nw);
                 }
             }
-            if constexpr (MODE != SBX_RGB_NONE) {
+            if constexpr (kPipe) {
+                // issue this row's LUT fetches, then pack and store the previous row's (fetched a whole row ago)
+                const float2 sc = *sc_p;
+                const float ccy = sc.y * a.rgb.cam_y;
+                float4 tn[VEC];
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) tn[k] = lut_fetch<T>(nw.v[k], href_u, colA[k], sc.x, ccy, Rv, camR2, a.rgb);
+                if (have_pend) {
+                    uint32_t px[VEC];
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) px[k] = lut_pack(tpend[k], a.rgb.intensity);
+                    store_px(rgb_p - N, px);
+                }
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) tpend[k] = tn[k];
+                have_pend = true;
+            } else if constexpr (MODE != SBX_RGB_NONE) {
                 const float2 sc = *sc_p;
                 const float ccy = sc.y * a.rgb.cam_y;
                 uint32_t px[VEC];
@@ -352,7 +388,8 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
     int left = l1 - l0 + 1;  // rows still to compute
     while (true) {
         load_slot(r2, 2);
-        release_stage();
+        // slot 2 was loaded just now; slot 1's edge values (r1.eL/eR) are first used by the row computed next
+        release_stage(row_bits(r2) | dep_bits(r1.eL) | dep_bits(r1.eR));
         compute_row(r0, r1, r2);
         if (--left == 0) break;
         mbar_wait(&full[stage], full_parity);
@@ -362,6 +399,14 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
         load_slot(r1, 1);
         compute_row(r2, r0, r1);
         if (--left == 0) break;
+    }
+    if constexpr (kPipe) {
+        if (active && have_pend) {  // the last row's colour
+            uint32_t px[VEC];
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) px[k] = lut_pack(tpend[k], a.rgb.intensity);
+            store_px(rgb_p - N, px);
+        }
     }
 
     // Pole rows (drainage.rs:480-503), folded into this kernel: the strips that updated a pole-adjacent ring wait
@@ -536,7 +581,7 @@ cudaError_t launch_march_tma(StepArgs<T> a, int batch, bool tfe, int band_rows_r
     if (occ == 0) {
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_march_tma<T, SBX_RGB_LUT, false>, consumers + 32, smem) != cudaSuccess || nb <= 0)
-            nb = MinBlocks<T>::value;
+            nb = MinBlocks<T, SBX_RGB_LUT>::value;
         occ = nb;
     }
     int band_rows = band_rows_req > 0 ? band_rows_req : auto_band_rows(rows, (long long)gx * batch, device_sm_count() * occ, 24);

@@ -103,8 +103,16 @@ __global__ void __launch_bounds__(288, 5) k_shade_tma(const StepArgs<T> a)
                 }
             }
         }
+        uint32_t bits = 0;  // the arrive must not overtake the loads above (see mbar_arrive_after)
+#pragma unroll
+        for (int r = 0; r < kSRowsPerStage; ++r) {
+            if (r < nr) {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) bits |= dep_bits(v[r][k]);
+            }
+        }
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[s]);  // the stage is in registers: hand it back before the colour work
+        if (lane == 0) mbar_arrive_after(&empty[s], bits);  // the stage is in registers: hand it back before the colour work
 #pragma unroll
         for (int r = 0; r < kSRowsPerStage; ++r) {
             if (r < nr) {
@@ -275,7 +283,9 @@ k_caustics_tma(const T *buf, long long bubble_stride, float *out, int N, int NT,
         mbar_wait(&full[s], (uint32_t)((rl / kCSlots) & 1));
         load_row(dn, s);
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[i % kCSlots]);  // row i (the `up` row) is in registers everywhere in this warp
+        // row i (the `up` row) is in registers everywhere in this warp: its loads were consumed by the `+ hr` adds of
+        // load_row two iterations ago, which precede this arrive in program order (in-order issue), so a plain arrive is safe
+        if (lane == 0) mbar_arrive(&empty[i % kCSlots]);
         if (active) {
             float o[VEC];
 #pragma unroll

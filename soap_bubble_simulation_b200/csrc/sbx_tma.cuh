@@ -21,6 +21,21 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
+// Hand a ring stage back to the producer AFTER this warp's shared-memory reads of it have returned.
+// A plain `ld.shared ...; mbarrier.arrive` pair is not enough: nothing makes the arrive wait for the loads' data
+// (SASS: SYNCS.ARRIVE carries no scoreboard wait on the preceding LDS), so under load-store-unit back-pressure the
+// arrive -- and the TMA overwrite it allows -- can overtake a load that is still queued, and the warp then reads the
+// NEXT contents of the slot (seen as one wrong row segment per ~1e6 warp-rows at 8192 x 16384).  Here the arrive's
+// address is made data-dependent on the loaded registers: `bits` is an OR of them and the mask is a run-time zero
+// (blockDim.y - 1 of a 1-D block) that no compiler stage can fold, so the instruction cannot issue before every
+// load that produced `bits` has written its registers -- for all lanes, since a warp's LDS is one instruction.
+__device__ __forceinline__ uint32_t dep_bits(float v) { return __float_as_uint(v); }
+__device__ __forceinline__ uint32_t dep_bits(double v) { return (uint32_t)__double2hiint(v) | (uint32_t)__double2loint(v); }
+__device__ __forceinline__ void mbar_arrive_after(uint64_t *bar, uint32_t bits)
+{
+    const uint32_t off = bits & (blockDim.y - 1u);
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar) + off) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
     asm volatile(

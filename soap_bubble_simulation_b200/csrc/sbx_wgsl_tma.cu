@@ -147,9 +147,13 @@ __global__ void __launch_bounds__(288, 3) k_wgsl_tma(const WgslArgs a)
         rc.eL = src2[-1];
         rc.eR = src2[4];
     };
-    auto release_stage = [&]() {
+    auto row_bits = [&](const RowW &r) {
+        return dep_bits(r.v[0]) | dep_bits(r.v[1]) | dep_bits(r.v[2]) | dep_bits(r.v[3]) | dep_bits(r.eL) | dep_bits(r.eR);
+    };
+    // `bits`: OR of the registers whose loads no instruction has consumed yet (see mbar_arrive_after)
+    auto release_stage = [&](uint32_t bits) {
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[stage]);
+        if (lane == 0) mbar_arrive_after(&empty[stage], bits);
         if (++stage == kWStages) { stage = 0; full_parity ^= 1u; stage_p = ring_t; }
         else stage_p += stage_floats;
     };
@@ -227,7 +231,8 @@ __global__ void __launch_bounds__(288, 3) k_wgsl_tma(const WgslArgs a)
     int left = l1 - l0 + 1;
     while (true) {
         load_slot(h2, g2, 2);
-        release_stage();
+        // slot 2 (h2, g2) was loaded just now; slot 1's edge values are first used by the row computed next
+        release_stage(row_bits(h2) | row_bits(g2) | dep_bits(h1.eL) | dep_bits(h1.eR) | dep_bits(g1.eL) | dep_bits(g1.eR));
         compute_row(h0, h1, h2, g0, g1, g2);
         if (--left == 0) break;
         mbar_wait(&full[stage], full_parity);

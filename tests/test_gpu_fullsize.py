@@ -60,6 +60,40 @@ def test_full_size_fused_step_matches_oracle(S, nt, nphi, steps):
     assert mn == float(got.min()) and mx == float(got.max())
 
 
+@pytest.mark.parametrize("what", ["cpu_f32", "cpu_f64", "wgsl", "shade"])
+def test_ring_kernels_are_deterministic_at_full_size(S, what):
+    """Two runs of 40 steps from the same 8192x16384 input must agree bit for bit (thickness and frame).  This is
+    the regression test of a ring-protocol race: a stage was handed back to the TMA producer by an mbarrier arrive
+    that did not wait for the warp's own shared-memory loads, and about one step in three at this size read one
+    64-128 cell row segment from the slot's next contents (relative error 1e-2 = the synthetic noise level).  40
+    steps x 2 runs would have hit it with near certainty."""
+    nt, nphi = 8192, 16384
+    f = synthetic_field(nt, nphi, dtype=np.float32)
+    dt = 0.25 * dt_max(nt, nphi)
+    view = S.View(mode=S.RGB_LUT, format=S.OUT_RGBA8)
+    runs = []
+    for _ in range(2):
+        if what == "wgsl":
+            sim = S.GPUDrainageSimulator(500e-9, nphi, nt)
+            sim.set_marangoni_enabled(True)
+            sim.set_dt(dt)
+            sim.upload(f)
+            sim.dispatch(40, view)
+        else:
+            sim = _sim(S, nt, nphi, prec=S.PREC_F64 if what == "cpu_f64" else S.PREC_F32)
+            sim.upload(f)
+            if what == "shade":
+                for _ in range(40):
+                    sim.shade(view)
+            else:
+                for _ in range(8):
+                    sim.step_fused(dt, view, 5)
+        runs.append((sim.download(np.float32)[0], sim.download_rgb()[0]))
+        sim.close()
+    assert np.array_equal(runs[0][0], runs[1][0], equal_nan=True)
+    assert np.array_equal(runs[0][1], runs[1][1])
+
+
 def test_axisymmetric_field_stays_axisymmetric_c3(S):
     """A phi-independent field has an exactly zero phi-Laplacian, so every row must stay constant bit for bit
     (checks the seam wrap, the strip halos and the band boundaries of the TMA ring at full size)."""
