@@ -121,6 +121,11 @@ if "hl" in which:  # headline only (A/B runs)
     single("C3 8192x16384 f32 fused LUT->RGBA8 (headline)", 8192, 16384, S.PREC_F32, S.RGB_LUT, 200, 12)
     single("C2 2048x4096 f32 fused LUT->RGBA8", 2048, 4096, S.PREC_F32, S.RGB_LUT, 400, 12)
 
+if "l2ab" in which:  # the other fields-larger-than-L2 cases of the march kernel (A/B of the L2 policy)
+    single("C3 f64 fused LUT->RGBA8", 8192, 16384, S.PREC_F64, S.RGB_LUT, 50, 20)
+    single("C3 f32 drainage only", 8192, 16384, S.PREC_F32, S.RGB_NONE, 100, 8)
+    single("C3 f32 fused two-beam Schlick->RGBA8", 8192, 16384, S.PREC_F32, S.RGB_SCHLICK_TWO_BEAM, 50, 12)
+
 if "modes" in which:
     single("C3 f32 fused EXACT3 (3-lambda exact Fresnel + gamma)->RGBA8", 8192, 16384, S.PREC_F32, S.RGB_EXACT3, 30, 12,
            note="SFU/issue-bound: 3 sinpi + 3 pow per cell, f64 phase")

@@ -160,6 +160,7 @@ struct sbx_drainage {
     int peer_up_rows = 0;
     unsigned long long epoch = 0;
     int band_rows = 0;
+    bool l2_keep_edges = false;          // field (in + out) larger than L2: keep the rows neighbouring bands share (SBX_L2_KEEP=0/1 overrides)
     bool use_resident = true;            // SBX_NO_RESIDENT=1: always use the streaming kernels
     FrontTable *res_tabs_host[2] = {nullptr, nullptr};  // pinned: per-step TFE tables of a resident launch
     FrontTable *res_tabs_dev[2] = {nullptr, nullptr};
@@ -414,6 +415,12 @@ extern "C" int32_t sbx_drainage_create(const sbx_drainage_cfg *cfg, int32_t devi
     if (const char *s = getenv("SBX_BAND_ROWS")) h->band_rows = atoi(s);
     if (const char *s = getenv("SBX_NO_TMA")) h->use_tma = atoi(s) == 0;
     if (const char *s = getenv("SBX_NO_RESIDENT")) h->use_resident = atoi(s) == 0;
+    {
+        int l2 = 0;
+        cudaDeviceGetAttribute(&l2, cudaDevAttrL2CacheSize, h->device);
+        h->l2_keep_edges = l2 > 0 && 2.0 * (double)h->total_elems * (double)h->esz > (double)l2;
+        if (const char *s = getenv("SBX_L2_KEEP")) h->l2_keep_edges = atoi(s) != 0;
+    }
 
 #define CU_H(expr)                                                                     \
     do {                                                                               \
@@ -855,6 +862,7 @@ static void fill_step_args(sbx_drainage *h, StepArgs<T> &a, double dt, const Rgb
     a.s_crit = h->critical;
     a.s_tfe_factor = 1.0 - reduction_rate * dt;  // drainage.rs:454
     a.rgb = rgb;
+    a.l2_keep_edges = h->l2_keep_edges ? 1 : 0;
 }
 
 // decide whether this launch writes the pole rows inside the TMA kernel, and which arrival count it waits for

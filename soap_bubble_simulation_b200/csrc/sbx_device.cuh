@@ -343,23 +343,6 @@ __device__ __forceinline__ uint32_t shade_px(T h, T href, float href_u, float co
     }
 }
 
-// The LUT colour stage in two halves, so that a kernel can issue the texture fetch of one row and pack / store it a
-// row later (the fetch latency then overlaps the next row's stencil instead of stalling the warp).
-template <typename T>
-__device__ __forceinline__ float4 lut_fetch(T h, float href_u, float colA, float sin_th, float ccy, float R, float camR2,
-                                            const RgbArgs &rgb)
-{
-    const float nc = fmaf(sin_th, colA, ccy);
-    const float len2 = fmaf(-2.f * R, nc, camR2);
-    const float u = __saturatef(fmaf((float)h, rgb.nm_over_max, href_u));
-    const float v = __saturatef(fabsf(nc - R) * rsqrt_approx(len2));
-    return tex2D<float4>(rgb.lut, u, v);
-}
-__device__ __forceinline__ uint32_t lut_pack(const float4 t, float intensity)
-{
-    return pack_rgba8_fast(__saturatef(t.x * intensity), __saturatef(t.y * intensity), __saturatef(t.z * intensity));
-}
-
 // ------------------------------------------------------------------ caustic map (thickness-buffer consumer, row f2)
 // caustics_compute.wgsl::main (src/render/shaders/caustics_compute.wgsl:29-126): 9-point stencil on the thickness
 // buffer, phi wrapped, theta clamped at the poles (ghost rows supply the neighbours of a latitude band).

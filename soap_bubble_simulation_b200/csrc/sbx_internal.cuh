@@ -93,6 +93,7 @@ struct StepArgs {
     int row_begin;           // global row of local row 1
     int l_first, l_last;     // local rows to update, inclusive (global poles excluded)
     int band_rows;           // rows marched by one block
+    int l2_keep_edges;       // TMA kernel: L2 evict_last policy on the rows neighbouring bands share (fields larger than L2)
     long long bubble_stride; // elements per bubble in in/out: (rows_local + 2) * num_phi
     long long rgb_bubble_stride;  // cells per bubble in rgb out: rows_local * num_phi
     T dt, crit, coefA;       // coefA = D / (R^2 dtheta^2)

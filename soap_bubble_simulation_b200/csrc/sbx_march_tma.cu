@@ -22,10 +22,7 @@ namespace {
 constexpr int kStages = 3;        // ring depth
 constexpr int kRowsPerStage = 3;  // theta rows per stage == the unroll of the three-row register window
 constexpr int kMaxBandRows = 64;
-#ifndef SBX_STORE_HINT
-#define SBX_STORE_HINT 0  // A/B knob, bit mask: 1 = streaming stores for the RGBA8 frame, 2 = for h', 4 = L2 evict_last on the
-                          // band-edge rows a neighbouring band re-reads, 8 = L2 evict_first on the interior rows
-#endif  // rows a CTA marches at most (their coefficients are staged in shared memory)
+  // rows a CTA marches at most (their coefficients are staged in shared memory)
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
 {
@@ -67,22 +64,15 @@ template <typename T> __device__ __forceinline__ T tmax(T a, T b);
 template <> __device__ __forceinline__ float tmax<float>(float a, float b) { return fmaxf(a, b); }
 template <> __device__ __forceinline__ double tmax<double>(double a, double b) { return fmax(a, b); }
 
-#ifndef SBX_TEX_PIPELINE
-#define SBX_TEX_PIPELINE 0  // A/B knob: 1 = the LUT fetch of a row is consumed one row later (f32 LUT mode)
-#endif
-#ifndef SBX_LUT_MIN_BLOCKS
-#define SBX_LUT_MIN_BLOCKS 4
-#endif
-template <typename T, int MODE> struct MinBlocks { static constexpr int value = 4; };
-template <int MODE> struct MinBlocks<double, MODE> { static constexpr int value = 3; };
-template <> struct MinBlocks<float, SBX_RGB_LUT> { static constexpr int value = SBX_LUT_MIN_BLOCKS; };
+template <typename T> struct MinBlocks { static constexpr int value = 4; };
+template <> struct MinBlocks<double> { static constexpr int value = 3; };
 
 }  // namespace
 
 // T = float (VEC 4) or double (VEC 2): a thread always owns one 16-byte packet of a row, a strip is 16*C bytes
 // wide plus a 16-byte halo each side, so ring geometry and copy sizes are identical for both types.
 template <typename T, int MODE, bool TFE>
-__global__ void __launch_bounds__(288, MinBlocks<T, MODE>::value) k_march_tma(const StepArgs<T> a)
+__global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const StepArgs<T> a)
 {
     constexpr int VEC = 16 / (int)sizeof(T);
     constexpr int HALO = VEC;
@@ -133,12 +123,12 @@ __global__ void __launch_bounds__(288, MinBlocks<T, MODE>::value) k_march_tma(co
             const bool wrapL = c0 == 0, wrapR = c0 + w >= N;
             const uint32_t main_elems = (uint32_t)w + (wrapL ? 0 : HALO) + (wrapR ? 0 : HALO);
             const uint32_t row_bytes = ((uint32_t)w + 2 * HALO) * (uint32_t)sizeof(T);
-#if SBX_STORE_HINT & 4
-            const uint64_t pol = l2_policy_evict_last();
-#endif
-#if SBX_STORE_HINT & 8
-            const uint64_t pol_first = l2_policy_evict_first();
-#endif
+            // Fields larger than L2: the band's two halo rows and its first / last owned rows are read again by the
+            // neighbouring band about one band-time later, by when the streaming traffic has evicted them (ncu: 3.7 %
+            // of the reads reached DRAM twice).  An evict_last policy on just those rows keeps them: +1.7 % at
+            // 8192 x 16384; on an L2-resident field (2048 x 4096) the same hint costs 7 %, so the host decides.
+            const bool keep_edges = a.l2_keep_edges != 0;
+            const uint64_t pol = keep_edges ? l2_policy_evict_last() : 0ull;
             for (int c = 0; c < nchunks; ++c) {
                 const int s = c % kStages;
                 if (c >= kStages) mbar_wait(&empty[s], (uint32_t)(((c / kStages) - 1) & 1));
@@ -152,21 +142,12 @@ __global__ void __launch_bounds__(288, MinBlocks<T, MODE>::value) k_march_tma(co
                     const T *grow_ptr = in + (long long)(l0 - 1 + r) * N;
                     T *dst = ring + ((size_t)s * kRowsPerStage + (r - r_begin)) * rowf;
                     // ring row layout: [0,HALO) left halo | [HALO, HALO+w) main | [HALO+w, 2 HALO+w) right halo
-#if SBX_STORE_HINT & 4
-                    // the band's two halo rows and its first/last owned rows are read again by the neighbouring band
-                    if (r <= 1 || r >= rows_load - 2)
+                    if (keep_edges && (r <= 1 || r >= rows_load - 2))
                         tma_bulk_g2s_hint(dst + (wrapL ? HALO : 0), grow_ptr + c0 - (wrapL ? 0 : HALO),
                                           main_elems * (uint32_t)sizeof(T), &full[s], pol);
                     else
-#endif
-#if SBX_STORE_HINT & 8
-                    if (r > 1 && r < rows_load - 2)  // interior rows are read exactly once
-                        tma_bulk_g2s_hint(dst + (wrapL ? HALO : 0), grow_ptr + c0 - (wrapL ? 0 : HALO),
-                                          main_elems * (uint32_t)sizeof(T), &full[s], pol_first);
-                    else
-#endif
-                    tma_bulk_g2s(dst + (wrapL ? HALO : 0), grow_ptr + c0 - (wrapL ? 0 : HALO),
-                                 main_elems * (uint32_t)sizeof(T), &full[s]);
+                        tma_bulk_g2s(dst + (wrapL ? HALO : 0), grow_ptr + c0 - (wrapL ? 0 : HALO),
+                                     main_elems * (uint32_t)sizeof(T), &full[s]);
                     if (wrapL) tma_bulk_g2s(dst, grow_ptr + (N - HALO), 16u, &full[s]);       // periodic seam
                     if (wrapR) tma_bulk_g2s(dst + HALO + w, grow_ptr, 16u, &full[s]);         // periodic seam
                 }
@@ -249,21 +230,9 @@ __global__ void __launch_bounds__(288, MinBlocks<T, MODE>::value) k_march_tma(co
         return b;
     };
     auto store_px = [&](uint32_t *dst, const uint32_t *px) {
-#if SBX_STORE_HINT & 1  // the frame is never read back by the step: streaming (evict-first) stores
-        if constexpr (VEC == 4) __stcs(reinterpret_cast<uint4 *>(dst), make_uint4(px[0], px[1], px[2], px[3]));
-        else __stcs(reinterpret_cast<uint2 *>(dst), make_uint2(px[0], px[1]));
-#else
+        // (streaming __stcs stores for the frame and/or h' were measured: -0.8 % / -1 %, so plain stores)
         if constexpr (VEC == 4) *reinterpret_cast<uint4 *>(dst) = make_uint4(px[0], px[1], px[2], px[3]);
         else *reinterpret_cast<uint2 *>(dst) = make_uint2(px[0], px[1]);
-#endif
-    };
-    auto store_h = [&](T *dst, const Vec<T, VEC> &r) {
-#if SBX_STORE_HINT & 2
-        if constexpr (VEC == 4) __stcs(reinterpret_cast<float4 *>(dst), make_float4(r.v[0], r.v[1], r.v[2], r.v[3]));
-        else __stcs(reinterpret_cast<double2 *>(dst), make_double2(r.v[0], r.v[1]));
-#else
-        stv<T, VEC>(dst, r);
-#endif
     };
 
     // running output pointers (bumped by one row per sub-step)
@@ -276,12 +245,6 @@ __global__ void __launch_bounds__(288, MinBlocks<T, MODE>::value) k_march_tma(co
     const int ring_top = 1, ring_bot = a.num_theta - 2;
     const bool has_ring = (grow <= ring_top && ring_top <= a.row_begin + l1 - 1) ||
                           (grow <= ring_bot && ring_bot <= a.row_begin + l1 - 1);  // block-uniform
-
-    constexpr bool kPipe = SBX_TEX_PIPELINE && MODE == SBX_RGB_LUT && sizeof(T) == 4;
-    float4 tpend[VEC];  // kPipe: the previous row's LUT fetches, not yet packed
-    bool have_pend = false;
-#pragma unroll
-    for (int k = 0; k < VEC; ++k) tpend[k] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     auto compute_row = [&](const RowT &up, const RowT &cur, const RowT &dn) {
         T cApB, cAmB, cE, cG;  // {A+B, A-B, E, G}
@@ -341,30 +304,14 @@ __global__ void __launch_bounds__(288, MinBlocks<T, MODE>::value) k_march_tma(co
             }
         }
         if (active) {
-            store_h(out_p, nw);
+            stv<T, VEC>(out_p, nw);
             if (a.peer.enabled) {  // boundary rows also land in the neighbours' ghost rows (peer stores over NVLink)
                 if constexpr (sizeof(T) == 4) {
                     if (grow == a.peer.push_up_grow) stv<T, VEC>(reinterpret_cast<T *>(a.peer.up_ghost) + jc, nw);
                     if (grow == a.peer.push_dn_grow) stv<T, VEC>(reinterpret_cast<T *>(a.peer.dn_ghost) + jc, nw);
                 }
             }
-            if constexpr (kPipe) {
-                // issue this row's LUT fetches, then pack and store the previous row's (fetched a whole row ago)
-                const float2 sc = *sc_p;
-                const float ccy = sc.y * a.rgb.cam_y;
-                float4 tn[VEC];
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) tn[k] = lut_fetch<T>(nw.v[k], href_u, colA[k], sc.x, ccy, Rv, camR2, a.rgb);
-                if (have_pend) {
-                    uint32_t px[VEC];
-#pragma unroll
-                    for (int k = 0; k < VEC; ++k) px[k] = lut_pack(tpend[k], a.rgb.intensity);
-                    store_px(rgb_p - N, px);
-                }
-#pragma unroll
-                for (int k = 0; k < VEC; ++k) tpend[k] = tn[k];
-                have_pend = true;
-            } else if constexpr (MODE != SBX_RGB_NONE) {
+            if constexpr (MODE != SBX_RGB_NONE) {
                 const float2 sc = *sc_p;
                 const float ccy = sc.y * a.rgb.cam_y;
                 uint32_t px[VEC];
@@ -400,15 +347,6 @@ __global__ void __launch_bounds__(288, MinBlocks<T, MODE>::value) k_march_tma(co
         compute_row(r2, r0, r1);
         if (--left == 0) break;
     }
-    if constexpr (kPipe) {
-        if (active && have_pend) {  // the last row's colour
-            uint32_t px[VEC];
-#pragma unroll
-            for (int k = 0; k < VEC; ++k) px[k] = lut_pack(tpend[k], a.rgb.intensity);
-            store_px(rgb_p - N, px);
-        }
-    }
-
     // Pole rows (drainage.rs:480-503), folded into this kernel: the strips that updated a pole-adjacent ring wait
     // until all strips of that ring have published their partial sums (they were dispatched together, so this
     // is a short spin among co-resident CTAs), add them in a fixed order and write their own slice of the pole
@@ -581,7 +519,7 @@ cudaError_t launch_march_tma(StepArgs<T> a, int batch, bool tfe, int band_rows_r
     if (occ == 0) {
         int nb = 0;
         if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_march_tma<T, SBX_RGB_LUT, false>, consumers + 32, smem) != cudaSuccess || nb <= 0)
-            nb = MinBlocks<T, SBX_RGB_LUT>::value;
+            nb = MinBlocks<T>::value;
         occ = nb;
     }
     int band_rows = band_rows_req > 0 ? band_rows_req : auto_band_rows(rows, (long long)gx * batch, device_sm_count() * occ, 24);
