@@ -121,6 +121,21 @@ if "hl" in which:  # headline only (A/B runs)
     single("C3 8192x16384 f32 fused LUT->RGBA8 (headline)", 8192, 16384, S.PREC_F32, S.RGB_LUT, 200, 12)
     single("C2 2048x4096 f32 fused LUT->RGBA8", 2048, 4096, S.PREC_F32, S.RGB_LUT, 400, 12)
 
+if "tfe" in which:
+    # The headline run starts at t = 0, where no marginal-regeneration front exists yet (first spawn at t = 0.5 s,
+    # drainage.rs:397-403), so it runs the kernel's no-front instantiation.  This line times the TFE = true
+    # instantiation with fronts alive: the simulator is advanced to t = 15 s with a dt far above the stability bound
+    # of this grid (the field values are meaningless by then -- timing only, same memory traffic and instruction path).
+    sim = S.DrainageSimulator(S.SimulationConfig.default(), precision=S.PREC_F32, num_theta=8192, num_phi=16384, h_ref=0.0)
+    sim.upload(synthetic_field(8192, 16384, dtype=np.float32))
+    sim.set_stream(stream.cuda_stream)
+    sim.step(2.5e-3, 6000)
+    view = S.View()
+    ms = timed(lambda n: sim.step_fused(2.5e-3, view, n), 100)
+    report("C3 f32 fused LUT->RGBA8 with marginal-regeneration fronts alive (timing only)", 8190 * 16384, 12, ms,
+           f"{sim.active_tfe_count()} fronts alive at t = {sim.current_time():.2f} s")
+    sim.close()
+
 if "l2ab" in which:  # the other fields-larger-than-L2 cases of the march kernel (A/B of the L2 policy)
     single("C3 f64 fused LUT->RGBA8", 8192, 16384, S.PREC_F64, S.RGB_LUT, 50, 20)
     single("C3 f32 drainage only", 8192, 16384, S.PREC_F32, S.RGB_NONE, 100, 8)

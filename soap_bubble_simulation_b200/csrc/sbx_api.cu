@@ -972,6 +972,7 @@ static int32_t step_wgsl_sem(sbx_drainage *h, double dt, const RgbArgs &rgb)
     WgslArgs a;
     fill_wgsl_args(h, a, rgb);
     int n = 0;
+    a.l2_keep_edges = h->l2_keep_edges ? 1 : 0;
     CU(launch_wgsl(a, h->batch, h->band_rows, h->use_tma, h->stream, &n));
     if (rgb.mode != SBX_RGB_NONE && (h->row_begin == 0 || h->row_end == h->num_theta)) {
         // frozen pole rows still need their colour: shade them from the (unchanged) pole values

@@ -115,6 +115,18 @@ __device__ __forceinline__ bool front_hit(const FrontTable &ft, unsigned rowmask
     return hit;
 }
 
+// fronts whose phi interval contains column `col` (bit per front); independent of the row
+__device__ __forceinline__ unsigned front_col_mask(const FrontTable &ft, int col)
+{
+    unsigned m = 0;
+#pragma unroll
+    for (int k = 0; k < kMaxFronts; ++k) {
+        const FrontCells &f = ft.f[k];
+        if (k < ft.count && ((col >= f.c0_lo && col <= f.c0_hi) || (col >= f.c1_lo && col <= f.c1_hi))) m |= 1u << k;
+    }
+    return m;
+}
+
 // ------------------------------------------------------------------ colour stage (f32)
 __device__ __forceinline__ float clamp01(float x) { return fminf(fmaxf(x, 0.f), 1.f); }
 

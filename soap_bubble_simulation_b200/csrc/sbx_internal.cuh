@@ -113,6 +113,7 @@ struct WgslArgs {
     const float2 *rowSC;
     int num_phi, num_theta, row_begin, l_first, l_last, band_rows;
     int rows_local;
+    int l2_keep_edges;  // as in StepArgs
     long long bubble_stride, rgb_bubble_stride;
     sbx_drainage_params p;
     float delta_theta, delta_phi;

@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
     // instead of two global loads on the critical path of its first instruction
     __shared__ __align__(16) T s_coef[kMaxBandRows][4];
     __shared__ float2 s_sc[kMaxBandRows];
+    __shared__ unsigned s_rm[kMaxBandRows];  // TFE: which fronts cover each row of the band (bit per front)
     const int C = blockDim.x - 32;  // consumer threads
     const int N = a.num_phi;
     const int strip_w_max = VEC * C;
@@ -169,6 +170,7 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
             *reinterpret_cast<double2 *>(&s_coef[r][2]) = __ldg(reinterpret_cast<const double2 *>(a.coefF + 4 * g) + 1);
         }
         s_sc[r] = __ldg(a.rowSC + g);
+        if constexpr (TFE) s_rm[r] = front_row_mask(a.fronts, (int)g);
     }
     bar_consumers(C);
     const int jloc = tid * VEC;  // column offset inside the strip
@@ -189,6 +191,15 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
     if constexpr (MODE != SBX_RGB_NONE) {
 #pragma unroll
         for (int k = 0; k < VEC; ++k) colA[k] = __ldg(a.rgb.colA + jc + k);
+    }
+    // TFE: a front's phi interval does not depend on the row, and a thread keeps its columns for the whole band, so
+    // the column half of TfeFront::contains (drainage.rs:55-71) is taken once: byte k of colmask = fronts covering
+    // column jc + k.  A cell is then in a front iff (row mask & its byte) != 0 -- one AND per row plus a test per cell
+    // instead of 8 x 4 compares per cell (C3 with 8 fronts alive was 164 Gcell/s with the per-cell compares).
+    unsigned colmask = 0;
+    if constexpr (TFE) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) colmask |= front_col_mask(a.fronts, jc + k) << (8 * k);
     }
     const float Rv = bp.radius;
     const float camR2 = a.rgb.cam2 + Rv * Rv;
@@ -241,6 +252,7 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
                       (long long)(l0 - 1) * N + jc;
     const T *cf_p = &s_coef[0][0];
     const float2 *sc_p = s_sc;
+    const unsigned *rm_p = s_rm;
     int grow = a.row_begin + l0 - 1;
     const int ring_top = 1, ring_bot = a.num_theta - 2;
     const bool has_ring = (grow <= ring_top && ring_top <= a.row_begin + l1 - 1) ||
@@ -296,12 +308,14 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
             bar_consumers(C);
         }
         if constexpr (TFE) {
-            const unsigned rm = front_row_mask(a.fronts, grow);
-            if (rm) {
+            const unsigned rm = *rm_p;
+            if (rm) {  // uniform over the CTA
+                const unsigned m = (rm * 0x01010101u) & colmask;
 #pragma unroll
                 for (int k = 0; k < VEC; ++k)
-                    if (front_hit(a.fronts, rm, jc + k)) nw.v[k] = fma(-(nw.v[k] + href), a.tfe_rdt, nw.v[k]);
+                    if (m & (0xffu << (8 * k))) nw.v[k] = fma(-(nw.v[k] + href), a.tfe_rdt, nw.v[k]);
             }
+            ++rm_p;
         }
         if (active) {
             stv<T, VEC>(out_p, nw);
@@ -377,12 +391,10 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) pv.v[k] = v;
                 if constexpr (TFE) {
-                    const unsigned rm = front_row_mask(a.fronts, prow);
-                    if (rm) {
+                    const unsigned m = (front_row_mask(a.fronts, prow) * 0x01010101u) & colmask;
 #pragma unroll
-                        for (int k = 0; k < VEC; ++k)
-                            if (front_hit(a.fronts, rm, jc + k)) pv.v[k] = fma(-(pv.v[k] + href), a.tfe_rdt, pv.v[k]);
-                    }
+                    for (int k = 0; k < VEC; ++k)
+                        if (m & (0xffu << (8 * k))) pv.v[k] = fma(-(pv.v[k] + href), a.tfe_rdt, pv.v[k]);
                 }
                 stv<T, VEC>(out + (long long)pl * N + jc, pv);
                 if constexpr (MODE != SBX_RGB_NONE) {

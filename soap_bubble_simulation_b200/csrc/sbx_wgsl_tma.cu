@@ -72,6 +72,8 @@ __global__ void __launch_bounds__(288, 3) k_wgsl_tma(const WgslArgs a)
             const bool wrapL = c0 == 0, wrapR = c0 + w >= N;
             const uint32_t main_floats = (uint32_t)w + (wrapL ? 0 : kWHalo) + (wrapR ? 0 : kWHalo);
             const uint32_t row_bytes = 2u * ((uint32_t)w + 2 * kWHalo) * 4u;  // both fields
+            const bool keep_edges = a.l2_keep_edges != 0;  // fields larger than L2, see k_march_tma
+            const uint64_t pol = keep_edges ? l2_policy_evict_last() : 0ull;
             for (int c = 0; c < nchunks; ++c) {
                 const int s = c % kWStages;
                 if (c >= kWStages) mbar_wait(&empty[s], (uint32_t)(((c / kWStages) - 1) & 1));
@@ -84,7 +86,10 @@ __global__ void __launch_bounds__(288, 3) k_wgsl_tma(const WgslArgs a)
                     for (int f = 0; f < 2; ++f) {
                         const float *grow_ptr = (f == 0 ? hin : cin) + (long long)(l0 - 1 + r) * N;
                         float *dst = slot + f * rowf;
-                        tma_bulk_g2s(dst + (wrapL ? kWHalo : 0), grow_ptr + c0 - (wrapL ? 0 : kWHalo), main_floats * 4u, &full[s]);
+                        if (keep_edges && (r <= 1 || r >= rows_load - 2))  // rows the neighbouring band reads again
+                            tma_bulk_g2s_hint(dst + (wrapL ? kWHalo : 0), grow_ptr + c0 - (wrapL ? 0 : kWHalo), main_floats * 4u, &full[s], pol);
+                        else
+                            tma_bulk_g2s(dst + (wrapL ? kWHalo : 0), grow_ptr + c0 - (wrapL ? 0 : kWHalo), main_floats * 4u, &full[s]);
                         if (wrapL) tma_bulk_g2s(dst, grow_ptr + (N - kWHalo), kWHalo * 4u, &full[s]);
                         if (wrapR) tma_bulk_g2s(dst + kWHalo + w, grow_ptr, kWHalo * 4u, &full[s]);
                     }

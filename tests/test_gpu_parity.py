@@ -171,6 +171,41 @@ def test_f32_with_tfe_fronts_long_run(S):
     assert np.abs(got / ora.data - 1).max() <= 1e-5
 
 
+@pytest.mark.parametrize("prec,tol", [("PREC_F32", 1e-5), ("PREC_F64", 1e-12)])
+def test_streaming_tma_kernel_with_fronts_alive(S, prec, tol):
+    """One launch per step (n = 1 never takes the resident path) on a two-strip grid while several marginal-
+    regeneration fronts are alive, wrapped ones included: exercises the TFE instantiation of k_march_tma, whose
+    front membership is a per-row mask ANDed with a per-thread column mask, against the oracle's f64 predicate."""
+    nt, nphi = 48, 2048
+    sim = make_sim(S, nt, nphi, getattr(S, prec), h_ref=0.0)
+    ora = O.OracleDrainage(nt, nphi)
+    f = synthetic_field(nt, nphi)
+    ff = f.astype(np.float32).astype(np.float64) if prec == "PREC_F32" else f
+    sim.upload(ff)
+    ora.data[:] = ff
+    sim.step(1e-3, 6000)
+    ora.step(1e-3, 6000)
+    assert ora.active_tfe_count() >= 3 and sim.fronts() == ora.fronts()
+    view = S.View(mode=S.RGB_LUT, format=S.OUT_RGBA8)
+    touched = np.zeros((nt, nphi), bool)
+    for i in range(40):
+        sim.upload(ora.data)  # judge every step on its own
+        before = ora.data.copy()
+        if i % 2:
+            sim.step(1e-3, 1)
+        else:
+            sim.step_fused(1e-3, view, 1)
+        ora.step(1e-3, 1)
+        got = sim.download()[0]
+        assert np.abs(got / ora.data - 1).max() <= tol, i
+        assert sim.fronts() == ora.fronts()
+        # cells a front thinned this step: (1 - 0.5 (1 - ratio) dt) = 0.999925, far outside the drainage increment
+        touched |= (ora.data / before) < 0.99995
+    assert touched.any() and not touched.all()
+    cols = np.nonzero(touched.any(axis=0))[0]
+    assert cols.min() < 64 or cols.max() > nphi - 64 or len(cols) > nphi // 8  # fronts are wide (0.3-0.7 rad)
+
+
 def test_critical_cells_are_skipped_and_clamped(S):
     nt, nphi = 32, 64
     f = synthetic_field(nt, nphi)

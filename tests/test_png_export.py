@@ -69,6 +69,7 @@ def test_frame_params_default_matches_the_reference_defaults():
 
     p = L.FrameParamsC()
     L.check(L.lib().sbx_frame_params_default(C.byref(p)))
+    assert C.sizeof(L.FrameParamsC) == 80 and L.FrameParamsC.background.offset == 64  # 20 four-byte fields, no padding
     assert (p.width, p.height) == (256, 256)
     assert p.cam_distance == pytest.approx(0.2) and p.cam_yaw == 0.0 and p.cam_pitch == pytest.approx(0.3)
     assert p.cam_fov_rad == pytest.approx(math.radians(45.0))
