@@ -136,6 +136,37 @@ if "tfe" in which:
            f"{sim.active_tfe_count()} fronts alive at t = {sim.current_time():.2f} s")
     sim.close()
 
+if "frame" in which:
+    # The reference's per-frame call sequence around the path (RenderPipeline::update, pipeline.rs:1289-1322):
+    # step, thickness_field().min_thickness(), .max_thickness(), get_thickness(pi/2, 0), has_critical_region().
+    import time
+    for nt, nphi, B, tag in ((8192, 16384, 1, "C3 8192x16384"), (256, 512, 512, "C4 foam 512 x 256x512")):
+        kw = dict(batch=B, batch_h0_m=np.linspace(300e-9, 700e-9, B), h_ref=1.0) if B > 1 else dict(h_ref=0.0)
+        sim = S.DrainageSimulator(S.SimulationConfig.default(), precision=S.PREC_F32, num_theta=nt, num_phi=nphi, **kw)
+        if B == 1:
+            sim.upload(synthetic_field(nt, nphi, dtype=np.float32))
+        sim.set_stream(stream.cuda_stream)
+        view = S.View()
+        dt = min(1e-3, 0.25 * dt_max(nt, nphi))
+        fld = sim.thickness_field()
+
+        def frame():
+            sim.step_fused(dt, view, 1)
+            lo, hi = fld.min_thickness(), fld.max_thickness()
+            mid = sim.get_thickness(math.pi / 2, 0.0)
+            return lo, hi, mid, sim.has_critical_region()
+
+        for _ in range(5):
+            frame()
+        t0 = time.perf_counter()
+        for _ in range(50):
+            frame()
+        ms = (time.perf_counter() - t0) / 50 * 1e3
+        ms_mm = timed(lambda n: [sim.step_fused(dt, view, 1) or sim.minmax() for _ in range(n)], 20) - timed(lambda n: sim.step_fused(dt, view, n), 20)
+        report(f"{tag}: one frame of the reference's update loop (fused step + min + max + get_thickness + has_critical), host wall clock",
+               B * (nt - 2) * nphi, 12, ms, f"min/max pass alone {ms_mm:.4f} ms = {B * nt * nphi * 4 / ms_mm / 1e6:.0f} GB/s; the three reductions share one pass")
+        sim.close()
+
 if "l2ab" in which:  # the other fields-larger-than-L2 cases of the march kernel (A/B of the L2 policy)
     single("C3 f64 fused LUT->RGBA8", 8192, 16384, S.PREC_F64, S.RGB_LUT, 50, 20)
     single("C3 f32 drainage only", 8192, 16384, S.PREC_F32, S.RGB_NONE, 100, 8)

@@ -115,6 +115,8 @@ struct sbx_drainage {
     double *scalar_dev = nullptr;
     double *scalar_host = nullptr;  // pinned
     static constexpr int kMinmaxBlocks = 592;
+    bool mm_valid = false;      // mm_cached holds min / max of the current field (cleared by everything that changes it)
+    double mm_cached[2] = {0.0, 0.0};
 
     // physics (the Rust struct's fields, drainage.rs:219-235)
     double density, gravity, viscosity, diffusion, critical, radius;
@@ -553,6 +555,7 @@ static int32_t halo_exchange(sbx_drainage *h);
 extern "C" int32_t sbx_drainage_upload(sbx_drainage *h, const void *host, int32_t dtype)
 {
     CHECK_H(h);
+    h->mm_valid = false;
     if (!host) return fail(SBX_ERR_INVALID, "host is null");
     if (dtype != SBX_F32 && dtype != SBX_F64) return fail(SBX_ERR_INVALID, "bad dtype %d", dtype);
     int32_t rc;
@@ -1075,6 +1078,7 @@ static int32_t steps_resident_wgsl(sbx_drainage *h, double dt, int nsteps, int *
 static int32_t do_steps(sbx_drainage *h, double dt, int32_t nsteps, const sbx_view *view)
 {
     if (nsteps < 0) return fail(SBX_ERR_INVALID, "nsteps < 0");
+    if (nsteps > 0) h->mm_valid = false;
     int32_t rc = ensure_tables(h);
     if (rc != SBX_OK) return rc;
     RgbArgs rgb;
@@ -1155,6 +1159,7 @@ extern "C" int32_t sbx_drainage_download_rgb(sbx_drainage *h, void *host)
 static int32_t step_host_pipelined(sbx_drainage *h, double dt, const sbx_view *view, const float *host_in,
                                    float *host_out_h, void *host_out_rgb)
 {
+    h->mm_valid = false;
     int32_t rc = ensure_tables(h);
     if (rc != SBX_OK) return rc;
     RgbArgs rgb;
@@ -1285,20 +1290,26 @@ extern "C" int32_t sbx_drainage_get_thickness(sbx_drainage *h, int32_t bubble, d
 extern "C" int32_t sbx_drainage_minmax(sbx_drainage *h, double *min_out, double *max_out)
 {
     CHECK_H(h);
-    const int nb = sbx_drainage::kMinmaxBlocks;
-    double mn = INFINITY, mx = -INFINITY;
-    for (int b = 0; b < h->batch; ++b) {  // owned rows only (ghost rows are skipped)
-        const long long off = (long long)b * h->bubble_stride + h->num_phi;
-        const long long n = (long long)h->rows_local * h->num_phi;
-        if (h->f64) CU(launch_minmax<double>(tbuf<double>(h, h->cur) + off, n, 0.0, h->mm_part, nb, h->stream));
-        else CU(launch_minmax<float>(tbuf<float>(h, h->cur) + off, n, h->b_href[b], h->mm_part, nb, h->stream));
+    // The reference's frame loop asks for min, max and has_critical_region one after the other (pipeline.rs:1298-1312,
+    // three full passes on the CPU); here the first query after the field changed runs ONE pass over the owned rows
+    // of all bubbles and the others reuse it.
+    if (!h->mm_valid) {
+        const int nb = sbx_drainage::kMinmaxBlocks;
+        const long long n = (long long)h->rows_local * h->num_phi;  // owned rows only (ghost rows are skipped)
+        const double *href = h->href_zero || h->f64 ? nullptr : h->href_dev;
+        if (h->f64) CU(launch_minmax<double>(tbuf<double>(h, h->cur), h->batch, h->bubble_stride, h->num_phi, n, href, h->mm_part, nb, h->stream));
+        else CU(launch_minmax<float>(tbuf<float>(h, h->cur), h->batch, h->bubble_stride, h->num_phi, n, href, h->mm_part, nb, h->stream));
         h->launches++;
         CU(cudaMemcpyAsync(h->mm_host, h->mm_part, 2 * nb * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
         CU(cudaStreamSynchronize(h->stream));
+        double mn = INFINITY, mx = -INFINITY;
         for (int i = 0; i < nb; ++i) { mn = fmin(mn, h->mm_host[2 * i]); mx = fmax(mx, h->mm_host[2 * i + 1]); }
+        h->mm_cached[0] = mn;
+        h->mm_cached[1] = mx;
+        h->mm_valid = true;
     }
-    if (min_out) *min_out = mn;
-    if (max_out) *max_out = mx;
+    if (min_out) *min_out = h->mm_cached[0];
+    if (max_out) *max_out = h->mm_cached[1];
     return SBX_OK;
 }
 
@@ -1328,6 +1339,7 @@ extern "C" int32_t sbx_drainage_current_time(sbx_drainage *h, double *out)
 extern "C" int32_t sbx_drainage_reset(sbx_drainage *h, double h0_m)
 {
     CHECK_H(h);
+    h->mm_valid = false;
     std::fill(h->b_h0.begin(), h->b_h0.end(), h0_m);
     if (!h->f64 && !h->href_zero) {
         // offset storage follows the new uniform level, so the reset field is exact (delta == 0)
@@ -1429,7 +1441,10 @@ extern "C" int32_t sbx_drainage_device_ptr(sbx_drainage *h, int32_t kind, void *
 {
     if (!h || !out) return fail(SBX_ERR_INVALID, "null argument");
     switch (kind) {
-    case SBX_PTR_THICKNESS: *out = (char *)h->buf[h->cur] + (size_t)h->num_phi * h->esz; return SBX_OK;
+    case SBX_PTR_THICKNESS:
+        h->mm_valid = false;  // the caller may write through the pointer
+        *out = (char *)h->buf[h->cur] + (size_t)h->num_phi * h->esz;
+        return SBX_OK;
     case SBX_PTR_CONCENTRATION:
         if (!h->wgsl) return fail(SBX_ERR_INVALID, "concentration exists only with SBX_SEM_WGSL");
         *out = h->conc[h->cur] + h->num_phi;

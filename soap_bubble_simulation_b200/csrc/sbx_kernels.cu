@@ -520,15 +520,36 @@ __global__ void k_fill(T *dst, long long n, T v)
         dst[i] = v;
 }
 
-// per-block min/max partials of the owned rows (ThicknessField::min/max_thickness, drainage.rs:180-193)
-template <typename T>
-__global__ void __launch_bounds__(256) k_minmax(const T *buf, long long n, double h_ref, double *part)
+// per-block min/max partials of the owned rows of every bubble (ThicknessField::min/max_thickness,
+// drainage.rs:180-193), one launch for the whole batch.  Work items are (bubble, chunk of kMmChunk packets); the
+// reduction runs in the storage type (exact, NaN ignored like f64::min/max) and the per-bubble storage offset is added
+// once per item -- (double)v + h_ref is monotone in v, so min/max commute with it.
+constexpr int kMmChunk = 4096;  // 16-byte packets per work item
+template <typename T, int VEC>
+__global__ void __launch_bounds__(256) k_minmax(const T *buf, int batch, long long bubble_stride, long long first,
+                                                long long n, const double *href, double *part)
 {
+    const long long nv = n / VEC;  // packets per bubble (VEC == 1: elements)
+    const long long chunks = (nv + kMmChunk - 1) / kMmChunk;
+    const long long items = chunks * batch;
     double mn = DBL_MAX, mx = -DBL_MAX;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
-        const double v = (double)buf[i] + h_ref;
-        mn = fmin(mn, v);
-        mx = fmax(mx, v);
+    for (long long it = blockIdx.x; it < items; it += gridDim.x) {
+        const int b = (int)(it / chunks);
+        const long long c0 = (it - (long long)b * chunks) * kMmChunk;
+        const long long c1 = c0 + kMmChunk < nv ? c0 + kMmChunk : nv;
+        const T *src = buf + (long long)b * bubble_stride + first;
+        T lo = src[c0 * VEC], hi = lo;  // any element of the item: a neutral start for threads that load nothing
+        for (long long i = c0 + threadIdx.x; i < c1; i += blockDim.x) {
+            const Vec<T, VEC> q = ldv<T, VEC>(src + i * VEC);
+#pragma unroll
+            for (int k = 0; k < VEC; ++k) {
+                if constexpr (sizeof(T) == 4) { lo = fminf(lo, q.v[k]); hi = fmaxf(hi, q.v[k]); }
+                else { lo = fmin(lo, q.v[k]); hi = fmax(hi, q.v[k]); }
+            }
+        }
+        const double off = href ? href[b] : 0.0;
+        mn = fmin(mn, (double)lo + off);
+        mx = fmax(mx, (double)hi + off);
     }
     __shared__ double smn[8], smx[8];
 #pragma unroll
@@ -1056,13 +1077,17 @@ template cudaError_t launch_fill<float>(float *, long long, float, cudaStream_t)
 template cudaError_t launch_fill<double>(double *, long long, double, cudaStream_t);
 
 template <typename T>
-cudaError_t launch_minmax(const T *buf, long long n, double h_ref, double *part, int nblocks, cudaStream_t st)
+cudaError_t launch_minmax(const T *buf, int batch, long long bubble_stride, long long first, long long n,
+                          const double *href, double *part, int nblocks, cudaStream_t st)
 {
-    k_minmax<T><<<nblocks, 256, 0, st>>>(buf, n, h_ref, part);
+    constexpr int VEC = 16 / (int)sizeof(T);
+    const bool vec = n % VEC == 0 && first % VEC == 0 && bubble_stride % VEC == 0;
+    if (vec) k_minmax<T, VEC><<<nblocks, 256, 0, st>>>(buf, batch, bubble_stride, first, n, href, part);
+    else k_minmax<T, 1><<<nblocks, 256, 0, st>>>(buf, batch, bubble_stride, first, n, href, part);
     return cudaGetLastError();
 }
-template cudaError_t launch_minmax<float>(const float *, long long, double, double *, int, cudaStream_t);
-template cudaError_t launch_minmax<double>(const double *, long long, double, double *, int, cudaStream_t);
+template cudaError_t launch_minmax<float>(const float *, int, long long, long long, long long, const double *, double *, int, cudaStream_t);
+template cudaError_t launch_minmax<double>(const double *, int, long long, long long, long long, const double *, double *, int, cudaStream_t);
 
 template <typename T>
 cudaError_t launch_sample(const T *buf, long long i00, long long i01, long long i10, long long i11, double tf,

@@ -73,7 +73,8 @@ cudaError_t launch_convert_out(TD *dst, const TS *src, long long n, long long bu
 template <typename T>
 cudaError_t launch_fill(T *dst, long long n, T v, cudaStream_t st);
 template <typename T>
-cudaError_t launch_minmax(const T *buf, long long n, double h_ref, double *part, int nblocks, cudaStream_t st);
+cudaError_t launch_minmax(const T *buf, int batch, long long bubble_stride, long long first, long long n,
+                          const double *href, double *part, int nblocks, cudaStream_t st);
 template <typename T>
 cudaError_t launch_sample(const T *buf, long long i00, long long i01, long long i10, long long i11, double tf,
                           double pf, double h_ref, double *out, cudaStream_t st);

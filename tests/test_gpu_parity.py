@@ -269,6 +269,44 @@ def test_get_thickness_and_minmax_match_oracle(S):
     assert sim.minmax() == (ora.min_thickness(), ora.max_thickness())
 
 
+@pytest.mark.parametrize("prec", ["PREC_F32", "PREC_F64"])
+@pytest.mark.parametrize("nt,nphi,B", [(32, 64, 5), (17, 50, 3), (256, 512, 64), (40, 4100, 1)])
+def test_minmax_one_pass_over_the_batch_and_cache(S, prec, nt, nphi, B):
+    """min/max over all bubbles in one launch (per-bubble storage offsets, ghost rows skipped, ragged widths on the
+    scalar path), and the cached result is dropped by everything that changes the field: the reference's frame loop
+    calls min_thickness, max_thickness and has_critical_region back to back (pipeline.rs:1298-1312)."""
+    rng = np.random.default_rng(nt * 1000 + nphi + B)
+    h0 = np.linspace(300e-9, 700e-9, B)
+    f = h0[:, None, None] * (1.0 + 0.2 * rng.uniform(-1, 1, (B, nt, nphi)))
+    if prec == "PREC_F32":
+        f = f.astype(np.float32).astype(np.float64)
+    kw = dict(batch=B, batch_h0_m=h0) if B > 1 else dict(h_ref=0.0)
+    sim = make_sim(S, nt, nphi, getattr(S, prec), **kw)
+    sim.upload(f)
+    n0 = sim.launch_count()
+    mn, mx = sim.minmax()
+    got = sim.download()
+    assert (mn, mx) == (float(got.min()), float(got.max()))
+    assert abs(mn / f.min() - 1) < 1e-6 and abs(mx / f.max() - 1) < 1e-6
+    launches = sim.launch_count() - n0
+    assert sim.minmax() == (mn, mx) and sim.has_critical_region() is False
+    assert sim.launch_count() - n0 == launches  # the second and third query reused the pass
+    # a step, an upload and a reset each invalidate it
+    sim.step(1e-4, 1)
+    g = sim.download()
+    assert sim.minmax() == (float(g.min()), float(g.max()))
+    f2 = f.copy()
+    f2[B - 1, nt // 2, nphi - 1] = 5e-9  # below the critical thickness, in the last column of the last bubble
+    f2[0, 1, 0] = 2e-6
+    sim.upload(f2)
+    mn2, mx2 = sim.minmax()
+    assert abs(mn2 - 5e-9) < 1e-12 and abs(mx2 - 2e-6) < 1e-12 and sim.has_critical_region() is True
+    sim.reset(450e-9)
+    mn3, mx3 = sim.minmax()
+    assert mn3 == mx3 and abs(mn3 / 450e-9 - 1) < 1e-7
+    sim.close()
+
+
 def test_batched_bubbles_match_independent_oracles(S):
     """foam batch (BASELINE config 4): independent bubbles with their own h0 and radius, no exchange."""
     nt, nphi, B = 32, 64, 5
