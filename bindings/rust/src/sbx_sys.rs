@@ -92,6 +92,7 @@ extern "C" {
     pub fn sbx_drainage_step_fused(h: *mut sbx_drainage, dt: f64, nsteps: i32, view: *const sbx_view) -> i32;
     pub fn sbx_drainage_get_thickness(h: *mut sbx_drainage, bubble: i32, theta: f64, phi: f64, out: *mut f64) -> i32;
     pub fn sbx_drainage_minmax(h: *mut sbx_drainage, min_out: *mut f64, max_out: *mut f64) -> i32;
+    pub fn sbx_drainage_track_minmax(h: *mut sbx_drainage, mode: i32) -> i32;
     pub fn sbx_drainage_has_critical(h: *mut sbx_drainage, out: *mut i32) -> i32;
     pub fn sbx_drainage_critical_thickness(h: *mut sbx_drainage, out: *mut f64) -> i32;
     pub fn sbx_drainage_current_time(h: *mut sbx_drainage, out: *mut f64) -> i32;

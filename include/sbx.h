@@ -195,6 +195,11 @@ int32_t sbx_drainage_get_thickness(sbx_drainage *h, int32_t bubble, double theta
 /* ThicknessField::min_thickness / max_thickness (drainage.rs:180-193), over the owned rows */
 int32_t sbx_drainage_minmax(sbx_drainage *h, double *min_out, double *max_out);
 /* has_critical_region (drainage.rs:565-567) */
+/* min / max as a by-product of the step kernel instead of a pass over the field: 0 = never, 1 = every step the TMA
+ * kernel takes, 2 = automatic (default): switched on once queries follow steps, as in the reference's frame loop
+ * (step, min_thickness, max_thickness, has_critical_region: pipeline.rs:1289-1312), and off again when they stop.
+ * Results are identical either way; no reference equivalent (its folds are separate passes, drainage.rs:180-193). */
+int32_t sbx_drainage_track_minmax(sbx_drainage *h, int32_t mode);
 int32_t sbx_drainage_has_critical(sbx_drainage *h, int32_t *out);
 int32_t sbx_drainage_critical_thickness(sbx_drainage *h, double *out); /* drainage.rs:570-572 */
 int32_t sbx_drainage_current_time(sbx_drainage *h, double *out);       /* drainage.rs:560-562; gpu_drainage.rs:464-466 */

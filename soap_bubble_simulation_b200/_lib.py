@@ -105,6 +105,7 @@ _SIGS = {
     "sbx_drainage_download_rgb": [C.c_void_p, C.c_void_p],
     "sbx_drainage_get_thickness": [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.POINTER(C.c_double)],
     "sbx_drainage_minmax": [C.c_void_p, C.POINTER(C.c_double), C.POINTER(C.c_double)],
+    "sbx_drainage_track_minmax": [C.c_void_p, C.c_int32],
     "sbx_drainage_has_critical": [C.c_void_p, C.POINTER(C.c_int32)],
     "sbx_drainage_critical_thickness": [C.c_void_p, C.POINTER(C.c_double)],
     "sbx_drainage_current_time": [C.c_void_p, C.POINTER(C.c_double)],

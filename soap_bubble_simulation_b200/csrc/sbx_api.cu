@@ -117,6 +117,15 @@ struct sbx_drainage {
     static constexpr int kMinmaxBlocks = 592;
     bool mm_valid = false;      // mm_cached holds min / max of the current field (cleared by everything that changes it)
     double mm_cached[2] = {0.0, 0.0};
+    // min / max as a by-product of the TMA step kernel (StepArgs::mm_cur): two sets of {min, max} ordered words per
+    // bubble; a tracked launch accumulates into one set and re-arms the other
+    void *mm_track[2] = {nullptr, nullptr};
+    void *mm_track_host = nullptr;   // pinned, one set
+    int mm_track_set = 0;            // set the last tracked launch wrote
+    bool mm_kernel_valid = false;    // that set describes the current field
+    int mm_track_mode = 2;           // 0 off, 1 on, 2 auto: on once queries follow steps (SBX_TRACK_MINMAX overrides)
+    bool mm_auto_on = false, stepped_since_mm = false;
+    int mm_auto_hits = 0, mm_auto_misses = 0;
 
     // physics (the Rust struct's fields, drainage.rs:219-235)
     double density, gravity, viscosity, diffusion, critical, radius;
@@ -196,6 +205,9 @@ static void free_all(sbx_drainage *h)
     cudaFree(h->pole_partial);
     cudaFree(h->pole_count);
     cudaFree(h->mm_part);
+    cudaFree(h->mm_track[0]);
+    cudaFree(h->mm_track[1]);
+    if (h->mm_track_host) cudaFreeHost(h->mm_track_host);
     cudaFree(h->scalar_dev);
     cudaFree(h->rgb_buf);
     cudaFree(h->colA);
@@ -455,6 +467,19 @@ extern "C" int32_t sbx_drainage_create(const sbx_drainage_cfg *cfg, int32_t devi
     CU_H(cudaMemsetAsync(h->pole_count, 0, (size_t)h->batch * 2 * sizeof(unsigned long long), h->stream));
     CU_H(cudaMalloc(&h->mm_part, 2 * sbx_drainage::kMinmaxBlocks * sizeof(double)));
     CU_H(cudaHostAlloc(&h->mm_host, 2 * sbx_drainage::kMinmaxBlocks * sizeof(double), cudaHostAllocDefault));
+    {
+        const size_t wb = h->f64 ? 8 : 4, set_bytes = (size_t)h->batch * 2 * wb;
+        CU_H(cudaHostAlloc(&h->mm_track_host, set_bytes, cudaHostAllocDefault));
+        for (int b = 0; b < h->batch; ++b) {  // armed: min = all ones, max = 0
+            if (h->f64) { ((unsigned long long *)h->mm_track_host)[2 * b] = ~0ull; ((unsigned long long *)h->mm_track_host)[2 * b + 1] = 0ull; }
+            else { ((unsigned int *)h->mm_track_host)[2 * b] = ~0u; ((unsigned int *)h->mm_track_host)[2 * b + 1] = 0u; }
+        }
+        for (int i = 0; i < 2; ++i) {
+            CU_H(cudaMalloc(&h->mm_track[i], set_bytes));
+            CU_H(cudaMemcpy(h->mm_track[i], h->mm_track_host, set_bytes, cudaMemcpyHostToDevice));
+        }
+        if (const char *e = getenv("SBX_TRACK_MINMAX")) h->mm_track_mode = atoi(e) != 0 ? 1 : 0;
+    }
     CU_H(cudaMalloc(&h->scalar_dev, 8 * sizeof(double)));
     CU_H(cudaHostAlloc(&h->scalar_host, 8 * sizeof(double), cudaHostAllocDefault));
     CU_H(cudaMalloc(&h->colA, (size_t)h->num_phi * sizeof(float)));
@@ -555,7 +580,7 @@ static int32_t halo_exchange(sbx_drainage *h);
 extern "C" int32_t sbx_drainage_upload(sbx_drainage *h, const void *host, int32_t dtype)
 {
     CHECK_H(h);
-    h->mm_valid = false;
+    h->mm_valid = h->mm_kernel_valid = false;
     if (!host) return fail(SBX_ERR_INVALID, "host is null");
     if (dtype != SBX_F32 && dtype != SBX_F64) return fail(SBX_ERR_INVALID, "bad dtype %d", dtype);
     int32_t rc;
@@ -933,8 +958,18 @@ static int32_t step_cpu_sem(sbx_drainage *h, double dt, const RgbArgs &rgb)
                 pushed = true;
             }
         }
+        const bool want_track = h->mm_track_mode == 1 || (h->mm_track_mode == 2 && h->mm_auto_on);
+        const bool tracked = want_track && h->use_tma && march_tma_supported<T>(a) &&
+                             ((!has_top || a.fold_top) && (!has_bottom || a.fold_bottom));  // the kernel writes every owned row
+        if (tracked) {
+            const int set = 1 - h->mm_track_set;
+            a.mm_cur = h->mm_track[set];
+            a.mm_next = h->mm_track[1 - set];
+            h->mm_track_set = set;
+        }
         CU(launch_step<T>(a, h->batch, ft.count > 0, false, has_top, has_bottom, h->band_rows, h->use_tma, h->stream, &n));
         h->cur = 1 - h->cur;
+        h->mm_kernel_valid = tracked;
         if (pushed) {
             h->launches += n;
             h->time += dt;
@@ -1078,7 +1113,12 @@ static int32_t steps_resident_wgsl(sbx_drainage *h, double dt, int nsteps, int *
 static int32_t do_steps(sbx_drainage *h, double dt, int32_t nsteps, const sbx_view *view)
 {
     if (nsteps < 0) return fail(SBX_ERR_INVALID, "nsteps < 0");
-    if (nsteps > 0) h->mm_valid = false;
+    if (nsteps > 0) {
+        h->mm_valid = h->mm_kernel_valid = false;
+        // auto mode: a caller that asks for min/max after its steps gets them from the kernel; one that stops asking loses it
+        if (h->stepped_since_mm && ++h->mm_auto_misses >= 8) { h->mm_auto_on = false; h->mm_auto_hits = 0; }
+        h->stepped_since_mm = true;
+    }
     int32_t rc = ensure_tables(h);
     if (rc != SBX_OK) return rc;
     RgbArgs rgb;
@@ -1159,7 +1199,7 @@ extern "C" int32_t sbx_drainage_download_rgb(sbx_drainage *h, void *host)
 static int32_t step_host_pipelined(sbx_drainage *h, double dt, const sbx_view *view, const float *host_in,
                                    float *host_out_h, void *host_out_rgb)
 {
-    h->mm_valid = false;
+    h->mm_valid = h->mm_kernel_valid = false;
     int32_t rc = ensure_tables(h);
     if (rc != SBX_OK) return rc;
     RgbArgs rgb;
@@ -1293,6 +1333,34 @@ extern "C" int32_t sbx_drainage_minmax(sbx_drainage *h, double *min_out, double 
     // The reference's frame loop asks for min, max and has_critical_region one after the other (pipeline.rs:1298-1312,
     // three full passes on the CPU); here the first query after the field changed runs ONE pass over the owned rows
     // of all bubbles and the others reuse it.
+    if (!h->mm_valid && h->stepped_since_mm) {
+        h->stepped_since_mm = false;
+        h->mm_auto_misses = 0;
+        if (++h->mm_auto_hits >= 2) h->mm_auto_on = true;
+    }
+    if (!h->mm_valid && h->mm_kernel_valid) {  // the last step kernel left them behind: 16 bytes per bubble to fetch
+        const size_t wb = h->f64 ? 8 : 4, set_bytes = (size_t)h->batch * 2 * wb;
+        CU(cudaMemcpyAsync(h->mm_track_host, h->mm_track[h->mm_track_set], set_bytes, cudaMemcpyDeviceToHost, h->stream));
+        CU(cudaStreamSynchronize(h->stream));
+        double mn = INFINITY, mx = -INFINITY;
+        for (int b = 0; b < h->batch; ++b) {
+            double lo, hi;
+            if (h->f64) {
+                auto dec = [](unsigned long long u) { u = (u >> 63) ? u & 0x7fffffffffffffffull : ~u; double d; memcpy(&d, &u, 8); return d; };
+                lo = dec(((unsigned long long *)h->mm_track_host)[2 * b]);
+                hi = dec(((unsigned long long *)h->mm_track_host)[2 * b + 1]);
+            } else {
+                auto dec = [](unsigned int u) { u = (u >> 31) ? u & 0x7fffffffu : ~u; float f; memcpy(&f, &u, 4); return (double)f; };
+                lo = dec(((unsigned int *)h->mm_track_host)[2 * b]) + h->b_href[b];
+                hi = dec(((unsigned int *)h->mm_track_host)[2 * b + 1]) + h->b_href[b];
+            }
+            mn = fmin(mn, lo);
+            mx = fmax(mx, hi);
+        }
+        h->mm_cached[0] = mn;
+        h->mm_cached[1] = mx;
+        h->mm_valid = true;
+    }
     if (!h->mm_valid) {
         const int nb = sbx_drainage::kMinmaxBlocks;
         const long long n = (long long)h->rows_local * h->num_phi;  // owned rows only (ghost rows are skipped)
@@ -1310,6 +1378,16 @@ extern "C" int32_t sbx_drainage_minmax(sbx_drainage *h, double *min_out, double 
     }
     if (min_out) *min_out = h->mm_cached[0];
     if (max_out) *max_out = h->mm_cached[1];
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_track_minmax(sbx_drainage *h, int32_t mode)
+{
+    if (!h) return fail(SBX_ERR_INVALID, "null handle");
+    if (mode < 0 || mode > 2) return fail(SBX_ERR_INVALID, "mode must be 0 (off), 1 (on) or 2 (auto)");
+    h->mm_track_mode = mode;
+    h->mm_auto_on = false;
+    h->mm_auto_hits = h->mm_auto_misses = 0;
     return SBX_OK;
 }
 
@@ -1339,7 +1417,7 @@ extern "C" int32_t sbx_drainage_current_time(sbx_drainage *h, double *out)
 extern "C" int32_t sbx_drainage_reset(sbx_drainage *h, double h0_m)
 {
     CHECK_H(h);
-    h->mm_valid = false;
+    h->mm_valid = h->mm_kernel_valid = false;
     std::fill(h->b_h0.begin(), h->b_h0.end(), h0_m);
     if (!h->f64 && !h->href_zero) {
         // offset storage follows the new uniform level, so the reset field is exact (delta == 0)
@@ -1442,7 +1520,7 @@ extern "C" int32_t sbx_drainage_device_ptr(sbx_drainage *h, int32_t kind, void *
     if (!h || !out) return fail(SBX_ERR_INVALID, "null argument");
     switch (kind) {
     case SBX_PTR_THICKNESS:
-        h->mm_valid = false;  // the caller may write through the pointer
+        h->mm_valid = h->mm_kernel_valid = false;  // the caller may write through the pointer
         *out = (char *)h->buf[h->cur] + (size_t)h->num_phi * h->esz;
         return SBX_OK;
     case SBX_PTR_CONCENTRATION:

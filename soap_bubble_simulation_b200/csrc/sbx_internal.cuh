@@ -94,6 +94,10 @@ struct StepArgs {
     int l_first, l_last;     // local rows to update, inclusive (global poles excluded)
     int band_rows;           // rows marched by one block
     int l2_keep_edges;       // TMA kernel: L2 evict_last policy on the rows neighbouring bands share (fields larger than L2)
+    // TMA kernel: min / max of the stored values this launch writes, as a by-product (nullptr: off).  Two
+    // order-preserving unsigned words {min, max} per bubble (32-bit for f32 storage, 64-bit for f64), merged with
+    // atomicMin / atomicMax once per CTA; the launch also re-arms the other set for the next step.
+    void *mm_cur, *mm_next;
     long long bubble_stride; // elements per bubble in in/out: (rows_local + 2) * num_phi
     long long rgb_bubble_stride;  // cells per bubble in rgb out: rows_local * num_phi
     T dt, crit, coefA;       // coefA = D / (R^2 dtheta^2)

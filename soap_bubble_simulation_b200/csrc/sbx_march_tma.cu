@@ -64,6 +64,23 @@ template <typename T> __device__ __forceinline__ T tmax(T a, T b);
 template <> __device__ __forceinline__ float tmax<float>(float a, float b) { return fmaxf(a, b); }
 template <> __device__ __forceinline__ double tmax<double>(double a, double b) { return fmax(a, b); }
 
+// order-preserving map of a floating-point value onto an unsigned word (for atomicMin / atomicMax)
+__device__ __forceinline__ unsigned int ordered_bits(float v)
+{
+    const unsigned int b = __float_as_uint(v);
+    return (b & 0x80000000u) ? ~b : b | 0x80000000u;
+}
+__device__ __forceinline__ unsigned long long ordered_bits(double v)
+{
+    const unsigned long long b = (unsigned long long)__double_as_longlong(v);
+    return (b >> 63) ? ~b : b | 0x8000000000000000ull;
+}
+template <typename T> struct OrderedWord { using type = unsigned int; };
+template <> struct OrderedWord<double> { using type = unsigned long long; };
+template <typename T> __device__ __forceinline__ T tmin(T a, T b);
+template <> __device__ __forceinline__ float tmin<float>(float a, float b) { return fminf(a, b); }
+template <> __device__ __forceinline__ double tmin<double>(double a, double b) { return fmin(a, b); }
+
 template <typename T> struct MinBlocks { static constexpr int value = 4; };
 template <> struct MinBlocks<double> { static constexpr int value = 3; };
 
@@ -258,6 +275,20 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
     const bool has_ring = (grow <= ring_top && ring_top <= a.row_begin + l1 - 1) ||
                           (grow <= ring_bot && ring_bot <= a.row_begin + l1 - 1);  // block-uniform
 
+    // min / max by-product (a.mm_cur != nullptr): running extremes of what this thread stores, NaN ignored like f64::min/max
+#ifdef SBX_NO_MM_TRACK  // A/B builds: the kernel without the by-product code
+    constexpr bool track = false;
+#else
+    const bool track = a.mm_cur != nullptr;
+#endif
+    T run_lo = (T)INFINITY, run_hi = (T)-INFINITY;
+    if (track && blockIdx.x == 0 && blockIdx.y == 0 && tid == 0) {  // re-arm the other set for the next step
+        using U = typename OrderedWord<T>::type;
+        U *nx = static_cast<U *>(a.mm_next) + 2 * b;
+        nx[0] = ~(U)0;
+        nx[1] = (U)0;
+    }
+
     auto compute_row = [&](const RowT &up, const RowT &cur, const RowT &dn) {
         T cApB, cAmB, cE, cG;  // {A+B, A-B, E, G}
         if constexpr (VEC == 4) {
@@ -318,6 +349,10 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
             ++rm_p;
         }
         if (active) {
+            if (track) {
+#pragma unroll
+                for (int k = 0; k < VEC; ++k) { run_lo = tmin<T>(run_lo, nw.v[k]); run_hi = tmax<T>(run_hi, nw.v[k]); }
+            }
             stv<T, VEC>(out_p, nw);
             if (a.peer.enabled) {  // boundary rows also land in the neighbours' ghost rows (peer stores over NVLink)
                 if constexpr (sizeof(T) == 4) {
@@ -396,6 +431,10 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
                     for (int k = 0; k < VEC; ++k)
                         if (m & (0xffu << (8 * k))) pv.v[k] = fma(-(pv.v[k] + href), a.tfe_rdt, pv.v[k]);
                 }
+                if (track) {
+#pragma unroll
+                    for (int k = 0; k < VEC; ++k) { run_lo = tmin<T>(run_lo, pv.v[k]); run_hi = tmax<T>(run_hi, pv.v[k]); }
+                }
                 stv<T, VEC>(out + (long long)pl * N + jc, pv);
                 if constexpr (MODE != SBX_RGB_NONE) {
                     const float2 sc = __ldg(a.rowSC + prow);
@@ -407,6 +446,26 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
                     store_px(reinterpret_cast<uint32_t *>(a.rgb.out) + (long long)b * a.rgb_bubble_stride +
                                  (long long)(pl - 1) * N + jc, px);
                 }
+            }
+        }
+    }
+
+    if (track) {  // one atomicMin / atomicMax per CTA
+        using U = typename OrderedWord<T>::type;
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            run_lo = tmin<T>(run_lo, __shfl_down_sync(0xffffffffu, run_lo, o));
+            run_hi = tmax<T>(run_hi, __shfl_down_sync(0xffffffffu, run_hi, o));
+        }
+        __shared__ T s_lo[8], s_hi[8];
+        if (lane == 0) { s_lo[tid >> 5] = run_lo; s_hi[tid >> 5] = run_hi; }
+        bar_consumers(C);
+        if (tid == 0) {
+            for (int i = 1; i < nwarps_c; ++i) { run_lo = tmin<T>(run_lo, s_lo[i]); run_hi = tmax<T>(run_hi, s_hi[i]); }
+            U *slot = static_cast<U *>(a.mm_cur) + 2 * b;
+            if (run_lo <= run_hi) {  // at least one finite-or-infinite value was seen
+                atomicMin(slot, ordered_bits(run_lo));
+                atomicMax(slot + 1, ordered_bits(run_hi));
             }
         }
     }

@@ -174,6 +174,10 @@ class _DeviceField:
         L.check(L.lib().sbx_drainage_minmax(self._h, C.byref(mn), C.byref(mx)))
         return mn.value, mx.value
 
+    def track_minmax(self, mode: int) -> None:
+        """0 off, 1 on, 2 auto (default): min/max as a by-product of the step kernel instead of a pass over the field."""
+        L.check(L.lib().sbx_drainage_track_minmax(self._h, int(mode)))
+
     def sync(self) -> None:
         L.check(L.lib().sbx_drainage_sync(self._h))
 

@@ -307,6 +307,74 @@ def test_minmax_one_pass_over_the_batch_and_cache(S, prec, nt, nphi, B):
     sim.close()
 
 
+@pytest.mark.parametrize("prec", ["PREC_F32", "PREC_F64"])
+@pytest.mark.parametrize("nt,nphi,B,offset", [(64, 256, 1, False), (48, 2048, 1, False), (32, 128, 7, True), (256, 512, 16, True)])
+def test_minmax_from_the_step_kernel_equals_the_pass(S, prec, nt, nphi, B, offset):
+    """min/max as a by-product of k_march_tma (ordered-word atomics, pole rows and TFE-thinned cells included) must be
+    exactly what a pass over the downloaded field gives -- forced on, in automatic mode (switches on after two
+    step+query rounds), with fronts alive, and for one launch per step as well as the last step of a multi-step call."""
+    rng = np.random.default_rng(nt + nphi + B)
+    h0 = np.linspace(300e-9, 700e-9, B)
+    f = h0[:, None, None] * (1.0 + 0.2 * rng.uniform(-1, 1, (B, nt, nphi)))
+    if prec == "PREC_F32":
+        f = f.astype(np.float32).astype(np.float64)
+    kw = dict(batch=B, batch_h0_m=h0) if offset else dict(h_ref=0.0, batch=B)
+    view = S.View(mode=S.RGB_LUT, format=S.OUT_RGBA8)
+
+    def check(sim, what):
+        g = sim.download()
+        assert sim.minmax() == (float(g.min()), float(g.max())), what
+
+    for mode in (1, 2):
+        sim = make_sim(S, nt, nphi, getattr(S, prec), **kw)
+        sim.track_minmax(mode)
+        sim.upload(f)
+        for i in range(6):
+            n0 = sim.launch_count()
+            if i % 2:
+                sim.step(1e-4, 1)
+            else:
+                sim.step_fused(1e-4, view, 1)
+            n1 = sim.launch_count()
+            check(sim, (mode, i))
+            assert n1 - n0 >= 1
+        sim.step(1e-4, 3)          # multi-step call: the last step's by-product (or a pass, on the resident path)
+        check(sim, (mode, "multi"))
+        sim.step(1e-3, 700)        # past t = 0.5 s: fronts alive
+        sim.step_fused(1e-3, view, 1)
+        assert sim.active_tfe_count() >= 1
+        check(sim, (mode, "fronts"))
+        f2 = f.copy()
+        f2[B - 1, 0, :] = 900e-9   # a pole row above everything: the pole mean of the next step comes from ring 1 instead
+        f2[0, nt // 2, 3] = 50e-9
+        sim.upload(f2)
+        check(sim, (mode, "upload"))
+        sim.step_fused(1e-4, view, 1)
+        check(sim, (mode, "after upload"))
+        sim.close()
+
+
+def test_minmax_tracking_switches_itself_on_and_off(S):
+    """Automatic mode: the third step+query round no longer needs a pass (one launch per step, none per query); eight
+    steps without a query switch it off again."""
+    sim = make_sim(S, 64, 256, S.PREC_F32, h_ref=0.0)
+    sim.upload(synthetic_field(64, 256))
+    per_round = []
+    for _ in range(5):
+        n0 = sim.launch_count()
+        sim.step(1e-4, 1)
+        sim.minmax()
+        sim.has_critical_region()
+        per_round.append(sim.launch_count() - n0)
+    assert per_round[0] >= 2 and per_round[-1] == 1, per_round
+    for _ in range(10):
+        sim.step(1e-4, 1)
+    n0 = sim.launch_count()
+    sim.minmax()
+    assert sim.launch_count() - n0 == 1  # a pass again
+    sim.close()
+
+
 def test_batched_bubbles_match_independent_oracles(S):
     """foam batch (BASELINE config 4): independent bubbles with their own h0 and radius, no exchange."""
     nt, nphi, B = 32, 64, 5
