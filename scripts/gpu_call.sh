@@ -1,6 +1,5 @@
 #!/bin/bash
 set -u
 O=gpurun_out; mkdir -p $O
-echo "== minmax tests"; timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -k "minmax or critical or api" 2>&1 | tail -6
-echo "== frame loop"; timeout 300 python scripts/measure_configs.py frame 2>&1 | grep "^{\|Error\|error" | tee $O/configs_frame.txt
-echo "== full gpu suite"; timeout 600 python -m pytest tests -m gpu -q 2>&1 | tail -6 | tee $O/pytest_gpu.txt
+echo "== A/B kernel with/without by-product code (tracking off)"; scripts/ab_variants.sh "hl" base nomm 2>&1 | tee $O/ab_mm_track_codegen.txt
+echo "== frame loop, tracking off / on"; scripts/ab_env.sh SBX_TRACK_MINMAX "0 1" "frame" 2>&1 | tee $O/ab_mm_track_frame.txt
