@@ -1,5 +1,9 @@
 #!/bin/bash
 set -u
-O=gpurun_out; mkdir -p $O
-echo "== A/B kernel with/without by-product code (tracking off)"; scripts/ab_variants.sh "hl" base nomm 2>&1 | tee $O/ab_mm_track_codegen.txt
-echo "== frame loop, tracking off / on"; scripts/ab_env.sh SBX_TRACK_MINMAX "0 1" "frame" 2>&1 | tee $O/ab_mm_track_frame.txt
+OUT=gpurun_out; mkdir -p $OUT; rm -f $OUT/sanitize_summary.txt
+for tool in memcheck synccheck; do
+  timeout 200 compute-sanitizer --tool $tool --launch-timeout 120 --error-exitcode 9 \
+      python scripts/sanitize_target.py > $OUT/sanitize_$tool.log 2>&1
+  echo "$tool rc=$?" | tee -a $OUT/sanitize_summary.txt
+  grep -E "ERROR SUMMARY|SANITIZE_TARGET_DONE|========= (Invalid|Barrier|Error)" $OUT/sanitize_$tool.log | head -8 | tee -a $OUT/sanitize_summary.txt
+done

@@ -59,6 +59,20 @@ px = np.empty((1, 1300, 256, 4), np.uint8)
 sim = S.DrainageSimulator(S.SimulationConfig.default(), num_theta=1300, num_phi=256, h_ref=0.0)
 sim.step_host(1e-6, 1, view, synthetic_field(1300, 256, dtype=np.float32)[None].copy(), out, px)
 sim.close()
+# min/max left behind by the step kernel (forced on), batch with per-bubble offsets, fronts alive on the streaming kernel
+sim = S.DrainageSimulator(S.SimulationConfig.default(), num_theta=48, num_phi=1024, batch=3,
+                          batch_h0_m=np.array([300e-9, 500e-9, 700e-9]))
+sim.track_minmax(1)
+sim.step(5e-3, 120)
+for _ in range(3):
+    sim.step_fused(5e-3, view, 1)
+    sim.minmax()
+    sim.has_critical_region()
+assert sim.active_tfe_count() >= 1
+# rows f3/f4: the fragment-shader frame (procedural film and drainage-field film)
+S.HeadlessRenderPipeline.new(96, 64).render_to_buffer()
+S.render_drainage_frame(sim, 64, 64, bubble=2)
+sim.close()
 S.generate_interference_lut(1.33, 1.0)
 S.InterferenceCalculator(1.33).batch(np.linspace(0, 2000, 100), np.linspace(0, 1, 100))
 print("SANITIZE_TARGET_DONE")
