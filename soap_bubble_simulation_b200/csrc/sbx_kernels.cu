@@ -108,6 +108,11 @@ __global__ void __launch_bounds__(256) k_march(const StepArgs<T> a)
         for (int k = 0; k < VEC; ++k) colA[k] = __ldg(a.rgb.colA + jc + k);
     }
     const float Rv = bp.radius;
+    unsigned colmask = 0;  // byte k: fronts whose phi interval covers column jc + k (does not depend on the row)
+    if constexpr (TFE) {
+#pragma unroll
+        for (int k = 0; k < VEC; ++k) colmask |= front_col_mask(a.fronts, jc + k) << (8 * k);
+    }
 
     Vec<T, VEC> up = ldv<T, VEC>(in + (long long)(l0 - 1) * N + jc);
     Vec<T, VEC> cur = ldv<T, VEC>(in + (long long)l0 * N + jc);
@@ -171,9 +176,10 @@ __global__ void __launch_bounds__(256) k_march(const StepArgs<T> a)
         if constexpr (TFE) {
             const unsigned rm = front_row_mask(a.fronts, grow);
             if (rm) {
+                const unsigned m = (rm * 0x01010101u) & colmask;  // row mask x column mask, as in k_march_tma
 #pragma unroll
                 for (int k = 0; k < VEC; ++k) {
-                    if (front_hit(a.fronts, rm, jc + k)) {
+                    if (m & (0xffu << (8 * k))) {
                         if constexpr (STRICT) nw.v[k] = (T)__dmul_rn((double)nw.v[k], a.s_tfe_factor);
                         else nw.v[k] = fma(-(nw.v[k] + href), a.tfe_rdt, nw.v[k]);  // h *= 1 - r dt, drainage.rs:453-455
                     }

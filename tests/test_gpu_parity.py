@@ -172,11 +172,12 @@ def test_f32_with_tfe_fronts_long_run(S):
 
 
 @pytest.mark.parametrize("prec,tol", [("PREC_F32", 1e-5), ("PREC_F64", 1e-12)])
-def test_streaming_tma_kernel_with_fronts_alive(S, prec, tol):
-    """One launch per step (n = 1 never takes the resident path) on a two-strip grid while several marginal-
-    regeneration fronts are alive, wrapped ones included: exercises the TFE instantiation of k_march_tma, whose
-    front membership is a per-row mask ANDed with a per-thread column mask, against the oracle's f64 predicate."""
-    nt, nphi = 48, 2048
+@pytest.mark.parametrize("nt,nphi", [(48, 2048), (48, 2050), (40, 100)])
+def test_streaming_kernels_with_fronts_alive(S, prec, tol, nt, nphi):
+    """One launch per step (n = 1 never takes the resident path) while several marginal-regeneration fronts are alive,
+    wrapped ones included: exercises the TFE instantiation of k_march_tma (two strips of 1024 columns) and of the
+    direct-load k_march (ragged width 2050: one column per thread; 100 columns: too narrow for the ring), whose front
+    membership is a per-row mask ANDed with a per-thread column mask, against the oracle's f64 predicate."""
     sim = make_sim(S, nt, nphi, getattr(S, prec), h_ref=0.0)
     ora = O.OracleDrainage(nt, nphi)
     f = synthetic_field(nt, nphi)
@@ -203,7 +204,7 @@ def test_streaming_tma_kernel_with_fronts_alive(S, prec, tol):
         touched |= (ora.data / before) < 0.99995
     assert touched.any() and not touched.all()
     cols = np.nonzero(touched.any(axis=0))[0]
-    assert cols.min() < 64 or cols.max() > nphi - 64 or len(cols) > nphi // 8  # fronts are wide (0.3-0.7 rad)
+    assert len(cols) > nphi // 16  # fronts are 0.3-0.7 rad wide
 
 
 def test_critical_cells_are_skipped_and_clamped(S):
