@@ -15,8 +15,10 @@ fn main() {
         .flag("-std=c++17")
         .flag("-O3")
         .flag("-lineinfo")
-        .files(["sbx_kernels.cu", "sbx_march_tma.cu", "sbx_wgsl_tma.cu", "sbx_api.cu", "sbx_comm.cu"].iter().map(|f| csrc.join(f)))
+        .files(["sbx_kernels.cu", "sbx_march_tma.cu", "sbx_wgsl_tma.cu", "sbx_shade_tma.cu", "sbx_resident.cu", "sbx_frame.cu",
+                "sbx_api.cu", "sbx_comm.cu"].iter().map(|f| csrc.join(f)))  // SRCS of csrc/Makefile
         .compile("sbx");
     println!("cargo:rustc-link-lib=cudart");
     println!("cargo:rustc-link-lib=dl");
+    println!("cargo:rustc-link-lib=z");  // sbx_export_frame_png
 }

@@ -102,3 +102,12 @@ def test_rgb_color_and_camera_host_helpers():
     assert S.RgbColor.new(1.0, 0.5, 0.0).to_u8_tuple() == (255, 128, 0)  # interference.rs:627-633
     x, y, z = S.camera_position(0.2, 0.0, 0.3)  # camera.rs:49-68
     assert abs(x) < 1e-12 and abs(y - 0.0591040) < 1e-6 and abs(z - 0.1910673) < 1e-6
+
+
+def test_rust_build_script_lists_every_source_of_the_makefile():
+    """bindings/rust/build.rs (source only) must compile the same .cu files csrc/Makefile links into libsbx.so."""
+    with open(os.path.join(ROOT, "soap_bubble_simulation_b200", "csrc", "Makefile")) as f:
+        srcs = re.search(r"^SRCS\s*:=\s*(.+)$", f.read(), flags=re.M).group(1).split()
+    with open(os.path.join(ROOT, "bindings", "rust", "build.rs")) as f:
+        rs = f.read()
+    assert srcs and all(f'"{s}"' in rs for s in srcs), [s for s in srcs if f'"{s}"' not in rs]
