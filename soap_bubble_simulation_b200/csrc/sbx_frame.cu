@@ -14,11 +14,9 @@
 
 namespace sbx {
 
-
 namespace {
 
 struct F3 { float x, y, z; };
-struct F4 { float x, y, z, w; };
 
 __device__ __forceinline__ float dot3(F3 a, F3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
 __device__ __forceinline__ float stepf(float edge, float x) { return x >= edge ? 1.0f : 0.0f; }
