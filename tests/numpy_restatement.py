@@ -1,0 +1,181 @@
+"""A SECOND, independent restatement of the reference's CPU drainage path, written in numpy straight from the Rust
+source (src/physics/drainage.rs) without looking at oracle/sbx_oracle.c.  It exists only to cross-check the C oracle:
+two transcriptions made separately must agree bit for bit (both are plain IEEE f64, no FMA contraction, glibc libm for
+the per-row sin/cos and the TFE pseudo-random numbers).  TEST INFRASTRUCTURE ONLY.
+
+Vectorised over phi; the operation order inside a cell follows the Rust expressions token for token."""
+import math
+
+import numpy as np
+
+PI = math.pi
+FRAC_PI_2 = math.pi / 2.0
+
+
+class TfeFront:  # drainage.rs:23-88
+    def __init__(self, phi_center, width, velocity):
+        self.phi_center, self.extent, self.width, self.velocity = phi_center, 0.0, width, velocity
+
+    def advance(self, dt):  # :47-49
+        self.extent = min(self.extent + self.velocity * dt, FRAC_PI_2)
+
+    def contains_row(self, theta, phi):  # :55-71, for one theta and an array of phi
+        if abs(theta - FRAC_PI_2) > self.extent:
+            return np.zeros(phi.shape, bool)
+        phi_diff = np.abs(phi - self.phi_center)
+        phi_diff = np.where(phi_diff > PI, 2.0 * PI - phi_diff, phi_diff)
+        return phi_diff < self.width / 2.0
+
+    def theta_range(self):  # :76-79
+        return FRAC_PI_2 - self.extent, FRAC_PI_2 + self.extent
+
+
+class NumpyDrainage:
+    """DrainageSimulator (drainage.rs:212-614) with config/default.json's physical parameters."""
+
+    def __init__(self, num_theta, num_phi, h0=500.0 * 1e-9, density=1000.0, gravity=9.81, viscosity=0.001,
+                 diffusion=1e-9, critical=10.0 * 1e-9, radius=0.05 / 2.0):
+        # defaults as DrainageSimulator::new derives them (drainage.rs:266-279): film_thickness_nm * 1e-9,
+        # critical_thickness_nm * 1e-9, diameter / 2 -- 500.0 * 1e-9 is one ulp away from the literal 500e-9
+        self.nt, self.nphi = num_theta, num_phi
+        self.delta_theta = PI / (num_theta - 1)        # :123
+        self.delta_phi = 2.0 * PI / num_phi            # :124
+        self.h = np.full((num_theta, num_phi), h0, np.float64)
+        self.density, self.gravity, self.viscosity = density, gravity, viscosity
+        self.diffusion, self.critical, self.radius = diffusion, critical, radius
+        self.time = 0.0
+        self.fronts = []
+        self.ratio, self.next_spawn, self.spawn_interval, self.tfe = 0.85, 0.5, 2.0, True  # :280-286
+
+    def step(self, dt):  # :298-392
+        nt, nphi, dth, dph = self.nt, self.nphi, self.delta_theta, self.delta_phi
+        drainage_coefficient = self.density * self.gravity / (3.0 * self.viscosity)
+        scratch = self.h.copy()
+        for i in range(1, nt - 1):
+            theta = i * dth                                # theta_at, :143-145
+            sin_theta, cos_theta = math.sin(theta), math.cos(theta)
+            sin_safe = math.copysign(1e-10, sin_theta) if abs(sin_theta) < 1e-10 else sin_theta
+            cur = scratch[i]
+            tm, tp = scratch[i - 1], scratch[i + 1]
+            pm, pp = np.roll(cur, 1), np.roll(cur, -1)     # (phi + n - 1) % n, (phi + 1) % n
+            cubed = cur * cur * cur
+            drainage_term = -drainage_coefficient * cubed * sin_theta
+            radius_squared = self.radius * self.radius
+            d2h_dtheta2 = (tp - 2.0 * cur + tm) / (dth * dth)
+            dh_dtheta = (tp - tm) / (2.0 * dth)
+            d2h_dphi2 = (pp - 2.0 * cur + pm) / (dph * dph)
+            laplacian = (d2h_dtheta2 + cos_theta / sin_safe * dh_dtheta + d2h_dphi2 / (sin_safe * sin_safe)) / radius_squared
+            dh_dt = drainage_term + self.diffusion * laplacian
+            new = np.fmax(cur + dt * dh_dt, 0.0)           # f64::max: a NaN operand yields the other one
+            self.h[i] = np.where(cur < self.critical, cur, new)   # `continue` leaves the cell as it was
+        self._update_poles()
+        if self.tfe:
+            self._marginal_regeneration(dt)
+        self.time += dt
+
+    def _update_poles(self):  # :480-503, sequential left-to-right sums
+        n = self.nphi
+        self.h[0, :] = np.cumsum(self.h[1])[-1] / float(n)
+        self.h[-1, :] = np.cumsum(self.h[-2])[-1] / float(n)
+
+    def _spawn(self):  # :464-477
+        t = self.time
+        phi = abs(math.sin(t * 7.89 + 1.23)) * 2.0 * PI
+        width = 0.3 + abs(math.sin(t * 3.21)) * 0.4
+        velocity = 0.05 + abs(math.cos(t * 5.67)) * 0.05
+        self.fronts.append(TfeFront(phi, width, velocity))
+        if len(self.fronts) > 8:
+            self.fronts.pop(0)
+
+    def _marginal_regeneration(self, dt):  # :395-461
+        self.next_spawn -= dt
+        if self.next_spawn <= 0.0:
+            self._spawn()
+            self.next_spawn = self.spawn_interval * (0.5 + abs(math.sin(self.time * 12.345)))
+        for f in self.fronts:
+            f.advance(dt)
+        self.fronts = [f for f in self.fronts if f.extent < FRAC_PI_2 * 0.95]
+        if not self.fronts:
+            return
+        nt, dth = self.nt, self.delta_theta
+        lo, hi = nt, 0
+        for f in self.fronts:
+            mn, mx = f.theta_range()
+            lo = min(lo, max(0, math.floor(mn / dth)))                 # `as usize` saturates negatives to 0
+            hi = max(hi, min(max(0, math.ceil(mx / dth)), nt - 1))
+        lo = min(lo, nt - 1)
+        phi = np.arange(self.nphi, dtype=np.float64) * self.delta_phi
+        reduction_rate = (1.0 - self.ratio) * 0.5
+        for i in range(lo, hi + 1):
+            theta = i * dth
+            hit = np.zeros(self.nphi, bool)
+            for f in self.fronts:                                       # one front per point: any() is enough
+                hit |= f.contains_row(theta, phi)
+            self.h[i] = np.where(hit, self.h[i] * (1.0 - reduction_rate * dt), self.h[i])
+
+    def get_thickness(self, theta, phi):  # :516-552
+        tc = min(max(theta, 0.0), PI) / self.delta_theta
+        pc = (phi % (2.0 * PI)) / self.delta_phi      # rem_euclid for a positive modulus
+        ti = min(int(math.floor(tc)), self.nt - 2)
+        pj = int(math.floor(pc)) % self.nphi
+        pj_hi = (pj + 1) % self.nphi
+        tf, pf = tc - ti, pc - pj
+        v0 = self.h[ti, pj] * (1.0 - pf) + self.h[ti, pj_hi] * pf
+        v1 = self.h[ti + 1, pj] * (1.0 - pf) + self.h[ti + 1, pj_hi] * pf
+        return v0 * (1.0 - tf) + v1 * tf
+
+
+class PyInterference:
+    """InterferenceCalculator (src/physics/interference.rs:127-447) in scalar Python floats (IEEE f64, glibc libm via
+    the math module), transcribed from the Rust expressions; second entry for the oracle's calculator."""
+
+    def __init__(self, n_film=1.33, wavelengths=(650.0, 532.0, 450.0), n_medium=1.0):  # :26-30, :141-151
+        self.n_film, self.n_medium, self.wl = n_film, n_medium, tuple(wavelengths)
+
+    @staticmethod
+    def _clamp(x, lo, hi):
+        return lo if x < lo else hi if x > hi else x
+
+    def transmission_angle_cos(self, ci):  # :197-211
+        c = self._clamp(ci, -1.0, 1.0)
+        sin_i = math.sqrt(1.0 - c * c)
+        sin_t = (self.n_medium / self.n_film) * sin_i
+        if abs(sin_t) > 1.0:
+            return 0.0
+        return math.sqrt(1.0 - sin_t * sin_t)
+
+    def optical_path_difference(self, d, ct, wl):  # :226-238
+        return 2.0 * self.n_film * d * ct + wl / 2.0
+
+    @staticmethod
+    def phase_difference(opd, wl):  # :248-254
+        return 2.0 * PI * opd / wl
+
+    def fresnel(self, ci):  # :266-298
+        c = self._clamp(ci, -1.0, 1.0)
+        ct = self.transmission_angle_cos(c)
+        n1, n2 = self.n_medium, self.n_film
+        n1ci, n2ct, n2ci, n1ct = n1 * c, n2 * ct, n2 * c, n1 * ct
+        rs = (n1ci - n2ct) / (n1ci + n2ct)
+        rp = (n2ci - n1ct) / (n2ci + n1ct)
+        Rs, Rp = rs * rs, rp * rp
+        return Rs, Rp, (Rs + Rp) / 2.0
+
+    def reflected_intensity(self, d, ci, wl):  # :312-353
+        if d <= 0.0:
+            return 0.0
+        ct = self.transmission_angle_cos(ci)
+        phase = self.phase_difference(self.optical_path_difference(d, ct, wl), wl)
+        R = self.fresnel(ci)[2]
+        cos_phase = math.cos(phase)
+        num = 2.0 * R * (1.0 - cos_phase)
+        den = 1.0 + R * R - 2.0 * R * cos_phase
+        if abs(den) < 2.220446049250313e-16:
+            return R
+        return self._clamp(num / den, 0.0, 1.0)
+
+    def color_linear(self, d, ci):  # :413-426 (RgbColor::new clamps, :52-61)
+        return tuple(self._clamp(self.reflected_intensity(d, ci, w), 0.0, 1.0) for w in self.wl)
+
+    def color(self, d, ci):  # :380-400
+        return tuple(self._clamp(math.pow(self.reflected_intensity(d, ci, w), 1.0 / 2.2), 0.0, 1.0) for w in self.wl)

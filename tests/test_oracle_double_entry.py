@@ -1,0 +1,83 @@
+"""Double-entry check of the drainage oracle: oracle/sbx_oracle.c and tests/numpy_restatement.py were transcribed
+separately from src/physics/drainage.rs and must agree BIT FOR BIT.  The reference holds no golden vectors for drainage
+and cannot be built here, so this is the strongest pin available for that half: a transcription
+slip would have to be made identically twice."""
+import math
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from numpy_restatement import NumpyDrainage
+from synth import synthetic_field
+
+
+def _pair(nt, nphi, field=None):
+    a, b = O.OracleDrainage(nt, nphi), NumpyDrainage(nt, nphi)
+    if field is not None:
+        a.data[:] = field
+        b.h[:] = field
+    return a, b
+
+
+@pytest.mark.parametrize("nt,nphi,steps,dt", [(128, 256, 1000, 1e-3), (33, 50, 1500, 1e-3), (16, 20, 6000, 2e-3)])
+def test_default_config_runs_with_fronts(nt, nphi, steps, dt):
+    """uniform 500 nm start (config/default.json): fronts spawn from t = 0.5 s, several are retired in the long run"""
+    a, b = _pair(nt, nphi)
+    for s in range(steps):
+        a.step(dt, 1)
+        b.step(dt)
+        if s % 250 == 249 or s == steps - 1:
+            assert np.array_equal(a.data, b.h), s
+            assert a.fronts() == [(f.phi_center, f.extent, f.width, f.velocity) for f in b.fronts], s
+    assert a.current_time() == b.time
+    if steps * dt > 0.6:
+        assert len(b.fronts) >= 1
+
+
+def test_noisy_field_critical_cells_and_queries():
+    nt, nphi = 48, 96
+    f = synthetic_field(nt, nphi)
+    f[10:13, 5:9] = 5e-9   # below the critical thickness: skipped
+    f[20, 30] = 0.0
+    f[30, 95] = 3e-6       # a spike at the periodic seam
+    a, b = _pair(nt, nphi, f)
+    for s in range(400):
+        a.step(1e-3, 1)
+        b.step(1e-3)
+    assert np.array_equal(a.data, b.h)
+    rng = np.random.default_rng(3)
+    for th, ph in list(zip(rng.uniform(-0.5, 3.6, 50), rng.uniform(-7, 14, 50))) + [(0, 0), (math.pi, 0), (math.pi / 2, 2 * math.pi)]:
+        assert a.get_thickness(th, ph) == b.get_thickness(th, ph)
+
+
+def test_unstable_run_stays_identical_even_through_overflow():
+    """dt far above the stability bound: values blow up to inf / NaN and the max(.., 0) clamp; both must follow the
+    same IEEE path (NaN handling of f64::max included)."""
+    nt, nphi = 24, 64
+    a, b = _pair(nt, nphi, synthetic_field(nt, nphi))
+    with np.errstate(all="ignore"):
+        for s in range(60):
+            a.step(0.5, 1)
+            b.step(0.5)
+    assert np.array_equal(a.data, b.h, equal_nan=True)
+
+
+def test_interference_calculator_double_entry():
+    """The f64 calculator: oracle (C) vs the separate Python transcription, bit for bit, over thickness x angle incl.
+    grazing incidence, zero / negative thickness and out-of-range cosines."""
+    from numpy_restatement import PyInterference
+
+    for n_film, wl in ((1.33, None), (1.45, (700.0, 546.1, 435.8))):
+        ora = O.OracleInterference(n_film, wl)
+        py = PyInterference(n_film, wl or (650.0, 532.0, 450.0))
+        rng = np.random.default_rng(11)
+        ds = list(rng.uniform(0.0, 2000.0, 300)) + [0.0, -5.0, 1e-3, 500.0, 1000.0, 1e5]
+        cs = list(rng.uniform(0.0, 1.0, 300)) + [0.0, 1.0, 1e-9, -0.3, 1.7, 0.5]
+        for d, c in zip(ds, cs):
+            assert ora.transmission_angle_cos(c) == py.transmission_angle_cos(c)
+            assert tuple(ora.fresnel(c)) == py.fresnel(c)
+            for w in py.wl:
+                assert ora.reflected_intensity(d, c, w) == py.reflected_intensity(d, c, w), (d, c, w)
+            assert tuple(ora.color_linear(d, c)) == py.color_linear(d, c)
+            assert tuple(ora.color(d, c)) == py.color(d, c)
