@@ -18,8 +18,8 @@
  *     drainage.rs:616-720, interference.rs:612-792, interference_lut.rs:165-205) and against closed-form
  *     identities derived from the cited formulas.  The reference holds NO golden vectors for the drainage step:
  *     the drainage numbers are "parity unpinned" in the sense of the task statement.  What stands in for a
- *     reference output is a double entry: a second restatement of the drainage simulator and of the f64 calculator,
- *     transcribed separately from the Rust source (tests/numpy_restatement.py), agrees with this file bit for bit
+ *     reference output is a double entry: a second restatement of the drainage simulator, the f64 calculator, the
+ *     WGSL drainage step and the LUT generator, transcribed separately from the Rust source (tests/numpy_restatement.py), agrees with this file bit for bit
  *     (tests/test_oracle_double_entry.py).
  *
  * All citations are file:line relative to the reference repository root.

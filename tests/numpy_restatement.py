@@ -179,3 +179,119 @@ class PyInterference:
 
     def color(self, d, ci):  # :380-400
         return tuple(self._clamp(math.pow(self.reflected_intensity(d, ci, w), 1.0 / 2.2), 0.0, 1.0) for w in self.wl)
+
+
+def wgsl_drainage_step(p, h, c):
+    """drainage.wgsl::drainage_step (src/render/shaders/drainage.wgsl:72-202) in numpy float32, transcribed from the
+    shader text: every intermediate is an f32 array or scalar, so each +, -, *, / rounds once to f32 like the shader's;
+    sin/cos of the row angle come from glibc's sinf/cosf.  `p` is any object with the DrainageParams fields
+    (gpu_drainage.rs:10-44); h, c: (grid_height, grid_width) float32.  Returns (h_out, c_out)."""
+    import ctypes
+
+    f32 = np.float32
+    libm = ctypes.CDLL("libm.so.6")
+    for fn in (libm.sinf, libm.cosf):
+        fn.restype, fn.argtypes = ctypes.c_float, [ctypes.c_float]
+    H, W = int(p.grid_height), int(p.grid_width)
+    h = np.ascontiguousarray(h, f32).reshape(H, W)
+    c = np.ascontiguousarray(c, f32).reshape(H, W)
+    ho, co = h.copy(), c.copy()                      # pole rows and sub-critical cells copy through (:85-89, :108-112)
+    PI32 = f32(3.14159265358979323846)
+    delta_theta = PI32 / f32(H - 1)
+    delta_phi = f32(2.0) * PI32 / f32(W)
+    dt, R = f32(p.dt), f32(p.bubble_radius)
+    drainage_coeff = f32(p.density) * f32(p.gravity) / (f32(3.0) * f32(p.viscosity))
+    radius_squared = R * R
+    mar = int(p.marangoni_enabled) != 0
+    for i in range(1, H - 1):
+        theta = f32(i) * delta_theta
+        sin_theta, cos_theta = f32(libm.sinf(float(theta))), f32(libm.cosf(float(theta)))
+        sin_safe = f32(np.sign(sin_theta)) * f32(0.0001) if abs(sin_theta) < f32(0.0001) else sin_theta
+        hh, cc = h[i], c[i]
+        h_tm, h_tp, h_pm, h_pp = h[i - 1], h[i + 1], np.roll(hh, 1), np.roll(hh, -1)
+        c_tm, c_tp, c_pm, c_pp = c[i - 1], c[i + 1], np.roll(cc, 1), np.roll(cc, -1)
+        h_cubed = hh * hh * hh
+        drainage_term = -drainage_coeff * h_cubed * sin_theta
+        d2h_dtheta2 = (h_tp - f32(2.0) * hh + h_tm) / (delta_theta * delta_theta)
+        dh_dtheta = (h_tp - h_tm) / (f32(2.0) * delta_theta)
+        d2h_dphi2 = (h_pp - f32(2.0) * hh + h_pm) / (delta_phi * delta_phi)
+        h_lap = (d2h_dtheta2 + cos_theta / sin_safe * dh_dtheta + d2h_dphi2 / (sin_safe * sin_safe)) / radius_squared
+        diffusion_term = f32(p.diffusion_coeff) * h_lap
+        marangoni_term = np.zeros(W, f32)
+        dc_dtheta = (c_tp - c_tm) / (f32(2.0) * delta_theta)
+        if mar:
+            dc_dphi = (c_pp - c_pm) / (f32(2.0) * delta_phi)
+            g_t = dc_dtheta / R
+            g_p = dc_dphi / (R * sin_safe)
+            grad_c_mag = np.sqrt(g_t * g_t + g_p * g_p)
+            marangoni_term = f32(p.marangoni_coeff) * (f32(p.gamma_reduction) * grad_c_mag) * hh * hh
+        dh_dt = drainage_term + diffusion_term + marangoni_term
+        new_h = np.fmax(hh + dt * dh_dt, f32(0.0))
+        d2c_dtheta2 = (c_tp - f32(2.0) * cc + c_tm) / (delta_theta * delta_theta)
+        d2c_dphi2 = (c_pp - f32(2.0) * cc + c_pm) / (delta_phi * delta_phi)
+        c_lap = (d2c_dtheta2 + cos_theta / sin_safe * dc_dtheta + d2c_dphi2 / (sin_safe * sin_safe)) / radius_squared
+        dc_dt = f32(p.surfactant_diffusion) * c_lap
+        if mar:
+            dc_dt = dc_dt + f32(0.001) * (h_lap * R * R) * cc
+        new_c = np.clip(cc + dt * dc_dt, f32(0.0), f32(1.0))
+        skip = hh < f32(p.critical_thickness)
+        ho[i] = np.where(skip, hh, new_h)
+        co[i] = np.where(skip, cc, new_c)
+    return ho, co
+
+
+def interference_lut(refractive_index=1.33, intensity=1.0, T=256, A=64, max_nm=2000.0):
+    """generate_interference_lut (src/render/interference_lut.rs:18-163) in numpy float32, vectorised over the thickness
+    axis; transcribed from the Rust text (f32 operations in its order, glibc sinf/expf, `as u8` truncation)."""
+    import ctypes
+
+    f32 = np.float32
+    libm = ctypes.CDLL("libm.so.6")
+    for fn in (libm.sinf, libm.expf):
+        fn.restype, fn.argtypes = ctypes.c_float, [ctypes.c_float]
+    sinf = np.vectorize(lambda x: libm.sinf(float(x)), otypes=[np.float32])
+    PI32 = f32(math.pi)
+    n = f32(refractive_index)
+
+    def gaussian(x, mean, sigma):  # :151-155
+        t = (f32(x) - f32(mean)) / f32(sigma)
+        return f32(libm.expf(float(f32(-0.5) * t * t)))
+
+    def cie(w):  # :136-148
+        x = f32(1.056) * gaussian(w, 599.8, 37.9) + f32(0.362) * gaussian(w, 442.0, 16.0) - f32(0.065) * gaussian(w, 501.1, 20.4)
+        y = f32(0.821) * gaussian(w, 568.8, 46.9) + f32(0.286) * gaussian(w, 530.9, 31.1)
+        z = f32(1.217) * gaussian(w, 437.0, 11.8) + f32(0.681) * gaussian(w, 459.0, 26.0)
+        return max(x, f32(0.0)), max(y, f32(0.0)), max(z, f32(0.0))
+
+    out = np.empty((A, T, 4), np.uint8)
+    thickness = (np.arange(T, dtype=f32) / f32(T - 1)) * f32(max_nm)                    # :25-26
+    for j in range(A):
+        ci = f32(j) / f32(A - 1)                                                          # :27
+        sin_i = np.sqrt(max(f32(1.0) - ci * ci, f32(0.0)))                                # :96-100
+        sin_t = sin_i / n
+        ct = np.sqrt(max(f32(1.0) - sin_t * sin_t, f32(0.0)))
+        n1ci, n2ct, n2ci, n1ct = f32(1.0) * ci, n * ct, n * ci, f32(1.0) * ct             # :103-120
+        r_s = (n1ci - n2ct) / max(n1ci + n2ct, f32(0.0001))
+        r_p = (n2ci - n1ct) / max(n2ci + n1ct, f32(0.0001))
+        R = (r_s * r_s + r_p * r_p) * f32(0.5)
+        optical_path = f32(2.0) * n * thickness * ct                                      # :61
+        one_minus_r = max(f32(1.0) - R, f32(0.001))                                       # :123-133
+        F = f32(4.0) * R / (one_minus_r * one_minus_r)
+        xyz = [np.zeros(T, f32), np.zeros(T, f32), np.zeros(T, f32)]
+        for w in (400.0, 450.0, 500.0, 550.0, 600.0, 650.0, 700.0):                       # :52, :66-78
+            phase = f32(2.0) * PI32 * optical_path / f32(w) + PI32
+            s = sinf(phase * f32(0.5))
+            sin2 = s * s
+            airy = (F * sin2) / np.maximum(f32(1.0) + F * sin2, f32(0.001))
+            cx, cy, cz = cie(w)
+            xyz[0] = xyz[0] + cx * airy
+            xyz[1] = xyz[1] + cy * airy
+            xyz[2] = xyz[2] + cz * airy
+        X, Y, Z = (v / f32(7.0) for v in xyz)                                             # :81-83
+        r = f32(3.2404542) * X - f32(1.5371385) * Y - f32(0.4985314) * Z                  # :158-163
+        g = f32(-0.969_266) * X + f32(1.8760108) * Y + f32(0.0415560) * Z
+        b = f32(0.0556434) * X - f32(0.2040259) * Y + f32(1.0572252) * Z
+        for k, ch in enumerate((r, g, b)):
+            out[j, :, k] = (np.clip(ch * f32(intensity), f32(0.0), f32(1.0)) * f32(255.0)).astype(np.uint8)  # :33-35
+        out[j, :, 3] = 255
+    return out

@@ -81,3 +81,32 @@ def test_interference_calculator_double_entry():
                 assert ora.reflected_intensity(d, c, w) == py.reflected_intensity(d, c, w), (d, c, w)
             assert tuple(ora.color_linear(d, c)) == py.color_linear(d, c)
             assert tuple(ora.color(d, c)) == py.color(d, c)
+
+
+@pytest.mark.parametrize("marangoni", [0, 1])
+@pytest.mark.parametrize("H,W", [(64, 128), (33, 50)])
+def test_wgsl_step_double_entry(H, W, marangoni):
+    """drainage.wgsl::drainage_step: the oracle's f32 restatement vs the separate numpy float32 transcription over 20
+    dispatches of a noisy thickness + concentration pair (sub-critical cells included)."""
+    from numpy_restatement import wgsl_drainage_step
+
+    rng = np.random.default_rng(H * 100 + W + marangoni)
+    h = (synthetic_field(H, W) * (1.0 + 0.05 * rng.uniform(-1, 1, (H, W)))).astype(np.float32)
+    c = (0.5 + 0.3 * rng.uniform(-1, 1, (H, W))).astype(np.float32)
+    h[5:8, 3:6] = 20e-9  # below the GPU path's 30 nm critical thickness
+    p = O.wgsl_params(grid_width=W, grid_height=H, marangoni_enabled=marangoni, dt=1e-3)
+    ha, ca, hb, cb = h, c, h, c
+    for _ in range(20):
+        ha, ca = O.wgsl_step(p, ha, ca)
+        hb, cb = wgsl_drainage_step(p, hb, cb)
+    assert np.array_equal(ha.reshape(H, W), hb) and np.array_equal(ca.reshape(H, W), cb)
+
+
+@pytest.mark.parametrize("n,intensity", [(1.33, 1.0), (1.40, 4.0)])
+def test_interference_lut_double_entry(n, intensity):
+    """generate_interference_lut: every one of the 65,536 bytes, oracle vs the separate numpy float32 transcription."""
+    from numpy_restatement import interference_lut
+
+    a = O.generate_interference_lut(n, intensity).reshape(64, 256, 4)
+    b = interference_lut(n, intensity)
+    assert np.array_equal(a, b), int(np.count_nonzero(a != b))
