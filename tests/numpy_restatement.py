@@ -295,3 +295,41 @@ def interference_lut(refractive_index=1.33, intensity=1.0, T=256, A=64, max_nm=2
             out[j, :, k] = (np.clip(ch * f32(intensity), f32(0.0), f32(1.0)) * f32(255.0)).astype(np.uint8)  # :33-35
         out[j, :, 3] = 255
     return out
+
+
+def caustic_map(p, thickness):
+    """caustics_compute.wgsl::main (src/render/shaders/caustics_compute.wgsl:29-126) in numpy float32 over the whole
+    grid: x = phi wraps, y = theta clamps at the poles; powf from glibc.  `p`: CausticParams fields; returns (H, W) f32."""
+    import ctypes
+
+    f32 = np.float32
+    libm = ctypes.CDLL("libm.so.6")
+    libm.powf.restype, libm.powf.argtypes = ctypes.c_float, [ctypes.c_float, ctypes.c_float]
+    powf = np.vectorize(lambda x, y: libm.powf(float(x), float(y)), otypes=[np.float32])
+    t = np.ascontiguousarray(thickness, f32)
+    H, W = t.shape
+
+    def s(dx, dy):  # sample_thickness(x + dx, y + dy), :29-43
+        rows = np.clip(np.arange(H) + dy, 0, H - 1)
+        return np.roll(t[rows], -dx, axis=1)
+
+    center, left, right, up, down = s(0, 0), s(-1, 0), s(1, 0), s(0, -1), s(0, 1)
+    h = f32(1.0)
+    h2 = h * h
+    gx = (right - left) / (f32(2.0) * h)                                   # :46-51
+    gy = (down - up) / (f32(2.0) * h)
+    laplacian = (left + right + up + down - f32(4.0) * center) / h2        # :54-65
+    d2x = (left + right - f32(2.0) * center) / h2                          # :68-88
+    d2y = (up + down - f32(2.0) * center) / h2
+    ul, ur, dl, dr = s(-1, -1), s(1, -1), s(-1, 1), s(1, 1)
+    dxy = (dr - dl - ur + ul) / (f32(4.0) * h2)
+    hessian_det = d2x * d2y - dxy * dxy
+    curvature_factor = -laplacian * f32(p.focal_length)                    # :91-112
+    focusing = f32(1.0) / np.maximum(np.abs(f32(1.0) - curvature_factor), f32(0.01))
+    branch_factor = np.where(hessian_det < -f32(p.branch_threshold), f32(1.5), f32(1.0))
+    grad_mag = np.sqrt(gx * gx + gy * gy)
+    refraction_factor = f32(1.0) + grad_mag * f32(0.5)
+    intensity = focusing * branch_factor * refraction_factor
+    intensity = powf(intensity, f32(p.caustic_sharpness))
+    intensity = intensity * f32(p.caustic_intensity)
+    return np.clip(intensity, f32(0.0), f32(10.0)).astype(f32)

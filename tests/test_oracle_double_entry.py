@@ -110,3 +110,21 @@ def test_interference_lut_double_entry(n, intensity):
     a = O.generate_interference_lut(n, intensity).reshape(64, 256, 4)
     b = interference_lut(n, intensity)
     assert np.array_equal(a, b), int(np.count_nonzero(a != b))
+
+
+@pytest.mark.parametrize("H,W", [(64, 128), (37, 50)])
+def test_caustic_map_double_entry(H, W):
+    """caustics_compute.wgsl (row f2): oracle vs the separate numpy float32 transcription.  The shader's `length()` and
+    `pow()` have no exact host definition, so this one is compared to 2 ulp instead of bit for bit."""
+    from numpy_restatement import caustic_map
+
+    rng = np.random.default_rng(H + W)
+    # thickness in the unit the consumer sees (the reference feeds metres; variations of 1e-8 would vanish in f32
+    # against focal_length, so scale the noise up to exercise every branch)
+    t = (1.0 + 0.3 * rng.uniform(-1, 1, (H, W))).astype(np.float32)
+    p = O.caustic_params(grid_width=W, grid_height=H)
+    a = O.caustic_map(p, t).reshape(H, W)
+    b = caustic_map(p, t)
+    assert (a > 0).all() and len(np.unique(a)) > 100
+    assert np.abs(a - b).max() <= 2 * np.spacing(np.abs(a).max())
+    assert np.count_nonzero(a != b) <= 0.01 * a.size
