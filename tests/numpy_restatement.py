@@ -333,3 +333,23 @@ def caustic_map(p, thickness):
     intensity = powf(intensity, f32(p.caustic_sharpness))
     intensity = intensity * f32(p.caustic_intensity)
     return np.clip(intensity, f32(0.0), f32(10.0)).astype(f32)
+
+
+def sample_thickness_at_uv(t, uv):
+    """sample_thickness_at_uv / thickness_gradient_uv (branched_flow_compute.wgsl:187-210), generalised from 128 x 64
+    to t.shape: nearest texel by truncation, eps = 0.01 central differences.  Returns (h, grad)."""
+    f32 = np.float32
+    t = np.ascontiguousarray(t, f32)
+    H, W = t.shape
+    uv = np.ascontiguousarray(uv, f32).reshape(-1, 2)
+
+    def at(u, v):
+        x = (np.clip(u, f32(0.0), f32(1.0)) * f32(W - 1)).astype(np.uint32)   # u32() truncates
+        y = (np.clip(v, f32(0.0), f32(1.0)) * f32(H - 1)).astype(np.uint32)
+        return t[y, x]
+
+    u, v = uv[:, 0], uv[:, 1]
+    eps = f32(0.01)
+    gx = (at(u + eps, v) - at(u - eps, v)) / (f32(2.0) * eps)
+    gy = (at(u, v + eps) - at(u, v - eps)) / (f32(2.0) * eps)
+    return at(u, v), np.stack([gx, gy], axis=1)

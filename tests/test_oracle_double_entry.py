@@ -128,3 +128,16 @@ def test_caustic_map_double_entry(H, W):
     assert (a > 0).all() and len(np.unique(a)) > 100
     assert np.abs(a - b).max() <= 2 * np.spacing(np.abs(a).max())
     assert np.count_nonzero(a != b) <= 0.01 * a.size
+
+
+def test_branched_flow_sampling_double_entry():
+    """sample_thickness_at_uv + thickness_gradient_uv (row f2): oracle vs the separate numpy transcription, exact."""
+    from numpy_restatement import sample_thickness_at_uv
+
+    rng = np.random.default_rng(5)
+    for H, W in ((64, 128), (100, 37)):
+        t = synthetic_field(H, W).astype(np.float32)
+        uv = np.concatenate([rng.uniform(-0.2, 1.2, (4000, 2)), [[0, 0], [1, 1], [0.5, 0.5], [0.995, 0.005]]]).astype(np.float32)
+        ha, ga = O.sample_thickness_uv(t, uv)
+        hb, gb = sample_thickness_at_uv(t, uv)
+        assert np.array_equal(ha, hb) and np.array_equal(ga, gb)
