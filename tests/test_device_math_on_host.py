@@ -1,0 +1,173 @@
+"""The product's per-cell drainage arithmetic, compiled for the HOST from the very text the kernels include
+(cell_update / cell_update_strict in csrc/sbx_device.cuh), against the oracle -- a CPU-side guard for the device math:
+the strict form must reproduce the oracle's interior update bit for bit, the fast form to rounding.  Only the
+`__device__` qualifiers and the IEEE intrinsics (__dmul_rn ... = plain IEEE ops under -ffp-contract=off) are shimmed.
+The GPU tests remain the parity tests proper; this one needs no GPU."""
+import ctypes
+import math
+import os
+import re
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as O
+from synth import synthetic_field
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+HARNESS = r"""
+#include <cmath>
+#include <cstddef>
+#define __device__
+#define __forceinline__ inline
+static inline double __dmul_rn(double a, double b) { return a * b; }
+static inline double __dadd_rn(double a, double b) { return a + b; }
+static inline double __dsub_rn(double a, double b) { return a - b; }
+static inline double __ddiv_rn(double a, double b) { return a / b; }
+using std::fma;
+namespace sbx {
+%s
+}
+// one interior pass over a [nt][nphi] field with the coefficient tables the library builds on the host
+// (sbx_api.cu: coefX = {sin, cos/sin_safe, sin_safe^2}; coefS = {G, B, E}; A = D/(R^2 dth^2))
+extern "C" void pass_strict(const double *in, double *out, int nt, int nphi, double rho, double g, double eta,
+                            double D, double R, double crit, double dt)
+{
+    const double PI = 3.14159265358979323846, dth = PI / (nt - 1), dph = 2.0 * PI / nphi;
+    const double coef = rho * g / (3.0 * eta);
+    for (int i = 1; i < nt - 1; ++i) {
+        const double th = i * dth, s = std::sin(th), c = std::cos(th);
+        const double ss = std::fabs(s) < 1e-10 ? std::copysign(1e-10, s) : s;
+        const sbx::StrictRow r{s, c / ss, ss * ss};
+        for (int j = 0; j < nphi; ++j) {
+            const size_t k = (size_t)i * nphi + j;
+            out[k] = sbx::cell_update_strict(in[k], in[k - nphi], in[k + nphi], in[(size_t)i * nphi + (j + nphi - 1) %% nphi],
+                                             in[(size_t)i * nphi + (j + 1) %% nphi], r, coef, dth * dth, 2.0 * dth, dph * dph,
+                                             R * R, D, dt, crit);
+        }
+    }
+}
+template <typename T>
+static void pass_fast_t(const T *in, T *out, int nt, int nphi, double rho, double g, double eta, double D, double R,
+                        double crit, double dt, double href)
+{
+    const double PI = 3.14159265358979323846, dth = PI / (nt - 1), dph = 2.0 * PI / nphi;
+    const double A = D / (R * R * dth * dth);
+    for (int i = 1; i < nt - 1; ++i) {
+        const double th = i * dth, s = std::sin(th), c = std::cos(th);
+        const double ss = std::fabs(s) < 1e-10 ? std::copysign(1e-10, s) : s;
+        const double G = rho * g / (3.0 * eta) * s, B = D * (c / ss) / (R * R * 2.0 * dth), E = D / (R * R * dph * dph * ss * ss);
+        for (int j = 0; j < nphi; ++j) {
+            const size_t k = (size_t)i * nphi + j;
+            out[k] = sbx::cell_update<T>(in[k], in[k - nphi], in[k + nphi], in[(size_t)i * nphi + (j + nphi - 1) %% nphi],
+                                         in[(size_t)i * nphi + (j + 1) %% nphi], (T)G, (T)A, (T)B, (T)E, (T)1, (T)href, (T)dt, (T)crit);
+        }
+    }
+}
+extern "C" void pass_fast_f64(const double *in, double *out, int nt, int nphi, double rho, double g, double eta, double D,
+                              double R, double crit, double dt, double href)
+{ pass_fast_t<double>(in, out, nt, nphi, rho, g, eta, D, R, crit, dt, href); }
+extern "C" void pass_fast_f32(const float *in, float *out, int nt, int nphi, double rho, double g, double eta, double D,
+                              double R, double crit, double dt, double href)
+{ pass_fast_t<float>(in, out, nt, nphi, rho, g, eta, D, R, crit, dt, href); }
+"""
+
+
+@pytest.fixture(scope="module")
+def hostlib(tmp_path_factory):
+    with open(os.path.join(ROOT, "soap_bubble_simulation_b200", "csrc", "sbx_device.cuh")) as f:
+        src = f.read()
+    m = re.search(r"template <typename T>\n__device__ __forceinline__ T cell_update\(.*?\n}\n.*?"
+                  r"__device__ __forceinline__ double cell_update_strict\(.*?\n}\n", src, flags=re.S)
+    assert m, "cell_update / cell_update_strict not found in sbx_device.cuh"
+    d = tmp_path_factory.mktemp("hostmath")
+    cpp = d / "hostmath.cpp"
+    cpp.write_text(HARNESS % m.group(0))
+    so = d / "libhostmath.so"
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-fno-fast-math", "-shared", "-fPIC",
+                           str(cpp), "-o", str(so)])
+    return ctypes.CDLL(str(so))
+
+
+PHYS = (1000.0, 9.81, 0.001, 1e-9, 0.05 / 2.0, 10.0 * 1e-9)  # rho, g, eta, D, R, crit (config/default.json)
+
+
+def _oracle_step(f, dt):
+    nt, nphi = f.shape
+    ora = O.OracleDrainage(nt, nphi)
+    ora.set_marginal_regeneration(False)
+    ora.data[:] = f
+    ora.step(dt, 1)
+    return ora.data.copy()
+
+
+@pytest.mark.parametrize("nt,nphi", [(64, 128), (33, 50)])
+def test_strict_form_is_bit_identical_to_the_oracle(hostlib, nt, nphi):
+    f = synthetic_field(nt, nphi)
+    f[10:12, 5:9] = 5e-9  # sub-critical cells
+    out = f.copy()
+    c = ctypes.c_double
+    hostlib.pass_strict(f.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p), nt, nphi,
+                        *(c(v) for v in PHYS), c(1e-3))
+    ref = _oracle_step(f, 1e-3)
+    assert np.array_equal(out[1:-1], ref[1:-1])
+
+
+@pytest.mark.parametrize("nt,nphi", [(64, 128), (33, 50)])
+def test_fast_form_matches_the_oracle_to_rounding(hostlib, nt, nphi):
+    f = synthetic_field(nt, nphi)
+    f[10:12, 5:9] = 5e-9
+    ref = _oracle_step(f, 1e-3)
+    c = ctypes.c_double
+    out = f.copy()
+    hostlib.pass_fast_f64(f.ctypes.data_as(ctypes.c_void_p), out.ctypes.data_as(ctypes.c_void_p), nt, nphi,
+                          *(c(v) for v in PHYS), c(1e-3), c(0.0))
+    assert np.abs(out[1:-1] / ref[1:-1] - 1).max() <= 1e-13
+    # increments, not just values: the fast form must resolve the per-step change itself
+    inc, inc_ref = out[1:-1] - f[1:-1], ref[1:-1] - f[1:-1]
+    assert np.abs(inc - inc_ref).max() <= 1e-9 * np.abs(inc_ref).max()
+    # f32, plain storage (h_ref = 0) and offset storage (h_ref = 500 nm keeps the sub-ulp increments)
+    f32 = f.astype(np.float32)
+    o32 = f32.copy()
+    hostlib.pass_fast_f32(f32.ctypes.data_as(ctypes.c_void_p), o32.ctypes.data_as(ctypes.c_void_p), nt, nphi,
+                          *(c(v) for v in PHYS), c(1e-3), c(0.0))
+    ref32 = _oracle_step(f32.astype(np.float64), 1e-3)
+    assert np.abs(o32[1:-1].astype(np.float64) / ref32[1:-1] - 1).max() <= 1.2e-7
+    href = 500.0 * 1e-9
+    u = np.full((nt, nphi), href)  # the default configuration: uniform film, increments 8e-10 relative per step
+    d32 = (u - href).astype(np.float32)
+    od = d32.copy()
+    hostlib.pass_fast_f32(d32.ctypes.data_as(ctypes.c_void_p), od.ctypes.data_as(ctypes.c_void_p), nt, nphi,
+                          *(c(v) for v in PHYS), c(1e-3), c(href))
+    refu = _oracle_step(u, 1e-3)
+    inc, inc_ref = od[1:-1].astype(np.float64), refu[1:-1] - href
+    assert np.abs(inc_ref).max() > 0 and np.abs(inc - inc_ref).max() <= 1e-3 * np.abs(inc_ref).max()
+
+
+def test_frame_kernel_noise_matches_the_shader_restatement(tmp_path):
+    """k_bubble_frame's simplex / FBM film thickness (csrc/sbx_frame.cu, from bubble.wgsl:104-229), host-compiled from
+    the kernel's own text, against the numpy restatement the golden-screenshot tests use (tests/golden_render.py)."""
+    import golden_render as G
+
+    with open(os.path.join(ROOT, "soap_bubble_simulation_b200", "csrc", "sbx_frame.cu")) as f:
+        src = f.read()
+    body = src[src.index("struct F3"):src.index("// Thickness of the drainage field")]
+    cpp = tmp_path / "noise.cpp"
+    cpp.write_text("#include <cmath>\n#define __device__\n#define __forceinline__ inline\n"
+                   "struct FrameArgs { float base_nm, film_time, swirl, drainage_speed, pattern_scale; };\n" + body +
+                   'extern "C" void ft(const float *n, int cnt, float base, float t, float *out) {\n'
+                   "  FrameArgs a{base, t, 1.0f, 0.5f, 1.0f};\n"
+                   "  for (int k = 0; k < cnt; ++k) out[k] = film_thickness_procedural(a, F3{n[3 * k], n[3 * k + 1], n[3 * k + 2]});\n}\n")
+    so = tmp_path / "libnoise.so"
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", str(cpp), "-o", str(so)])
+    lib = ctypes.CDLL(str(so))
+    rng = np.random.default_rng(1)
+    n = rng.normal(size=(100000, 3))
+    n = (n / np.linalg.norm(n, axis=1, keepdims=True)).astype(np.float32)
+    for t in (0.0, 3.7):
+        out = np.empty(len(n), np.float32)
+        lib.ft(n.ctypes.data_as(ctypes.c_void_p), len(n), ctypes.c_float(500.0), ctypes.c_float(t), out.ctypes.data_as(ctypes.c_void_p))
+        ref = G.film_thickness(n, 500.0, film_time=t)
+        assert np.abs(out - ref).max() <= 1e-3  # nm; f32 rounding of a ~500 nm value is 3e-5
