@@ -171,3 +171,66 @@ def test_frame_kernel_noise_matches_the_shader_restatement(tmp_path):
         lib.ft(n.ctypes.data_as(ctypes.c_void_p), len(n), ctypes.c_float(500.0), ctypes.c_float(t), out.ctypes.data_as(ctypes.c_void_p))
         ref = G.film_thickness(n, 500.0, film_time=t)
         assert np.abs(out - ref).max() <= 1e-3  # nm; f32 rounding of a ~500 nm value is 3e-5
+
+
+COLOUR_SHIMS = r"""
+#include <cmath>
+#define __device__
+#define __forceinline__ inline
+struct RgbArgs { float n_film, inv_n2, two_n, r0, omr0; double inv_n2_d; double two_n_over_wl[3]; float two_pi_over_wl_f[3]; };
+static inline float clamp01(float x) { return std::fmin(std::fmax(x, 0.f), 1.f); }
+static inline float rcp_approx(float x) { return 1.0f / x; }       // the SFU approximations, exact here: this test
+static inline float sqrt_approx(float x) { return std::sqrt(x); }  // checks the algebra, the GPU tests the hardware
+static inline float ex2_approx(float x) { return std::exp2(x); }
+static inline float lg2_approx(float x) { return std::log2(x); }
+static inline float __saturatef(float x) { return clamp01(x); }
+#define __cosf(x) std::cos((float)(x))  /* glibc declares a __cosf of its own */
+using std::fma; using std::fmaf; using std::fabs; using std::rint; using std::fmaxf; using std::fminf;
+"""
+
+
+def test_colour_stage_algebra_matches_the_oracle(tmp_path):
+    """rgb_exact3 / rgb_two_beam / rgb_schlick_wall (csrc/sbx_device.cuh) host-compiled from the kernel text with exact
+    stand-ins for the SFU approximations: the algebra (f64 fringe phase folded to the nearest zero, 1 - R from the
+    transmittances, Airy, gamma) must agree with InterferenceCalculator (interference.rs:380-426) within the
+    north-star tolerance of 1e-4 -- measured here it is ~1e-6 -- over thickness x angle incl. grazing incidence."""
+    with open(os.path.join(ROOT, "soap_bubble_simulation_b200", "csrc", "sbx_device.cuh")) as f:
+        src = f.read()
+    body = src[src.index("// sin(pi x) for |x| <= 0.5"):src.index("// bubble.wgsl:425-439 through the texture unit")]
+    cpp = tmp_path / "colour.cpp"
+    cpp.write_text(COLOUR_SHIMS + body + r"""
+extern "C" void eval(int mode, double n, const double *d, const float *ci, int cnt, float *out) {
+  RgbArgs a{};
+  a.n_film = (float)n; a.inv_n2 = (float)(1.0 / (n * n)); a.inv_n2_d = 1.0 / (n * n); a.two_n = (float)(2.0 * n);
+  a.r0 = (float)(((n - 1.0) / (n + 1.0)) * ((n - 1.0) / (n + 1.0))); a.omr0 = 1.0f - a.r0;
+  const double wl[3] = {650.0, 532.0, 450.0};
+  for (int k = 0; k < 3; ++k) { a.two_n_over_wl[k] = 2.0 * n / wl[k]; a.two_pi_over_wl_f[k] = (float)(2.0 * 3.14159265358979323846 / wl[k]); }
+  for (int i = 0; i < cnt; ++i) {
+    if (mode == 0) rgb_exact3(d[i], ci[i], a, true, out + 3 * i);
+    else if (mode == 1) rgb_exact3(d[i], ci[i], a, false, out + 3 * i);
+    else if (mode == 2) rgb_schlick_wall(d[i], ci[i], a, out + 3 * i);
+    else rgb_two_beam((float)d[i], ci[i], a, out + 3 * i);
+  }
+}
+""")
+    so = tmp_path / "libcolour.so"
+    subprocess.check_call(["/usr/bin/g++", "-O2", "-std=c++17", "-ffp-contract=off", "-shared", "-fPIC", str(cpp), "-o", str(so)])
+    lib = ctypes.CDLL(str(so))
+    rng = np.random.default_rng(2)
+    d = np.concatenate([rng.uniform(0.0, 2000.0, 20000), [0.0, 500.0, 1000.0, 1e-3]])
+    ci = np.concatenate([rng.uniform(0.0, 1.0, 20000), [1.0, 1.0, 0.0, 0.02]]).astype(np.float32)
+    out = np.empty((len(d), 3), np.float32)
+
+    def run(mode):
+        lib.eval(mode, ctypes.c_double(1.33), d.ctypes.data_as(ctypes.c_void_p), ci.ctypes.data_as(ctypes.c_void_p), len(d),
+                 out.ctypes.data_as(ctypes.c_void_p))
+        return out.astype(np.float64)
+
+    ora = O.OracleInterference(1.33)
+    assert np.abs(run(0) - ora.batch(d, ci.astype(np.float64), gamma=True)).max() <= 1e-4
+    assert np.abs(run(1) - ora.batch(d, ci.astype(np.float64), gamma=False)).max() <= 1e-4
+    sub = np.r_[0:2000, len(d) - 4:len(d)]  # the scalar oracle entry points: a subset
+    wall, two = run(2).copy(), run(3).copy()
+    for i in sub:
+        assert np.abs(wall[i] - np.array(O.schlick_wall_rgb(float(d[i]), float(ci[i])))).max() <= 1e-4, i
+        assert np.abs(two[i] - np.clip(O.schlick_two_beam_rgb(float(d[i]), float(ci[i])), 0.0, 1.0)).max() <= 1e-4, i  # the kernel saturates
