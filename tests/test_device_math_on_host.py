@@ -234,3 +234,28 @@ extern "C" void eval(int mode, double n, const double *d, const float *ci, int c
     for i in sub:
         assert np.abs(wall[i] - np.array(O.schlick_wall_rgb(float(d[i]), float(ci[i])))).max() <= 1e-4, i
         assert np.abs(two[i] - np.clip(O.schlick_two_beam_rgb(float(d[i]), float(ci[i])), 0.0, 1.0)).max() <= 1e-4, i  # the kernel saturates
+
+
+def test_band_height_model_picks_whole_waves(tmp_path):
+    """auto_band_rows (csrc/sbx_launch.h, host code): the band height that fills whole waves of CTAs.  The documented
+    choices -- 56 rows at 8192 x 16384 (16 strips, 592 CTA slots: 3.97 waves), 14 rows at 2048 x 4096 (4 strips: one
+    wave of 588 CTAs), the default for launches of 16 waves or more -- are what DESIGN.md 4.1 / BASELINE.md quote."""
+    cpp = tmp_path / "band.cpp"
+    cpp.write_text('#include "sbx_launch.h"\nextern "C" int band(int rows, long long per_band, int slots, int dflt)\n'
+                   "{ return sbx::auto_band_rows(rows, per_band, slots, dflt); }\n")
+    so = tmp_path / "libband.so"
+    subprocess.check_call(["/usr/bin/g++", "-O1", "-std=c++17", "-shared", "-fPIC", "-I/usr/local/cuda/include",
+                           "-I" + os.path.join(ROOT, "soap_bubble_simulation_b200", "csrc"), str(cpp), "-o", str(so)])
+    lib = ctypes.CDLL(str(so))
+    lib.band.argtypes = [ctypes.c_int, ctypes.c_longlong, ctypes.c_int, ctypes.c_int]
+    slots = 148 * 4
+    b3 = lib.band(8190, 16, slots, 24)
+    assert b3 == 56 and math.ceil(8190 / b3) * 16 <= 4 * slots
+    b2 = lib.band(2046, 4, slots, 24)
+    assert b2 == 14 and math.ceil(2046 / b2) * 4 <= slots
+    assert lib.band(254, 4096, slots, 24) == 24   # foam of 4096 bubbles: far more than 16 waves, default height
+    assert lib.band(10, 1, slots, 24) == 6    # a tiny grid is split into two bands that run side by side
+    assert lib.band(0, 1, slots, 24) == 1
+    for rows, per_band in ((8190, 16), (2046, 4), (1022, 2), (254, 512), (62, 1)):
+        b = lib.band(rows, per_band, slots, 24)
+        assert 1 <= b <= max(rows, 1) and b <= 64
