@@ -211,6 +211,19 @@ int32_t sbx_drainage_set_tfe_ratio(sbx_drainage *h, double ratio);              
 int32_t sbx_drainage_tfe_ratio(sbx_drainage *h, double *out);                     /* drainage.rs:606-608 */
 int32_t sbx_drainage_active_tfe_count(sbx_drainage *h, int32_t *out);             /* drainage.rs:611-613 */
 int32_t sbx_drainage_fronts(sbx_drainage *h, sbx_tfe_front *out8, int32_t *count);
+/* Checkpoint / resume of the host state machine: the fields DrainageSimulator keeps beside the thickness field
+ * (current_time, tfe_fronts, next_tfe_spawn_time; drainage.rs:237-255).  Together with download / upload of the
+ * field this restores a simulator exactly (the reference has no serialisation of its own; a shim would expose
+ * these as plain getters / setters).  set_state rejects count > 8 and non-finite values. */
+typedef struct {
+    double time;       /* current_time */
+    double next_spawn; /* next_tfe_spawn_time */
+    int32_t count;     /* tfe_fronts.len(), <= 8 (drainage.rs:474) */
+    int32_t _pad;
+    sbx_tfe_front fronts[8];
+} sbx_tfe_state;
+int32_t sbx_drainage_get_state(sbx_drainage *h, sbx_tfe_state *out);
+int32_t sbx_drainage_set_state(sbx_drainage *h, const sbx_tfe_state *state);
 
 /* GPUDrainageSimulator setters (gpu_drainage.rs:377-456), SBX_SEM_WGSL only */
 int32_t sbx_drainage_update_params(sbx_drainage *h, const sbx_drainage_params *p); /* :377-380 */
@@ -336,7 +349,9 @@ int32_t sbx_drainage_attach_comm(sbx_drainage *h, sbx_comm *c);
 #define SBX_IPC_BYTES 256
 int32_t sbx_drainage_ipc_export(sbx_drainage *h, uint8_t out[SBX_IPC_BYTES]);
 int32_t sbx_drainage_ipc_attach(sbx_drainage *h, const uint8_t *up, const uint8_t *down);
-/* 0 = ok, 1 = a neighbour wait timed out during some step since the last query */
+/* Device-side wait status since the last query, a bit mask: 0 = ok, bit 0 = a wait for a latitude neighbour's step
+ * flag timed out, bit 1 = a wait for the other strips of a pole ring (the folded pole rows) timed out.  Every
+ * in-kernel spin is bounded, so a lost neighbour or a failed launch shows up here instead of hanging the GPU. */
 int32_t sbx_drainage_peer_status(sbx_drainage *h, int32_t *out);
 /* global min/max over all ranks' bands */
 int32_t sbx_drainage_minmax_global(sbx_drainage *h, double *min_out, double *max_out);

@@ -24,7 +24,10 @@
 /* ================================================================== drainage (f64) */
 
 struct orc_drainage {
-    int num_theta, num_phi;
+    int num_theta, num_phi; /* rows held in h / scratch, columns */
+    /* Window mode (orc_drainage_create_window): h holds global rows [row0, row0 + num_theta) of a sphere with
+     * nt_global rows.  The whole-sphere simulator is the window row0 = 0, num_theta = nt_global. */
+    int nt_global, row0;
     double *h, *scratch;
     double delta_theta, delta_phi;
     double density, gravity, viscosity, diffusion, critical, radius;
@@ -46,6 +49,8 @@ orc_drainage *orc_drainage_create(int num_theta, int num_phi, double h0, double 
     orc_drainage *s = (orc_drainage *)calloc(1, sizeof(*s));
     size_t n = (size_t)num_theta * (size_t)num_phi;
     s->num_theta = num_theta;
+    s->nt_global = num_theta;
+    s->row0 = 0;
     s->num_phi = num_phi;
     s->h = (double *)malloc(n * sizeof(double));
     s->scratch = (double *)malloc(n * sizeof(double));
@@ -66,6 +71,22 @@ orc_drainage *orc_drainage_create(int num_theta, int num_phi, double h0, double 
     s->next_spawn = 0.5;     /* drainage.rs:285 */
     s->spawn_interval = 2.0; /* drainage.rs:286 */
     s->nthreads = 1;
+    return s;
+}
+
+/* A latitude slab of a larger sphere: same simulator, but the field holds only global rows [row0, row0 + rows).
+ * Rows whose theta neighbours lie outside the window keep their values, so after k steps the k rows next to a
+ * cut edge are no longer those of the whole-sphere run; everything further inside is bit-identical to it (a cell
+ * reads its four neighbours only, drainage.rs:336-343).  Pole rows are averaged only when the window holds them. */
+orc_drainage *orc_drainage_create_window(int nt_global, int num_phi, int row0, int rows, double h0, double density,
+                                         double gravity, double viscosity, double diffusion, double critical,
+                                         double radius)
+{
+    if (row0 < 0 || rows < 2 || row0 + rows > nt_global) return NULL;
+    orc_drainage *s = orc_drainage_create(rows, num_phi, h0, density, gravity, viscosity, diffusion, critical, radius);
+    s->nt_global = nt_global;
+    s->row0 = row0;
+    s->delta_theta = M_PI / (double)(nt_global - 1); /* drainage.rs:123 on the global grid */
     return s;
 }
 
@@ -124,7 +145,7 @@ static void marginal_regeneration(orc_drainage *s, double dt)
     s->nfronts = w;
     if (s->nfronts == 0) return;
 
-    const int num_theta = s->num_theta, num_phi = s->num_phi;
+    const int num_theta = s->nt_global, num_phi = s->num_phi;
     const double dth = s->delta_theta, dph = s->delta_phi;
     size_t min_idx = (size_t)num_theta, max_idx = 0;
     for (int k = 0; k < s->nfronts; ++k) { /* drainage.rs:428-434 */
@@ -139,13 +160,15 @@ static void marginal_regeneration(orc_drainage *s, double dt)
     if (min_idx > (size_t)(num_theta - 1)) min_idx = (size_t)(num_theta - 1);
     for (size_t i = min_idx; i <= max_idx; ++i) { /* drainage.rs:440-460 */
         double theta = (double)i * dth;
+        if ((long)i < (long)s->row0 || (long)i >= (long)s->row0 + s->num_theta) continue; /* window mode */
+        const size_t li = i - (size_t)s->row0;
         for (int j = 0; j < num_phi; ++j) {
             double phi = (double)j * dph;
             for (int k = 0; k < s->nfronts; ++k) {
                 if (front_contains(&s->fronts[k], theta, phi)) {
-                    double current = s->h[i * (size_t)num_phi + (size_t)j];
+                    double current = s->h[li * (size_t)num_phi + (size_t)j];
                     double reduction_rate = (1.0 - s->tfe_ratio) * 0.5;
-                    s->h[i * (size_t)num_phi + (size_t)j] = current * (1.0 - reduction_rate * dt);
+                    s->h[li * (size_t)num_phi + (size_t)j] = current * (1.0 - reduction_rate * dt);
                     break;
                 }
             }
@@ -158,14 +181,18 @@ static void update_poles(orc_drainage *s)
 {
     const int num_phi = s->num_phi;
     const size_t last = (size_t)s->num_theta - 1;
-    double top = 0.0;
-    for (int j = 0; j < num_phi; ++j) top += s->h[(size_t)num_phi + (size_t)j];
-    double top_avg = top / (double)num_phi;
-    for (int j = 0; j < num_phi; ++j) s->h[j] = top_avg;
-    double bot = 0.0;
-    for (int j = 0; j < num_phi; ++j) bot += s->h[(last - 1) * (size_t)num_phi + (size_t)j];
-    double bot_avg = bot / (double)num_phi;
-    for (int j = 0; j < num_phi; ++j) s->h[last * (size_t)num_phi + (size_t)j] = bot_avg;
+    if (s->row0 == 0) {
+        double top = 0.0;
+        for (int j = 0; j < num_phi; ++j) top += s->h[(size_t)num_phi + (size_t)j];
+        double top_avg = top / (double)num_phi;
+        for (int j = 0; j < num_phi; ++j) s->h[j] = top_avg;
+    }
+    if (s->row0 + s->num_theta == s->nt_global) {
+        double bot = 0.0;
+        for (int j = 0; j < num_phi; ++j) bot += s->h[(last - 1) * (size_t)num_phi + (size_t)j];
+        double bot_avg = bot / (double)num_phi;
+        for (int j = 0; j < num_phi; ++j) s->h[last * (size_t)num_phi + (size_t)j] = bot_avg;
+    }
 }
 
 /* one interior row, drainage.rs:314-381 */
@@ -175,7 +202,7 @@ static void interior_row(orc_drainage *s, int i, double dt, double drainage_coef
     const double delta_theta = s->delta_theta, delta_phi = s->delta_phi;
     const double *sc = s->scratch;
     double *out = s->h;
-    double theta = (double)i * delta_theta;
+    double theta = (double)(i + s->row0) * delta_theta; /* i is the row inside the window */
     double sin_theta = sin(theta);
     double cos_theta = cos(theta);
     double sin_theta_safe = fabs(sin_theta) < 1e-10 ? copysign(1e-10, sin_theta) : sin_theta;

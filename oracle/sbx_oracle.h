@@ -52,6 +52,12 @@ typedef struct orc_drainage orc_drainage;
 orc_drainage *orc_drainage_create(int num_theta, int num_phi, double h0_m, double density,
                                   double gravity, double viscosity, double diffusion,
                                   double critical_thickness_m, double radius_m);
+/* Window mode: the same simulator holding only global rows [row0, row0 + rows) of a sphere with nt_global rows
+ * (checker for latitude-band sharded runs at sizes the whole-sphere oracle cannot finish in seconds).  After k
+ * steps the k rows next to a cut edge are stale; rows further inside equal the whole-sphere run bit for bit. */
+orc_drainage *orc_drainage_create_window(int nt_global, int num_phi, int row0, int rows, double h0_m,
+                                         double density, double gravity, double viscosity, double diffusion,
+                                         double critical_thickness_m, double radius_m);
 void orc_drainage_destroy(orc_drainage *s);
 
 /* DrainageSimulator::step (src/physics/drainage.rs:298-392).  nthreads > 1 runs the interior

@@ -11,7 +11,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import oracle_lib as O  # noqa: E402
 import soap_bubble_simulation_b200 as S  # noqa: E402
-from synth import dt_max, synthetic_field  # noqa: E402
+from soap_bubble_simulation_b200.synth import dt_max, synthetic_field  # noqa: E402
 
 nt, nphi = 8192, 16384
 trials = int(sys.argv[1]) if len(sys.argv) > 1 else 6

@@ -17,7 +17,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 import soap_bubble_simulation_b200 as S  # noqa: E402
-from synth import dt_max, synthetic_field  # noqa: E402
+from soap_bubble_simulation_b200.synth import dt_max, synthetic_field  # noqa: E402
 
 PEAK = 6532.5
 try:

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import soap_bubble_simulation_b200 as S  # noqa: E402
-from synth import dt_max, synthetic_field  # noqa: E402
+from soap_bubble_simulation_b200.synth import dt_max, synthetic_field  # noqa: E402
 
 mode = getattr(S, sys.argv[1] if len(sys.argv) > 1 else "RGB_EXACT3")
 prec = getattr(S, sys.argv[2] if len(sys.argv) > 2 else "PREC_F32")

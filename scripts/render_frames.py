@@ -10,7 +10,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import soap_bubble_simulation_b200 as S  # noqa: E402
-from synth import synthetic_field  # noqa: E402
+from soap_bubble_simulation_b200.synth import synthetic_field  # noqa: E402
 
 out = sys.argv[1] if len(sys.argv) > 1 else os.path.join(ROOT, "gpurun_out")
 os.makedirs(out, exist_ok=True)

@@ -8,7 +8,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 import soap_bubble_simulation_b200 as S  # noqa: E402
-from synth import dt_max, synthetic_field  # noqa: E402
+from soap_bubble_simulation_b200.synth import dt_max, synthetic_field  # noqa: E402
 
 view = S.View()
 for nt, nphi in ((130, 1028), (64, 2048), (37, 50)):

@@ -82,6 +82,11 @@ class TfeFrontC(C.Structure):
                 ("velocity", C.c_double)]
 
 
+class TfeStateC(C.Structure):
+    _fields_ = [("time", C.c_double), ("next_spawn", C.c_double), ("count", C.c_int32), ("_pad", C.c_int32),
+                ("fronts", TfeFrontC * 8)]
+
+
 _SIGS = {
     # name: (argtypes)   -- every function returns int32 except sbx_last_error
     "sbx_version": [C.POINTER(C.c_int32), C.POINTER(C.c_int32)],
@@ -116,6 +121,8 @@ _SIGS = {
     "sbx_drainage_tfe_ratio": [C.c_void_p, C.POINTER(C.c_double)],
     "sbx_drainage_active_tfe_count": [C.c_void_p, C.POINTER(C.c_int32)],
     "sbx_drainage_fronts": [C.c_void_p, C.POINTER(TfeFrontC), C.POINTER(C.c_int32)],
+    "sbx_drainage_get_state": [C.c_void_p, C.POINTER(TfeStateC)],
+    "sbx_drainage_set_state": [C.c_void_p, C.POINTER(TfeStateC)],
     "sbx_drainage_update_params": [C.c_void_p, C.POINTER(DrainageParamsC)],
     "sbx_drainage_params_get": [C.c_void_p, C.POINTER(DrainageParamsC)],
     "sbx_drainage_set_physics": [C.c_void_p] + [C.c_double] * 6,

@@ -94,7 +94,8 @@ struct sbx_drainage {
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;  // host-pipelined step: H2D / D2H engines
     std::vector<cudaEvent_t> ev_in, ev_comp;
-    cudaEvent_t ev_start = nullptr, ev_out = nullptr;
+    cudaEvent_t ev_start = nullptr, ev_out = nullptr, ev_all = nullptr;
+    bool ghost_stale = false;  // sharded host-buffer step: the ghost rows of the current buffer were not refreshed
     void *buf[2] = {nullptr, nullptr};   // thickness ping-pong
     float *conc[2] = {nullptr, nullptr}; // WGSL concentration ping-pong
     int cur = 0;
@@ -231,6 +232,7 @@ static void free_all(sbx_drainage *h)
     for (auto e : h->ev_comp) cudaEventDestroy(e);
     if (h->ev_start) cudaEventDestroy(h->ev_start);
     if (h->ev_out) cudaEventDestroy(h->ev_out);
+    if (h->ev_all) cudaEventDestroy(h->ev_all);
     delete h;
 }
 
@@ -576,6 +578,7 @@ static int32_t download_conv(sbx_drainage *h, TH *host, const TS *src)
 }
 
 static int32_t halo_exchange(sbx_drainage *h);
+static int32_t ensure_ghosts(sbx_drainage *h);
 
 extern "C" int32_t sbx_drainage_upload(sbx_drainage *h, const void *host, int32_t dtype)
 {
@@ -868,6 +871,7 @@ static void fill_step_args(sbx_drainage *h, StepArgs<T> &a, double dt, const Rgb
     a.bub = reinterpret_cast<const BubbleParam<T> *>(h->bub);
     a.pole_partial = h->pole_partial;
     a.pole_count = h->pole_count;
+    a.dev_status = (unsigned int *)(h->sync_dev + 4);
     a.num_phi = h->num_phi;
     a.num_theta = h->num_theta;
     a.row_begin = h->row_begin;
@@ -893,14 +897,22 @@ static void fill_step_args(sbx_drainage *h, StepArgs<T> &a, double dt, const Rgb
     a.l2_keep_edges = h->l2_keep_edges ? 1 : 0;
 }
 
-// decide whether this launch writes the pole rows inside the TMA kernel, and which arrival count it waits for
+// decide whether this launch writes the pole rows inside the TMA kernel, and which arrival count it waits for.
+// The host-side count is committed only after the launch has been accepted (commit_pole_fold): a failed launch
+// must not leave the device counters one round behind what every later step would wait for.
 template <typename T>
 static void set_pole_fold(sbx_drainage *h, StepArgs<T> &a, bool top, bool bottom)
 {
     a.fold_top = a.fold_bottom = 0;
     if (!h->use_tma || h->strict || !march_tma_folds_poles<T>(a)) return;
-    if (top) { a.fold_top = 1; a.pole_want[0] = ++h->fold_count[0]; }
-    if (bottom) { a.fold_bottom = 1; a.pole_want[1] = ++h->fold_count[1]; }
+    if (top) { a.fold_top = 1; a.pole_want[0] = h->fold_count[0] + 1; }
+    if (bottom) { a.fold_bottom = 1; a.pole_want[1] = h->fold_count[1] + 1; }
+}
+template <typename T>
+static void commit_pole_fold(sbx_drainage *h, const StepArgs<T> &a)
+{
+    if (a.fold_top) ++h->fold_count[0];
+    if (a.fold_bottom) ++h->fold_count[1];
 }
 
 template <typename T>
@@ -968,6 +980,7 @@ static int32_t step_cpu_sem(sbx_drainage *h, double dt, const RgbArgs &rgb)
             h->mm_track_set = set;
         }
         CU(launch_step<T>(a, h->batch, ft.count > 0, false, has_top, has_bottom, h->band_rows, h->use_tma, h->stream, &n));
+        commit_pole_fold<T>(h, a);
         h->cur = 1 - h->cur;
         h->mm_kernel_valid = tracked;
         if (pushed) {
@@ -1121,6 +1134,7 @@ static int32_t do_steps(sbx_drainage *h, double dt, int32_t nsteps, const sbx_vi
     }
     int32_t rc = ensure_tables(h);
     if (rc != SBX_OK) return rc;
+    if (nsteps > 0 && (rc = ensure_ghosts(h)) != SBX_OK) return rc;
     RgbArgs rgb;
     rc = prepare_rgb(h, view, rgb);
     if (rc != SBX_OK) return rc;
@@ -1195,7 +1209,30 @@ extern "C" int32_t sbx_drainage_download_rgb(sbx_drainage *h, void *host)
 // One fused step with host buffers, pipelined over latitude chunks so that the H2D copy of chunk c+1, the
 // kernels of chunk c and the D2H copies of chunk c-1 overlap (three streams, both copy engines busy: the step is
 // PCIe-bound, so the round trip costs max(H2D, D2H) instead of their sum).  f32 in/out, CPU semantics, one
-// bubble, whole or banded sphere without a communicator.
+// bubble, whole sphere or one latitude band of a sharded sphere.  On a sharded handle every rank makes this call
+// with its own band: the first and the last chunk are uploaded first, the neighbours' boundary rows of the INPUT
+// field are exchanged once (sbx_comm_halo on the upload stream, 2 x num_phi x 4 bytes) while the other chunks
+// are still crossing PCIe, and the two chunks that read a ghost row wait for that exchange only.
+static int32_t ensure_ghosts(sbx_drainage *h)
+{
+    if (!h->comm || !h->ghost_stale) return SBX_OK;
+    h->ghost_stale = false;
+    return halo_exchange(h);
+}
+
+static int host_chunk_rows(const sbx_drainage *h)
+{
+    // ~32 MiB of f32 per chunk (504 rows at 16384 columns: a multiple of the kernel's band heights), >= 8 rows
+    if (const char *e = getenv("SBX_HOST_CHUNK_ROWS")) {
+        const int env = atoi(e);
+        if (env >= 8) return env;
+    }
+    long long r = (32ll << 20) / ((long long)h->num_phi * 4);
+    r = r / 56 * 56;
+    if (r < 56) r = 56;
+    return (int)r;
+}
+
 static int32_t step_host_pipelined(sbx_drainage *h, double dt, const sbx_view *view, const float *host_in,
                                    float *host_out_h, void *host_out_rgb)
 {
@@ -1206,13 +1243,15 @@ static int32_t step_host_pipelined(sbx_drainage *h, double dt, const sbx_view *v
     rc = prepare_rgb(h, view, rgb);
     if (rc != SBX_OK) return rc;
     const int N = h->num_phi, rows = h->rows_local;
-    const int chunk_rows = 504;  // ~32 MiB at 16384 columns; a multiple of the kernel's 24-row bands
+    const int chunk_rows = host_chunk_rows(h);
     const int nchunks = (rows + chunk_rows - 1) / chunk_rows;
+    const int L = nchunks - 1;
     if (!h->copy_in) {
         CU(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
         CU(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
         CU(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
         CU(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_all, cudaEventDisableTiming));
     }
     while ((int)h->ev_in.size() < nchunks) {
         cudaEvent_t a, b;
@@ -1235,24 +1274,44 @@ static int32_t step_host_pipelined(sbx_drainage *h, double dt, const sbx_view *v
     CU(cudaEventRecord(h->ev_start, h->stream));
     CU(cudaStreamWaitEvent(h->copy_in, h->ev_start, 0));
     CU(cudaStreamWaitEvent(h->copy_out, h->ev_start, 0));
-    for (int c = 0; c < nchunks; ++c) {
+    auto upload_chunk = [&](int c) -> int32_t {
         const int r0 = c * chunk_rows, r1 = std::min(rows, r0 + chunk_rows);  // owned rows [r0, r1)
         CU(cudaMemcpyAsync(in + (size_t)(r0 + 1) * N, host_in + (size_t)r0 * N, (size_t)(r1 - r0) * N * 4,
                            cudaMemcpyHostToDevice, h->copy_in));
         CU(cudaEventRecord(h->ev_in[c], h->copy_in));
+        return SBX_OK;
+    };
+    // upload order: 0, L, [halo rows of the input field], 1 .. L-1
+    if ((rc = upload_chunk(0)) != SBX_OK) return rc;
+    if (L > 0 && (rc = upload_chunk(L)) != SBX_OK) return rc;
+    if (h->comm) {
+        const char *err = nullptr;
+        const size_t row_bytes = (size_t)N * 4;
+        char *base = (char *)in;
+        if (sbx_comm_halo(h->comm, base + row_bytes, base, base + (size_t)rows * row_bytes,
+                          base + (size_t)(rows + 1) * row_bytes, row_bytes, h->copy_in, &err) != 0)
+            return fail(SBX_ERR_COMM, "halo exchange failed: %s", err ? err : "?");
     }
+    for (int c = 1; c < L; ++c)
+        if ((rc = upload_chunk(c)) != SBX_OK) return rc;
+    CU(cudaEventRecord(h->ev_all, h->copy_in));
     int n = 0;
     for (int c = 0; c < nchunks; ++c) {
         const int r0 = c * chunk_rows, r1 = std::min(rows, r0 + chunk_rows);
-        CU(cudaStreamWaitEvent(h->stream, h->ev_in[std::min(c + 1, nchunks - 1)], 0));  // needs the row below too
+        // chunk c reads the first row of chunk c + 1 too; in upload order ev_in[c + 1] (c + 1 < L) covers 0, L, the
+        // halo rows and 1 .. c + 1; the last two chunks wait for everything
+        CU(cudaStreamWaitEvent(h->stream, c + 1 < L ? h->ev_in[c + 1] : h->ev_all, 0));
         StepArgs<float> ac = a;
         ac.l_first = std::max(l_first, r0 + 1);
         ac.l_last = std::min(l_last, r1);
         // the pole rows are written by the launch that holds the ring next to them
         const bool top = c == 0 && h->row_begin == 0;
         const bool bottom = c == (rows - 2) / chunk_rows && h->row_end == h->num_theta;
-        set_pole_fold<float>(h, ac, top, bottom);
-        CU(launch_step<float>(ac, 1, ft.count > 0, false, top, bottom, h->band_rows, h->use_tma, h->stream, &n));
+        if (ac.l_first <= ac.l_last) {
+            set_pole_fold<float>(h, ac, top, bottom);
+            CU(launch_step<float>(ac, 1, ft.count > 0, false, top, bottom, h->band_rows, h->use_tma, h->stream, &n));
+            commit_pole_fold<float>(h, ac);
+        }
         CU(cudaEventRecord(h->ev_comp[c], h->stream));
         CU(cudaStreamWaitEvent(h->copy_out, h->ev_comp[c], 0));
         if (host_out_rgb && px)
@@ -1265,6 +1324,7 @@ static int32_t step_host_pipelined(sbx_drainage *h, double dt, const sbx_view *v
     h->launches += n;
     h->cur = 1 - h->cur;
     h->time += dt;
+    h->ghost_stale = h->comm != nullptr;  // the new field's ghost rows are fetched when a device-resident step needs them
     CU(cudaEventRecord(h->ev_out, h->copy_out));
     CU(cudaStreamWaitEvent(h->stream, h->ev_out, 0));
     CU(cudaStreamSynchronize(h->stream));
@@ -1277,7 +1337,7 @@ extern "C" int32_t sbx_drainage_step_host(sbx_drainage *h, double dt, int32_t ns
 {
     CHECK_H(h);
     int32_t rc = SBX_OK;
-    if (host_in && nsteps == 1 && !h->wgsl && !h->f64 && h->batch == 1 && !h->comm && h->href_zero &&
+    if (host_in && nsteps == 1 && !h->wgsl && !h->f64 && h->batch == 1 && h->href_zero &&
         in_dtype == SBX_F32 && (!host_out_h || out_dtype == SBX_F32) && h->num_phi % 4 == 0 && h->rows_local >= 8 &&
         !getenv("SBX_NO_HOST_PIPELINE"))
         return step_host_pipelined(h, dt, view, (const float *)host_in, (float *)host_out_h, host_out_rgb);
@@ -1314,7 +1374,10 @@ extern "C" int32_t sbx_drainage_get_thickness(sbx_drainage *h, int32_t bubble, d
     const size_t pj = (size_t)floor(pc) % (size_t)NP;
     const size_t pj_hi = (pj + 1) % (size_t)NP;
     const double tf = tc - (double)ti, pf = pc - (double)pj;
-    if ((int)ti < h->row_begin || (int)ti + 1 >= h->row_end)
+    // the lower of the two rows may be the bottom ghost row when it is kept current by the per-step NCCL exchange
+    // (with the in-kernel peer push the neighbour's store is ordered by device flags only, not by this stream)
+    const bool ghost_ok = h->comm && !h->peer_enabled && !h->ghost_stale && h->row_end < h->num_theta;
+    if ((int)ti < h->row_begin || (int)ti + 1 > h->row_end || ((int)ti + 1 == h->row_end && !ghost_ok))
         return fail(SBX_ERR_INVALID, "theta rows %zu,%zu are not owned by this band [%d,%d)", ti, ti + 1, h->row_begin, h->row_end);
     const long long base = (long long)bubble * h->bubble_stride;
     const long long r0 = base + (long long)((int)ti - h->row_begin + 1) * NP, r1 = r0 + NP;
@@ -1483,12 +1546,40 @@ extern "C" int32_t sbx_drainage_fronts(sbx_drainage *h, sbx_tfe_front *out8, int
     return SBX_OK;
 }
 
+extern "C" int32_t sbx_drainage_get_state(sbx_drainage *h, sbx_tfe_state *out)
+{
+    if (!h || !out) return fail(SBX_ERR_INVALID, "null argument");
+    memset(out, 0, sizeof *out);
+    out->time = h->time;
+    out->next_spawn = h->next_spawn;
+    out->count = (int32_t)h->fronts.size();
+    for (size_t i = 0; i < h->fronts.size() && i < (size_t)kMaxFronts; ++i) out->fronts[i] = h->fronts[i];
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_set_state(sbx_drainage *h, const sbx_tfe_state *st)
+{
+    if (!h || !st) return fail(SBX_ERR_INVALID, "null argument");
+    if (st->count < 0 || st->count > kMaxFronts) return fail(SBX_ERR_INVALID, "count %d out of range [0,%d]", st->count, kMaxFronts);
+    if (!std::isfinite(st->time) || !std::isfinite(st->next_spawn)) return fail(SBX_ERR_INVALID, "time / next_spawn must be finite");
+    for (int i = 0; i < st->count; ++i) {
+        const sbx_tfe_front &f = st->fronts[i];
+        if (!std::isfinite(f.phi_center) || !std::isfinite(f.extent) || !std::isfinite(f.width) || !std::isfinite(f.velocity))
+            return fail(SBX_ERR_INVALID, "front %d has a non-finite field", i);
+    }
+    h->time = st->time;
+    h->next_spawn = st->next_spawn;
+    h->fronts.assign(st->fronts, st->fronts + st->count);
+    return SBX_OK;
+}
+
 extern "C" int32_t sbx_drainage_update_params(sbx_drainage *h, const sbx_drainage_params *p)
 {
     if (!h || !p) return fail(SBX_ERR_INVALID, "null argument");
     if (!h->wgsl) return fail(SBX_ERR_INVALID, "update_params applies to SBX_SEM_WGSL handles");
     if (p->grid_width != (uint32_t)h->num_phi || p->grid_height != (uint32_t)h->num_theta)
         return fail(SBX_ERR_INVALID, "grid size is fixed at creation (%dx%d)", h->num_phi, h->num_theta);
+    if (p->bubble_radius != h->wp.bubble_radius) h->tables_dirty = true;  // BubbleParam.radius feeds the view cosine
     h->wp = *p;
     std::fill(h->b_radius.begin(), h->b_radius.end(), (double)p->bubble_radius);
     return SBX_OK;
@@ -1561,6 +1652,7 @@ extern "C" int32_t sbx_drainage_caustics(sbx_drainage *h, const sbx_caustic_para
 {
     CHECK_H(h);
     if (!p) return fail(SBX_ERR_INVALID, "p is null");
+    { int32_t rcg = ensure_ghosts(h); if (rcg != SBX_OK) return rcg; }
     const size_t cells = (size_t)h->batch * h->rows_local * h->num_phi;
     if (!h->caustic_buf) CU(cudaMalloc(&h->caustic_buf, cells * sizeof(float)));
     sbx_caustic_params q = *p;
@@ -1933,6 +2025,7 @@ extern "C" int32_t sbx_interference_terms(double n_film, const double *d_nm, con
 // ------------------------------------------------------------------ multi-GPU glue
 static int32_t halo_exchange(sbx_drainage *h)
 {
+    h->ghost_stale = false;
     if (!h->comm) return SBX_OK;
     const char *err = nullptr;
     // my first owned row -> upper neighbour's bottom ghost; my last owned row -> lower neighbour's top ghost
@@ -2044,7 +2137,7 @@ extern "C" int32_t sbx_drainage_peer_status(sbx_drainage *h, int32_t *out)
     CU(cudaMemcpyAsync(h->scalar_host, h->sync_dev + 4, sizeof v, cudaMemcpyDeviceToHost, h->stream));
     CU(cudaStreamSynchronize(h->stream));
     memcpy(&v, h->scalar_host, sizeof v);
-    *out = v ? 1 : 0;
+    *out = (int32_t)(v & 3ull);  // bit 0: neighbour wait timed out, bit 1: pole-ring wait timed out
     if (v) CU(cudaMemsetAsync(h->sync_dev + 4, 0, sizeof v, h->stream));
     return SBX_OK;
 }

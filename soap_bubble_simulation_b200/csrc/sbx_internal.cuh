@@ -68,7 +68,7 @@ struct PeerArgs {
     const unsigned long long *flag_from_up;    // mine: written by the up neighbour
     const unsigned long long *flag_from_dn;    // mine: written by the down neighbour
     unsigned int *done_first, *done_last;      // CTA counters of my first / last band
-    unsigned int *status;                      // != 0: a wait timed out
+    unsigned int *status;                      // bit 0 set: a neighbour wait timed out (same word as StepArgs::dev_status)
     unsigned long long epoch;                  // number of this step, >= 1
     int push_up_grow, push_dn_grow;            // global row whose new values go to the up / down neighbour (-1: none)
     int enabled;
@@ -88,6 +88,7 @@ struct StepArgs {
     unsigned long long *pole_count;  // [batch][2] monotonic arrival counters (TMA kernel's folded pole rows)
     unsigned long long pole_want[2]; // arrivals per strip count the folded launches: wait for pole_want * strips
     int fold_top, fold_bottom;       // TMA kernel: this launch also writes the top / bottom pole row
+    unsigned int *dev_status;        // bit mask of in-kernel waits that timed out: 1 = latitude neighbour, 2 = pole ring
     int pole_slots;
     int num_phi, num_theta;  // global grid
     int row_begin;           // global row of local row 1

@@ -46,7 +46,7 @@ __device__ __forceinline__ void wait_neighbour(const unsigned long long *flag, u
     const unsigned long long t0 = globaltimer_ns();
     while (ld_acquire_sys(flag) < want) {
         if (globaltimer_ns() - t0 > 5000000000ull) {  // 5 s
-            atomicExch(status, 1u);
+            atomicOr(status, 1u);
             break;
         }
         __nanosleep(64);
@@ -382,10 +382,12 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
     load_slot(r0, 0);
     load_slot(r1, 1);
     int left = l1 - l0 + 1;  // rows still to compute
+    uint32_t unconsumed = row_bits(r0) | row_bits(r1);  // first release only: nothing of stage 0 has been used yet
     while (true) {
         load_slot(r2, 2);
         // slot 2 was loaded just now; slot 1's edge values (r1.eL/eR) are first used by the row computed next
-        release_stage(row_bits(r2) | dep_bits(r1.eL) | dep_bits(r1.eR));
+        release_stage(row_bits(r2) | dep_bits(r1.eL) | dep_bits(r1.eR) | unconsumed);
+        unconsumed = 0;
         compute_row(r0, r1, r2);
         if (--left == 0) break;
         mbar_wait(&full[stage], full_parity);
@@ -408,8 +410,17 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
             if (!(which == 0 ? a.fold_top : a.fold_bottom) || ring < g_first || ring > g_last) continue;
             const unsigned long long want = a.pole_want[which] * (unsigned long long)gridDim.x;
             if (tid == 0) {
+                // bounded like wait_neighbour: if a sibling strip never arrives (a failed launch, or strips that could
+                // not be co-resident) the step finishes with a wrong pole row and says so instead of hanging the GPU
                 const volatile unsigned long long *cnt = a.pole_count + 2 * b + which;
-                while (*cnt < want) __nanosleep(32);
+                const unsigned long long t0 = globaltimer_ns();
+                while (*cnt < want) {
+                    if (globaltimer_ns() - t0 > 2000000000ull) {  // 2 s
+                        atomicOr(a.dev_status, 2u);
+                        break;
+                    }
+                    __nanosleep(32);
+                }
                 __threadfence();
                 const double *pp = a.pole_partial + (long long)b * 2 * a.pole_slots + which * a.pole_slots;
                 double t = 0.0;
@@ -571,8 +582,11 @@ bool march_tma_folds_poles(const StepArgs<T> &a)
 {
     constexpr int VEC = 16 / (int)sizeof(T);
     if (!march_tma_supported<T>(a) || a.l_last < a.l_first) return false;
+    // the strips of a ring are dispatched back to back and wait for each other at the end of their band: that
+    // terminates as long as they all fit on the device at once, whatever else is resident (SMs x resident CTAs)
     const int strip = tma_consumers<T>(a.num_phi) * VEC;
-    return (a.num_phi + strip - 1) / strip <= 128;
+    const int slots = device_sm_count() * MinBlocks<T>::value;
+    return (a.num_phi + strip - 1) / strip <= (slots < 128 ? slots : 128);
 }
 
 template <typename T>

@@ -25,16 +25,31 @@ __device__ __forceinline__ void mbar_arrive(uint64_t *bar)
 // A plain `ld.shared ...; mbarrier.arrive` pair is not enough: nothing makes the arrive wait for the loads' data
 // (SASS: SYNCS.ARRIVE carries no scoreboard wait on the preceding LDS), so under load-store-unit back-pressure the
 // arrive -- and the TMA overwrite it allows -- can overtake a load that is still queued, and the warp then reads the
-// NEXT contents of the slot (seen as one wrong row segment per ~1e6 warp-rows at 8192 x 16384).  Here the arrive's
-// address is made data-dependent on the loaded registers: `bits` is an OR of them and the mask is a run-time zero
-// (blockDim.y - 1 of a 1-D block) that no compiler stage can fold, so the instruction cannot issue before every
-// load that produced `bits` has written its registers -- for all lanes, since a warp's LDS is one instruction.
+// NEXT contents of the slot (seen as one wrong row segment per ~1e6 warp-rows at 8192 x 16384).
+// The releasing lane therefore first STORES an OR of the loaded registers (`bits`) to a per-warp sink word in shared
+// memory and arrives after that: the store cannot issue before every load that produced `bits` has written its
+// registers (a true register dependency, for all lanes, since a warp's LDS is one instruction), and the arrive has
+// release semantics, which orders it after the thread's earlier store.  No assumption about the block shape and
+// nothing a compiler stage can fold away.  (SBX_ARRIVE_SINK=0 builds the round-1 form, which carried the dependency
+// in the barrier ADDRESS through a run-time zero, blockDim.y - 1: same measured behaviour, 1-D blocks only.)
+#ifndef SBX_ARRIVE_SINK
+#define SBX_ARRIVE_SINK 1
+#endif
 __device__ __forceinline__ uint32_t dep_bits(float v) { return __float_as_uint(v); }
 __device__ __forceinline__ uint32_t dep_bits(double v) { return (uint32_t)__double2hiint(v) | (uint32_t)__double2loint(v); }
 __device__ __forceinline__ void mbar_arrive_after(uint64_t *bar, uint32_t bits)
 {
+#if SBX_ARRIVE_SINK
+    __shared__ uint32_t s_sink[32];  // one word per warp of the block
+    asm volatile(
+        "st.volatile.shared.u32 [%1], %2;\n\t"
+        "mbarrier.arrive.release.cta.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)),
+        "r"(smem_u32(&s_sink[threadIdx.x >> 5])), "r"(bits)
+        : "memory");
+#else
     const uint32_t off = bits & (blockDim.y - 1u);
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar) + off) : "memory");
+#endif
 }
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {

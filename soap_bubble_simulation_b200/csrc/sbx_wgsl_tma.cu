@@ -234,10 +234,12 @@ __global__ void __launch_bounds__(288, 3) k_wgsl_tma(const WgslArgs a)
     load_slot(h0, g0, 0);
     load_slot(h1, g1, 1);
     int left = l1 - l0 + 1;
+    uint32_t unconsumed = row_bits(h0) | row_bits(g0) | row_bits(h1) | row_bits(g1);  // first release: stage 0 is untouched
     while (true) {
         load_slot(h2, g2, 2);
         // slot 2 (h2, g2) was loaded just now; slot 1's edge values are first used by the row computed next
-        release_stage(row_bits(h2) | row_bits(g2) | dep_bits(h1.eL) | dep_bits(h1.eR) | dep_bits(g1.eL) | dep_bits(g1.eR));
+        release_stage(row_bits(h2) | row_bits(g2) | dep_bits(h1.eL) | dep_bits(h1.eR) | dep_bits(g1.eL) | dep_bits(g1.eR) | unconsumed);
+        unconsumed = 0;
         compute_row(h0, h1, h2, g0, g1, g2);
         if (--left == 0) break;
         mbar_wait(&full[stage], full_parity);

@@ -45,7 +45,9 @@ def camera_position(distance: float, yaw: float, pitch: float):
 class ThicknessField:
     """ThicknessField (drainage.rs:96-204).  Standalone it is a plain host container; obtained from
     ``DrainageSimulator.thickness_field()`` it is a view of the device field (reductions run on the GPU,
-    ``data()`` downloads, ``set``/``data_mut`` edits are uploaded before the next step)."""
+    ``data()`` downloads, ``set``/``data_mut`` edits are uploaded before the next step).  The reference has one
+    bubble per simulator; on a batched (foam) handle the view shows bubble 0 and edits to it are written back
+    into the full batch."""
 
     def __init__(self, num_theta: int, num_phi: int, initial_thickness: float, _sim=None):
         self._num_theta, self._num_phi = int(num_theta), int(num_phi)
@@ -60,14 +62,15 @@ class ThicknessField:
     # -- synchronisation with the device (attached fields only)
     def _refresh(self) -> np.ndarray:
         if self._sim is not None and (self._host is None or self._sim._host_stale) and not self._dirty:
-            self._host = self._sim.download(np.float64)[0]
+            self._full = self._sim.download(np.float64)  # (batch, rows, phi)
+            self._host = self._full[0]                   # a view: edits land in the full array
             self._sim._host_stale = False
         return self._host
 
     def _flush(self) -> None:
         if self._sim is not None and self._dirty:
-            self._sim.upload(self._host)
             self._dirty = False
+            self._sim.upload(self._full)
 
     def get(self, theta_index: int, phi_index: int) -> float:  # drainage.rs:137-139
         return float(self._refresh()[theta_index, phi_index])
@@ -155,6 +158,8 @@ class _DeviceField:
             raise ValueError(f"field has {a.size} cells, expected {self._shape()}")
         L.check(L.lib().sbx_drainage_upload(self._h, a.ctypes.data, L.F64 if a.dtype == np.float64 else L.F32))
         self._host_stale = True
+        if getattr(self, "_field", None) is not None:
+            self._field._dirty = False  # an explicit upload replaces pending ThicknessField edits
 
     def download(self, dtype=np.float64) -> np.ndarray:
         out = np.empty(self._shape(), dtype=dtype)
@@ -199,7 +204,13 @@ class _DeviceField:
         A, T = a.shape[0], a.shape[1]
         L.check(L.lib().sbx_drainage_set_lut(self._h, a.ctypes.data, T, A, max_nm))
 
+    def _flush_field(self) -> None:
+        f = getattr(self, "_field", None)
+        if f is not None:
+            f._flush()
+
     def shade(self, view: View) -> None:
+        self._flush_field()
         vc = view.to_c()
         L.check(L.lib().sbx_drainage_shade(self._h, C.byref(vc)))
 
@@ -211,6 +222,10 @@ class _DeviceField:
     def step_host(self, dt: float, nsteps: int, view: Optional[View], host_in: Optional[np.ndarray],
                   host_out_h: Optional[np.ndarray], host_out_rgb: Optional[np.ndarray]) -> None:
         """Host-buffer round trip (sbx_drainage_step_host): upload, nsteps fused steps, download."""
+        if host_in is None:
+            self._flush_field()  # pending ThicknessField edits are the input
+        elif getattr(self, "_field", None) is not None:
+            self._field._dirty = False  # the uploaded field replaces them
         vc = view.to_c() if view is not None else None
 
         def dt_of(a):
@@ -374,6 +389,25 @@ class DrainageSimulator(_DeviceField):
         n = C.c_int32()
         L.check(L.lib().sbx_drainage_fronts(self._h, buf, C.byref(n)))
         return [(buf[k].phi_center, buf[k].extent, buf[k].width, buf[k].velocity) for k in range(n.value)]
+
+    def get_state(self):
+        """(current_time, next_tfe_spawn_time, fronts) -- the host state machine beside the field (drainage.rs:237-255)."""
+        st = L.TfeStateC()
+        L.check(L.lib().sbx_drainage_get_state(self._h, C.byref(st)))
+        fr = [(st.fronts[k].phi_center, st.fronts[k].extent, st.fronts[k].width, st.fronts[k].velocity)
+              for k in range(st.count)]
+        return st.time, st.next_spawn, fr
+
+    def set_state(self, time: float, next_spawn: float, fronts) -> None:
+        """Restore a checkpoint taken with get_state (field: download / upload)."""
+        st = L.TfeStateC()
+        st.time, st.next_spawn, st.count = float(time), float(next_spawn), len(fronts)
+        if len(fronts) > 8:
+            raise ValueError("at most 8 fronts (drainage.rs:474)")
+        for k, f in enumerate(fronts):
+            st.fronts[k].phi_center, st.fronts[k].extent, st.fronts[k].width, st.fronts[k].velocity = map(float, f)
+        L.check(L.lib().sbx_drainage_set_state(self._h, C.byref(st)))
+        self._host_stale = True
 
     def set_physics(self, density, gravity, viscosity, diffusion, critical_thickness_m, radius_m) -> None:
         L.check(L.lib().sbx_drainage_set_physics(self._h, density, gravity, viscosity, diffusion,

@@ -1,5 +1,7 @@
 """torchrun worker for the multi-GPU parity test: latitude-band sharded drainage (+ fused colour) against
-the single-domain CPU oracle.  Usage: torchrun --nproc-per-node N tests/mgpu_worker.py <nt> <nphi> <steps> <prec>"""
+the single-domain CPU oracle.  Usage: torchrun --nproc-per-node N tests/mgpu_worker.py <nt> <nphi> <steps> <prec> <halo>
+halo: nccl | peer (device-resident steps), host (sbx_drainage_step_host per rank, then device-resident steps),
+foam (independent bubbles sharded by bubble index, no exchange)."""
 import os
 import sys
 
@@ -13,8 +15,41 @@ sys.path.insert(0, os.path.dirname(HERE))
 
 import oracle_lib as O  # noqa: E402
 import soap_bubble_simulation_b200 as S  # noqa: E402
-from soap_bubble_simulation_b200.sharding import Comm, band_partition  # noqa: E402
+from soap_bubble_simulation_b200.sharding import Comm, band_partition, bubble_range  # noqa: E402
 from synth import dt_max, synthetic_field  # noqa: E402
+
+
+def foam(nt, nphi, steps, prec, rank, world, local):
+    """config 4 in small: 3 * world + 1 bubbles with their own h0 / radius, split by bubble_range, no exchange."""
+    total = 3 * world + 1
+    b0, b1 = bubble_range(total, world, rank)
+    idx = np.arange(total) / (total - 1)
+    h0, rad = (300.0 + 400.0 * idx) * 1e-9, 0.0125 + 0.0875 * idx
+    sim = S.DrainageSimulator(S.SimulationConfig.default(), precision=prec, device=local, num_theta=nt, num_phi=nphi,
+                              h_ref=1.0, batch=b1 - b0, batch_h0_m=h0[b0:b1], batch_radius_m=rad[b0:b1])
+    view = S.View(mode=S.RGB_LUT, format=S.OUT_RGBA8)
+    dt = 1e-3
+    sim.step(dt, steps - 1)
+    sim.step_fused(dt, view, 1)
+    got, px = sim.download(), sim.download_rgb()
+    ok, worst, worst_inc, worst_px = True, 0.0, 0.0, 0
+    for k, b in enumerate(range(b0, b1)):
+        ora = O.OracleDrainage(nt, nphi, h0_m=float(h0[b]), radius_m=float(rad[b]))
+        ora.step(dt, steps)
+        worst = max(worst, float(np.abs(got[k] / ora.data - 1).max()))
+        dref = ora.data - h0[b]
+        worst_inc = max(worst_inc, float(np.abs((got[k] - h0[b]) - dref).max() / np.abs(dref).max()))
+        ref = O.shade_field(ora.data, nt, 0, float(rad[b]), view.cam_pos, intensity=4.0, mode=1)
+        worst_px = max(worst_px, int(np.abs(px[k].astype(int) - ref.astype(int)).max()))
+    ok = worst <= 1e-5 and worst_inc <= 1e-3 and worst_px <= 1
+    allok = [None] * world
+    dist.all_gather_object(allok, (b0, b1, ok, worst, worst_inc, worst_px))
+    covered = sorted(b for r in allok for b in range(r[0], r[1]))
+    ok_all = all(r[2] for r in allok) and covered == list(range(total))
+    if rank == 0:
+        print(f"MGPU world={world} foam {total} bubbles of {nt}x{nphi}: err={max(r[3] for r in allok):.3e} "
+              f"incr={max(r[4] for r in allok):.3e} rgba_max_diff={max(r[5] for r in allok)} ok={ok_all}", flush=True)
+    return ok_all
 
 
 def main():
@@ -23,6 +58,10 @@ def main():
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    if halo == "foam":
+        ok = foam(nt, nphi, steps, prec, rank, world, local)
+        dist.destroy_process_group()
+        sys.exit(0 if ok else 1)
     rb, re = band_partition(nt, world)[rank]
     sim = S.DrainageSimulator(S.SimulationConfig.default(), precision=prec, device=local, num_theta=nt,
                               num_phi=nphi, h_ref=0.0, row_begin=rb, row_end=re)
@@ -32,16 +71,31 @@ def main():
     sim.upload(band)
     comm = Comm(rank, world, local)
     sim.attach_comm(comm)
-    if halo == "peer":
+    if halo in ("peer", "host"):
         comm.enable_peer_halo(sim)
     dt = min(5e-3, 0.25 * dt_max(nt, nphi))  # 5 ms steps reach the first TFE front (t = 0.5 s) quickly
     view = S.View(mode=S.RGB_LUT, format=S.OUT_RGBA8)
-    sim.step(dt, steps - 1)
-    sim.step_fused(dt, view, 1)
+    if halo == "host":
+        # the end-to-end path: every rank hands its band in host memory to sbx_drainage_step_host (chunk-pipelined,
+        # input halo rows exchanged inside the call) and feeds the result back; then device-resident steps follow,
+        # whose ghost rows have to be fetched first
+        cur = band.astype(np.float32)[None].copy()
+        out_h = np.empty_like(cur)
+        out_px = np.empty(cur.shape + (4,), np.uint8)
+        n_host = steps - 4
+        for _ in range(n_host):
+            sim.step_host(dt, 1, view, cur, out_h, out_px)
+            cur, out_h = out_h, cur
+        assert np.array_equal(sim.download(np.float32), cur)
+        sim.step(dt, 3)
+        sim.step_fused(dt, view, 1)
+    else:
+        sim.step(dt, steps - 1)
+        sim.step_fused(dt, view, 1)
     got = sim.download()[0]
     px = sim.download_rgb()[0]
     mn, mx = sim.minmax_global()
-    peer_bad = Comm.peer_status(sim) if halo == "peer" else 0
+    peer_bad = Comm.peer_status(sim) if halo in ("peer", "host") else 0
     gathered = [None] * world
     dist.all_gather_object(gathered, (rb, re, got, px, sim.fronts(), peer_bad))
     ok = True

@@ -22,18 +22,25 @@ def _free_port():
         return s.getsockname()[1]
 
 
-@pytest.mark.parametrize("world", [2, 4])
+@pytest.mark.parametrize("world", [2, 4, 8])
 @pytest.mark.parametrize("nt,nphi,steps,prec,halo", [(64, 128, 120, 0, "nccl"), (64, 128, 140, 2, "nccl"),
                                                      (61, 50, 30, 1, "nccl"), (256, 1024, 8, 0, "nccl"),
                                                      (64, 128, 120, 0, "peer"), (256, 1024, 60, 0, "peer"),
-                                                     (16, 256, 40, 0, "peer")])
+                                                     (16, 256, 40, 0, "peer"),
+                                                     (64, 128, 120, 0, "host"), (1300, 256, 12, 0, "host"),
+                                                     (64, 128, 40, 0, "foam"), (32, 64, 30, 1, "foam")])
 def test_sharded_matches_oracle(world, nt, nphi, steps, prec, halo):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
+    if nt < 2 * world:
+        pytest.skip("fewer than two rows per band")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(HERE, "mgpu_worker.py"), str(nt), str(nphi), str(steps), str(prec), halo]
-    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    env = dict(os.environ)
+    if halo == "host":
+        env["SBX_HOST_CHUNK_ROWS"] = "56"  # several chunks per band: first / last chunk wait for the halo rows
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     sys.stdout.write(r.stdout[-2000:])
     assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-3000:]
     assert "ok=True" in r.stdout

@@ -594,7 +594,8 @@ def test_errors_are_reported_not_fatal(S):
 
 def test_step_host_pipelined_equals_separate_calls(S, monkeypatch):
     """sbx_drainage_step_host (chunk-pipelined H2D / kernels / D2H) against upload + step_fused + download."""
-    nt, nphi = 1300, 256  # three 504-row chunks
+    nt, nphi = 1300, 256
+    monkeypatch.setenv("SBX_HOST_CHUNK_ROWS", "504")  # three chunks (the default is ~32 MiB per chunk)
     f = synthetic_field(nt, nphi, dtype=np.float32)
     dt = 0.25 * dt_max(nt, nphi)
     view = S.View(mode=S.RGB_LUT, format=S.OUT_RGBA8)
