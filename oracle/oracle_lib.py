@@ -64,6 +64,7 @@ def lib() -> C.CDLL:
     sig = {
         "orc_drainage_create": (p, [i, i, d, d, d, d, d, d, d]),
         "orc_drainage_create_window": (p, [i, i, i, i, d, d, d, d, d, d, d]),
+        "orc_drainage_set_state": (i, [p, d, d, C.POINTER(TfeFront), i]),
         "orc_drainage_destroy": (None, [p]),
         "orc_drainage_step": (None, [p, d]),
         "orc_drainage_set_threads": (None, [p, i]),
@@ -212,6 +213,13 @@ class OracleDrainage:
 
     def active_tfe_count(self):
         return self._L.orc_drainage_active_tfe_count(self._s)
+
+    def set_state(self, time, next_spawn, fronts):
+        buf = (TfeFront * 9)()
+        for k, f in enumerate(fronts):
+            buf[k].phi_center, buf[k].extent, buf[k].width, buf[k].velocity = f
+        if self._L.orc_drainage_set_state(self._s, time, next_spawn, buf, len(fronts)) != 0:
+            raise ValueError("bad state")
 
     def fronts(self):
         buf = (TfeFront * 9)()

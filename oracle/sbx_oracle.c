@@ -327,6 +327,17 @@ int orc_drainage_fronts(const orc_drainage *s, orc_tfe_front *out)
 }
 double orc_drainage_next_spawn(const orc_drainage *s) { return s->next_spawn; }
 
+/* restore current_time, next_tfe_spawn_time and tfe_fronts (drainage.rs:237-255): checkpoint / resume of a run */
+int orc_drainage_set_state(orc_drainage *s, double time, double next_spawn, const orc_tfe_front *fronts, int count)
+{
+    if (count < 0 || count > ORC_MAX_FRONTS) return -1;
+    s->time = time;
+    s->next_spawn = next_spawn;
+    s->nfronts = count;
+    if (count) memcpy(s->fronts, fronts, (size_t)count * sizeof(orc_tfe_front));
+    return 0;
+}
+
 /* ================================================================== WGSL drainage (f32) */
 
 void orc_wgsl_params_default(orc_wgsl_params *p)

@@ -84,6 +84,8 @@ double orc_drainage_tfe_ratio(const orc_drainage *s);                           
 int orc_drainage_active_tfe_count(const orc_drainage *s);                           /* :611-613 */
 int orc_drainage_fronts(const orc_drainage *s, orc_tfe_front *out);                 /* returns count */
 double orc_drainage_next_spawn(const orc_drainage *s);
+/* restore current_time, next_tfe_spawn_time, tfe_fronts (drainage.rs:237-255); 0 = ok */
+int orc_drainage_set_state(orc_drainage *s, double time, double next_spawn, const orc_tfe_front *fronts, int count);
 
 /* ------------------------------------------------------------------ WGSL drainage (f32) */
 
