@@ -64,7 +64,7 @@ pub struct sbx_caustic_params {
 
 pub enum sbx_drainage {}
 pub enum sbx_comm {}
-pub const SBX_IPC_BYTES: usize = 256;
+pub const SBX_IPC_BYTES: usize = 512;
 
 pub const SBX_SEM_CPU: i32 = 0;
 pub const SBX_SEM_WGSL: i32 = 1;
@@ -83,6 +83,7 @@ pub const SBX_RGB_EXACT3: i32 = 2;
 pub const SBX_RGB_EXACT3_LINEAR: i32 = 3;
 pub const SBX_RGB_SCHLICK_WALL: i32 = 4;
 pub const SBX_RGB_SCHLICK_TWO_BEAM: i32 = 5;
+pub const SBX_RGB_SPECTRAL: i32 = 6;
 pub const SBX_OUT_RGBA8: i32 = 0;
 pub const SBX_OUT_RGB_F32: i32 = 1;
 
@@ -129,6 +130,7 @@ extern "C" {
     pub fn sbx_drainage_set_physics(h: *mut sbx_drainage, density: f64, gravity: f64, viscosity: f64, diffusion: f64,
                                     critical_thickness_m: f64, radius_m: f64) -> i32;
     pub fn sbx_drainage_set_lut(h: *mut sbx_drainage, rgba: *const u8, t: i32, a: i32, max_nm: f32) -> i32;
+    pub fn sbx_drainage_set_spectrum(h: *mut sbx_drainage, wavelengths_nm: *const f32, n: i32) -> i32;
     pub fn sbx_drainage_launch_count(h: *mut sbx_drainage, out: *mut i64) -> i32;
     pub fn sbx_caustic_params_default(p: *mut sbx_caustic_params) -> i32;
     pub fn sbx_drainage_caustics(h: *mut sbx_drainage, p: *const sbx_caustic_params, host_out: *mut f32) -> i32;

@@ -70,6 +70,13 @@ typedef enum {
                                    multi-bounce Airy, gamma 1/2.2) */
     SBX_RGB_EXACT3_LINEAR = 3,  /* calculate_interference_color_linear, interference.rs:413-426 */
     SBX_RGB_SCHLICK_WALL = 4,   /* wall.wgsl:165-207: Schlick Fresnel, transmitted Airy, 650/532/450 nm */
+    SBX_RGB_SPECTRAL = 6,       /* direct per-cell spectral evaluation without a LUT: thin_film_interference of the
+                                   fragment shaders (bubble_instanced.wgsl:190-218, bubble.wgsl:442-483 ==
+                                   interference_lut.rs:45-93) with the wavelength list as a parameter
+                                   (sbx_drainage_set_spectrum; default the reference's 7 wavelengths 400..700 nm):
+                                   Snell, unpolarised Fresnel, Airy per wavelength, CIE Gaussians -> XYZ -> linear
+                                   sRGB, times intensity, clamp.  SFU-bound by construction (BASELINE config 5's
+                                   direct half); colour only -- the drainage step runs first, then this pass */
     SBX_RGB_SCHLICK_TWO_BEAM = 5 /* the documented original model (docs/key-insights.md:288-309): two-beam
                                    I = (1+cos phi)/2 with phi = 2 pi (2 n d cos theta_t)/lambda + pi, times Schlick
                                    Fresnel, times 4 -- what README/north_star describe; no compiled reference code
@@ -241,6 +248,10 @@ int32_t sbx_drainage_device_ptr(sbx_drainage *h, int32_t kind, void **out);
  * builds generate_interference_lut(view.n_film, 1.0) itself on first use */
 int32_t sbx_drainage_set_lut(sbx_drainage *h, const uint8_t *rgba, int32_t T, int32_t A, float max_nm);
 
+/* wavelength list of SBX_RGB_SPECTRAL (1 <= n <= 256, nanometres); the handle starts with the reference's
+ * seven (400, 450, ..., 700 nm; bubble_instanced.wgsl:191) */
+int32_t sbx_drainage_set_spectrum(sbx_drainage *h, const float *wavelengths_nm, int32_t n);
+
 /* number of kernels this handle has launched so far (bench.py's gpu_launches) */
 int32_t sbx_drainage_launch_count(sbx_drainage *h, int64_t *out);
 
@@ -342,11 +353,12 @@ int32_t sbx_comm_destroy(sbx_comm *c);
 int32_t sbx_drainage_attach_comm(sbx_drainage *h, sbx_comm *c);
 /* Peer-memory halo push (all ranks on one NVLink/NVSwitch box).  Each rank exports a descriptor of its field
  * buffers (CUDA IPC handles), the caller moves the blobs between processes (torch.distributed), and attach maps
- * the neighbours' buffers.  From then on the f32 fast-path step stores each band's boundary rows directly into
- * the neighbours' ghost rows from inside the stencil kernel and orders neighbouring steps with two flags in
- * device memory -- no per-step collective.  Requires an attached communicator (used for the exchanges after
- * upload/reset and for the precisions the fast path does not cover).  up/down = blob of rank-1 / rank+1 or NULL. */
-#define SBX_IPC_BYTES 256
+ * the neighbours' buffers.  From then on the ring kernels (f32 and f64 CPU semantics, WGSL semantics with both of
+ * its fields) store each band's boundary rows directly into the neighbours' ghost rows from inside the stencil
+ * kernel and order neighbouring steps with two flags in device memory -- no per-step collective.  Requires an
+ * attached communicator (used for the exchanges after upload/reset and for the modes the ring kernels do not
+ * cover: strict f64, ragged widths, float colour output).  up/down = blob of rank-1 / rank+1 or NULL. */
+#define SBX_IPC_BYTES 512
 int32_t sbx_drainage_ipc_export(sbx_drainage *h, uint8_t out[SBX_IPC_BYTES]);
 int32_t sbx_drainage_ipc_attach(sbx_drainage *h, const uint8_t *up, const uint8_t *down);
 /* Device-side wait status since the last query, a bit mask: 0 = ok, bit 0 = a wait for a latitude neighbour's step

@@ -116,6 +116,7 @@ def lib() -> C.CDLL:
         "orc_sample_thickness_uv": (None, [p, i, i, p, C.c_size_t, p, p]),
         "orc_sample_thickness_normal": (None, [p, i, i, p, C.c_size_t, C.c_float, p, p]),
         "orc_shade_field": (None, [p, i, i, i, i, d, dp, d, p, i, i, f, f, i, p, i]),
+        "orc_shade_field_spectral": (None, [p, i, i, i, i, d, dp, f, f, p, i, p, p, i]),
     }
     for name, (res, args) in sig.items():
         fn = getattr(L, name)
@@ -369,6 +370,25 @@ def shade_field(h: np.ndarray, num_theta: int, row0: int, radius, cam, n_film=1.
     A, T = lut.shape[0], lut.shape[1]
     lib().orc_shade_field(h.ctypes.data, num_theta, nphi, row0, rows, radius, a, n_film, lut.ctypes.data, T, A,
                           max_nm, intensity, mode, out.ctypes.data, threads)
+    return out
+
+
+def shade_field_spectral(h: np.ndarray, num_theta: int, row0: int, radius, cam, wavelengths, n_film=1.33,
+                         intensity=4.0, threads=1, as_float=False) -> np.ndarray:
+    """Per-cell spectral colour (bubble_instanced.wgsl:190-218 with the wavelength list as a parameter) of the band h:
+    RGBA8 (rows, num_phi, 4) or, as_float, (rows, num_phi, 3) float32."""
+    h = np.ascontiguousarray(h, dtype=np.float64)
+    rows, nphi = h.shape
+    wl = np.ascontiguousarray(wavelengths, dtype=np.float32)
+    a = (C.c_double * 3)(*cam)
+    if as_float:
+        out = np.empty((rows, nphi, 3), dtype=np.float32)
+        lib().orc_shade_field_spectral(h.ctypes.data, num_theta, nphi, row0, rows, radius, a, n_film, intensity,
+                                       wl.ctypes.data, len(wl), None, out.ctypes.data, threads)
+    else:
+        out = np.empty((rows, nphi, 4), dtype=np.uint8)
+        lib().orc_shade_field_spectral(h.ctypes.data, num_theta, nphi, row0, rows, radius, a, n_film, intensity,
+                                       wl.ctypes.data, len(wl), out.ctypes.data, None, threads)
     return out
 
 

@@ -668,6 +668,15 @@ static void thin_film_spectral(float d_nm, float cos_theta, float n_film, float 
 
 static const float LUT_WL7[7] = {400.f, 450.f, 500.f, 550.f, 600.f, 650.f, 700.f}; /* :52 */
 
+/* thin_film_interference of the fragment shaders (bubble_instanced.wgsl:190-218, bubble.wgsl:442-483): the same f32
+ * algorithm per pixel with interference_intensity applied and the result clamped; wavelength list as a parameter */
+void orc_thin_film_spectral(float d_nm, float cos_theta, float n_film, float intensity, const float *wl, int n_lambda,
+                            float rgb[3])
+{
+    thin_film_spectral(d_nm, cos_theta, n_film, intensity, wl, n_lambda, rgb);
+    for (int k = 0; k < 3; ++k) rgb[k] = rgb[k] < 0.f ? 0.f : (rgb[k] > 1.f ? 1.f : rgb[k]);
+}
+
 void orc_thin_film_interference(float d_nm, float cos_theta, float n_film, float intensity, float rgb[3])
 {
     thin_film_spectral(d_nm, cos_theta, n_film, intensity, LUT_WL7, 7, rgb);
@@ -760,6 +769,32 @@ double orc_view_cos(double theta, double phi, double radius, const double cam[3]
     double len = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
     double d = (v[0] * n[0] + v[1] * n[1] + v[2] * n[2]) / len;
     return fabs(d);
+}
+
+/* per-cell spectral colour of a field band (the view cosine as in orc_shade_field): RGBA8 by round(255 x) or 3 floats */
+void orc_shade_field_spectral(const double *h, int num_theta, int num_phi, int row0, int num_rows, double radius,
+                              const double cam[3], float n_film, float intensity, const float *wl, int n_lambda,
+                              uint8_t *out_rgba, float *out_rgb, int nthreads)
+{
+    const double dth = M_PI / (double)(num_theta - 1), dph = 2.0 * M_PI / (double)num_phi;
+    if (nthreads < 1) nthreads = 1;
+#pragma omp parallel for schedule(static) num_threads(nthreads)
+    for (int r = 0; r < num_rows; ++r) {
+        const double theta = (double)(row0 + r) * dth;
+        for (int j = 0; j < num_phi; ++j) {
+            const size_t idx = (size_t)r * (size_t)num_phi + (size_t)j;
+            const double c = orc_view_cos(theta, (double)j * dph, radius, cam);
+            float f[3];
+            orc_thin_film_spectral((float)(h[idx] * 1e9), (float)c, n_film, intensity, wl, n_lambda, f);
+            if (out_rgb) { out_rgb[3 * idx] = f[0]; out_rgb[3 * idx + 1] = f[1]; out_rgb[3 * idx + 2] = f[2]; }
+            if (out_rgba) {
+                double d[3] = {f[0], f[1], f[2]};
+                uint8_t px[3];
+                orc_rgb_to_u8(d, px);
+                out_rgba[4 * idx] = px[0]; out_rgba[4 * idx + 1] = px[1]; out_rgba[4 * idx + 2] = px[2]; out_rgba[4 * idx + 3] = 255;
+            }
+        }
+    }
 }
 
 void orc_shade_field(const double *h, int num_theta, int num_phi, int row0, int num_rows, double radius,

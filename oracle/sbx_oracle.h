@@ -173,6 +173,12 @@ double orc_view_cos(double theta, double phi, double radius, const double cam[3]
  * fused colour stage: per cell view cosine as orc_view_cos, then mode 1 = orc_lut_shade (bubble.wgsl:425-439; mode 4 = the same with 8-bit filter weights)
  * or mode 2/3 = orc_interference_color / _linear (interference.rs:380-426); RGBA8 via round(255 x), A=255
  * (interference.rs:73-79).  row0/num_rows select a band of the global grid; OpenMP over rows. */
+/* thin_film_interference of the fragment shaders (bubble_instanced.wgsl:190-218): per-pixel spectral colour, clamped */
+void orc_thin_film_spectral(float d_nm, float cos_theta, float n_film, float intensity, const float *wavelengths_nm,
+                            int n_lambda, float rgb[3]);
+void orc_shade_field_spectral(const double *h, int num_theta, int num_phi, int row0, int num_rows, double radius,
+                              const double cam[3], float n_film, float intensity, const float *wavelengths_nm,
+                              int n_lambda, uint8_t *out_rgba, float *out_rgb, int nthreads);
 void orc_shade_field(const double *h, int num_theta, int num_phi, int row0, int num_rows, double radius,
                      const double cam[3], double n_film, const uint8_t *lut_rgba, int T, int A, float max_nm,
                      float intensity, int mode, uint8_t *out_rgba, int nthreads);

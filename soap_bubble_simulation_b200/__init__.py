@@ -2,7 +2,7 @@
 pjt222/soap_bubble_simulation.  Host-side mirrors of the reference API over the C ABI in include/sbx.h."""
 from . import _lib, shader_code
 from ._lib import (F32, F64, OUT_RGB_F32, OUT_RGBA8, PREC_F32, PREC_F64, PREC_F64_STRICT, RGB_EXACT3,
-                   RGB_EXACT3_LINEAR, RGB_LUT, RGB_NONE, RGB_SCHLICK_TWO_BEAM, RGB_SCHLICK_WALL, SEM_CPU, SEM_WGSL, SbxError)
+                   RGB_EXACT3_LINEAR, RGB_LUT, RGB_NONE, RGB_SCHLICK_TWO_BEAM, RGB_SCHLICK_WALL, RGB_SPECTRAL, SEM_CPU, SEM_WGSL, SbxError)
 from .config import (BubbleParameters, ConfigError, EnvironmentParameters, FluidParameters,
                      SimulationConfig)
 from .drainage import DrainageSimulator, ThicknessField, View, camera_position

@@ -18,10 +18,10 @@ ERR_INVALID, ERR_CUDA, ERR_NOMEM, ERR_UNSUPPORTED, ERR_COMM, ERR_IO = -1, -2, -3
 SEM_CPU, SEM_WGSL = 0, 1
 PREC_F32, PREC_F64, PREC_F64_STRICT = 0, 1, 2
 F32, F64 = 0, 1
-RGB_NONE, RGB_LUT, RGB_EXACT3, RGB_EXACT3_LINEAR, RGB_SCHLICK_WALL, RGB_SCHLICK_TWO_BEAM = 0, 1, 2, 3, 4, 5
+RGB_NONE, RGB_LUT, RGB_EXACT3, RGB_EXACT3_LINEAR, RGB_SCHLICK_WALL, RGB_SCHLICK_TWO_BEAM, RGB_SPECTRAL = 0, 1, 2, 3, 4, 5, 6
 OUT_RGBA8, OUT_RGB_F32 = 0, 1
 PTR_THICKNESS, PTR_CONCENTRATION, PTR_RGB, PTR_CAUSTICS = 0, 1, 2, 3
-IPC_BYTES = 256
+IPC_BYTES = 512
 
 
 class SbxError(RuntimeError):
@@ -128,6 +128,7 @@ _SIGS = {
     "sbx_drainage_set_physics": [C.c_void_p] + [C.c_double] * 6,
     "sbx_drainage_device_ptr": [C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)],
     "sbx_drainage_set_lut": [C.c_void_p, C.c_void_p, C.c_int32, C.c_int32, C.c_float],
+    "sbx_drainage_set_spectrum": [C.c_void_p, C.POINTER(C.c_float), C.c_int32],
     "sbx_drainage_launch_count": [C.c_void_p, C.POINTER(C.c_int64)],
     "sbx_caustic_params_default": [C.POINTER(CausticParamsC)],
     "sbx_drainage_caustics": [C.c_void_p, C.POINTER(CausticParamsC), C.c_void_p],

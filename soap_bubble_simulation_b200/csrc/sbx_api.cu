@@ -93,6 +93,8 @@ struct sbx_drainage {
 
     cudaStream_t own_stream = nullptr, stream = nullptr;
     cudaStream_t copy_in = nullptr, copy_out = nullptr;  // host-pipelined step: H2D / D2H engines
+    cudaStream_t halo_stream = nullptr;                  // NCCL halo path: boundary bands + exchange beside the interior
+    cudaEvent_t ev_prev = nullptr, ev_halo = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_comp;
     cudaEvent_t ev_start = nullptr, ev_out = nullptr, ev_all = nullptr;
     bool ghost_stale = false;  // sharded host-buffer step: the ghost rows of the current buffer were not refreshed
@@ -162,12 +164,17 @@ struct sbx_drainage {
     float lut_max_nm = 2000.f;
     bool lut_user = false;
 
+    float4 *spec_dev = nullptr;  // SBX_RGB_SPECTRAL wavelength table
+    int n_spec = 0;
+    float spec_n_film = -1.f;
+    std::vector<float> spec_wl;
     float *caustic_buf = nullptr;
     sbx_comm *comm = nullptr;
     // peer-memory halo push
     bool peer_enabled = false;
     unsigned long long *sync_dev = nullptr;  // [0] flag from up, [1] flag from down, [2],[3] band counters, [4] status
     void *peer_up_buf[2] = {nullptr, nullptr}, *peer_dn_buf[2] = {nullptr, nullptr};
+    void *peer_up_conc[2] = {nullptr, nullptr}, *peer_dn_conc[2] = {nullptr, nullptr};  // WGSL: concentration buffers
     unsigned long long *peer_up_sync = nullptr, *peer_dn_sync = nullptr;
     int peer_up_rows = 0;
     unsigned long long epoch = 0;
@@ -216,11 +223,14 @@ static void free_all(sbx_drainage *h)
     for (int i = 0; i < 2; ++i) {
         if (h->peer_up_buf[i]) cudaIpcCloseMemHandle(h->peer_up_buf[i]);
         if (h->peer_dn_buf[i]) cudaIpcCloseMemHandle(h->peer_dn_buf[i]);
+        if (h->peer_up_conc[i]) cudaIpcCloseMemHandle(h->peer_up_conc[i]);
+        if (h->peer_dn_conc[i]) cudaIpcCloseMemHandle(h->peer_dn_conc[i]);
     }
     if (h->peer_up_sync) cudaIpcCloseMemHandle(h->peer_up_sync);
     if (h->peer_dn_sync) cudaIpcCloseMemHandle(h->peer_dn_sync);
     cudaFree(h->sync_dev);
     cudaFree(h->caustic_buf);
+    cudaFree(h->spec_dev);
     if (h->mm_host) cudaFreeHost(h->mm_host);
     if (h->scalar_host) cudaFreeHost(h->scalar_host);
     if (h->lut_tex) cudaDestroyTextureObject(h->lut_tex);
@@ -228,6 +238,9 @@ static void free_all(sbx_drainage *h)
     if (h->own_stream) cudaStreamDestroy(h->own_stream);
     if (h->copy_in) cudaStreamDestroy(h->copy_in);
     if (h->copy_out) cudaStreamDestroy(h->copy_out);
+    if (h->halo_stream) cudaStreamDestroy(h->halo_stream);
+    if (h->ev_prev) cudaEventDestroy(h->ev_prev);
+    if (h->ev_halo) cudaEventDestroy(h->ev_halo);
     for (auto e : h->ev_in) cudaEventDestroy(e);
     for (auto e : h->ev_comp) cudaEventDestroy(e);
     if (h->ev_start) cudaEventDestroy(h->ev_start);
@@ -734,13 +747,43 @@ static void tfe_table(const sbx_drainage *h, FrontTable &ft)
 }
 
 // ------------------------------------------------------------------ colour stage set-up
+static const float kLutWl7[7] = {400.f, 450.f, 500.f, 550.f, 600.f, 650.f, 700.f};  // interference_lut.rs:52
 static int32_t ensure_lut(sbx_drainage *h, float n_film);
+
+// per-wavelength table of SBX_RGB_SPECTRAL: {2 pi / lambda, w} with w = M cie(lambda) / n -- the CIE Gaussian fit
+// (interference_lut.rs:136-148), the XYZ -> linear sRGB matrix (:158-163) and the 1 / n normalisation (:81-83),
+// evaluated in f32 like the reference and folded once on the host
+static int32_t ensure_spectrum(sbx_drainage *h)
+{
+    if (h->spec_dev && h->n_spec == (int)h->spec_wl.size()) return SBX_OK;
+    if (h->spec_wl.empty()) h->spec_wl.assign(kLutWl7, kLutWl7 + 7);
+    const int n = (int)h->spec_wl.size();
+    std::vector<float4> tab((size_t)n);
+    auto gauss = [](float x, float mean, float sigma) { const float t = (x - mean) / sigma; return expf(-0.5f * t * t); };
+    for (int k = 0; k < n; ++k) {
+        const float wl = h->spec_wl[k];
+        const float x = fmaxf(1.056f * gauss(wl, 599.8f, 37.9f) + 0.362f * gauss(wl, 442.0f, 16.0f) - 0.065f * gauss(wl, 501.1f, 20.4f), 0.0f);
+        const float y = fmaxf(0.821f * gauss(wl, 568.8f, 46.9f) + 0.286f * gauss(wl, 530.9f, 31.1f), 0.0f);
+        const float z = fmaxf(1.217f * gauss(wl, 437.0f, 11.8f) + 0.681f * gauss(wl, 459.0f, 26.0f), 0.0f);
+        const float inv_n = 1.0f / (float)n;
+        tab[k] = make_float4((float)(2.0 * M_PI / (double)wl),
+                             (3.2404542f * x - 1.5371385f * y - 0.4985314f * z) * inv_n,
+                             (-0.969266f * x + 1.8760108f * y + 0.0415560f * z) * inv_n,
+                             (0.0556434f * x - 0.2040259f * y + 1.0572252f * z) * inv_n);
+    }
+    CU(cudaStreamSynchronize(h->stream));
+    if (h->spec_dev) { CU(cudaFree(h->spec_dev)); h->spec_dev = nullptr; }
+    CU(cudaMalloc(&h->spec_dev, (size_t)n * sizeof(float4)));
+    CU(cudaMemcpy(h->spec_dev, tab.data(), (size_t)n * sizeof(float4), cudaMemcpyHostToDevice));
+    h->n_spec = n;
+    return SBX_OK;
+}
 
 static int32_t prepare_rgb(sbx_drainage *h, const sbx_view *v, RgbArgs &r)
 {
     memset(&r, 0, sizeof r);
     if (!v || v->mode == SBX_RGB_NONE) { r.mode = SBX_RGB_NONE; return SBX_OK; }
-    if (v->mode < SBX_RGB_NONE || v->mode > SBX_RGB_SCHLICK_TWO_BEAM) return fail(SBX_ERR_INVALID, "bad rgb mode %d", v->mode);
+    if (v->mode < SBX_RGB_NONE || v->mode > SBX_RGB_SPECTRAL) return fail(SBX_ERR_INVALID, "bad rgb mode %d", v->mode);
     if (v->format != SBX_OUT_RGBA8 && v->format != SBX_OUT_RGB_F32) return fail(SBX_ERR_INVALID, "bad rgb format %d", v->format);
     if (!(v->n_film > 0.0)) return fail(SBX_ERR_INVALID, "n_film must be > 0");
     const size_t cells = (size_t)h->batch * h->rows_local * h->num_phi;
@@ -760,6 +803,12 @@ static int32_t prepare_rgb(sbx_drainage *h, const sbx_view *v, RgbArgs &r)
         int32_t rc = ensure_lut(h, (float)v->n_film);
         if (rc != SBX_OK) return rc;
     }
+    if (v->mode == SBX_RGB_SPECTRAL) {
+        int32_t rc = ensure_spectrum(h);
+        if (rc != SBX_OK) return rc;
+        r.spec = h->spec_dev;
+        r.n_spec = h->n_spec;
+    }
     r.mode = v->mode;
     r.format = v->format;
     r.out = h->rgb_buf;
@@ -778,6 +827,9 @@ static int32_t prepare_rgb(sbx_drainage *h, const sbx_view *v, RgbArgs &r)
     r.omr0 = 1.0f - r.r0;
     const double wl[3] = {650.0, 532.0, 450.0};  // interference.rs:26-30
     for (int k = 0; k < 3; ++k) { r.two_n_over_wl[k] = 2.0 * v->n_film / wl[k]; r.inv_wl_f[k] = (float)(1.0 / wl[k]); r.two_pi_over_wl_f[k] = (float)(2.0 * M_PI / wl[k]); }
+    r.inv_n2_hi = (float)r.inv_n2_d;
+    r.inv_n2_lo = (float)(r.inv_n2_d - (double)r.inv_n2_hi);
+    for (int k = 0; k < 3; ++k) { r.w_hi[k] = (float)r.two_n_over_wl[k]; r.w_lo[k] = (float)(r.two_n_over_wl[k] - (double)r.w_hi[k]); }
     return SBX_OK;
 }
 
@@ -805,7 +857,6 @@ static int32_t install_lut(sbx_drainage *h, const uint8_t *dev_or_host, bool on_
     return SBX_OK;
 }
 
-static const float kLutWl7[7] = {400.f, 450.f, 500.f, 550.f, 600.f, 650.f, 700.f};  // interference_lut.rs:52
 
 static int32_t build_lut_device(float n, float intensity, const float *wl, int nl, int T, int A, float max_nm,
                                 uint8_t **dev_out, cudaStream_t st)
@@ -897,6 +948,30 @@ static void fill_step_args(sbx_drainage *h, StepArgs<T> &a, double dt, const Rgb
     a.l2_keep_edges = h->l2_keep_edges ? 1 : 0;
 }
 
+// arguments of the in-kernel halo push for the step that writes ping-pong half 1 - cur (every rank writes the same
+// half in the same step); element size = the handle's storage type
+static void fill_peer(sbx_drainage *h, PeerArgs &p)
+{
+    p.enabled = 1;
+    p.epoch = ++h->epoch;
+    const size_t N = (size_t)h->num_phi;
+    const int o = 1 - h->cur;
+    const size_t up_off = (size_t)(h->peer_up_rows + 1) * N;  // the up neighbour's bottom ghost row
+    p.up_ghost = h->peer_up_buf[o] ? (char *)h->peer_up_buf[o] + up_off * h->esz : nullptr;
+    p.dn_ghost = h->peer_dn_buf[o] ? h->peer_dn_buf[o] : nullptr;
+    p.up_ghost2 = h->peer_up_conc[o] ? (char *)h->peer_up_conc[o] + up_off * 4 : nullptr;
+    p.dn_ghost2 = h->peer_dn_conc[o] ? h->peer_dn_conc[o] : nullptr;
+    p.up_flag_remote = h->peer_up_sync ? h->peer_up_sync + 1 : nullptr;  // I am its lower neighbour
+    p.dn_flag_remote = h->peer_dn_sync ? h->peer_dn_sync + 0 : nullptr;  // I am its upper neighbour
+    p.flag_from_up = h->sync_dev + 0;
+    p.flag_from_dn = h->sync_dev + 1;
+    p.done_first = (unsigned int *)(h->sync_dev + 2);
+    p.done_last = (unsigned int *)(h->sync_dev + 3);
+    p.status = (unsigned int *)(h->sync_dev + 4);
+    p.push_up_grow = p.up_ghost ? h->row_begin : -1;
+    p.push_dn_grow = p.dn_ghost ? h->row_end - 1 : -1;
+}
+
 // decide whether this launch writes the pole rows inside the TMA kernel, and which arrival count it waits for.
 // The host-side count is committed only after the launch has been accepted (commit_pole_fold): a failed launch
 // must not leave the device counters one round behind what every later step would wait for.
@@ -949,24 +1024,9 @@ static int32_t step_cpu_sem(sbx_drainage *h, double dt, const RgbArgs &rgb)
         a.fronts = ft;
         bool pushed = false;
         set_pole_fold<T>(h, a, has_top, has_bottom);
-        if constexpr (sizeof(T) == 4) {
+        {
             if (h->peer_enabled && h->use_tma && march_tma_supported<T>(a)) {
-                PeerArgs &p = a.peer;
-                p.enabled = 1;
-                p.epoch = ++h->epoch;
-                const size_t N = (size_t)h->num_phi;
-                const int o = 1 - h->cur;  // every rank writes the same ping-pong half in the same step
-                p.up_ghost = h->peer_up_buf[o] ? (float *)h->peer_up_buf[o] + (size_t)(h->peer_up_rows + 1) * N : nullptr;
-                p.dn_ghost = h->peer_dn_buf[o] ? (float *)h->peer_dn_buf[o] : nullptr;
-                p.up_flag_remote = h->peer_up_sync ? h->peer_up_sync + 1 : nullptr;  // I am its lower neighbour
-                p.dn_flag_remote = h->peer_dn_sync ? h->peer_dn_sync + 0 : nullptr;  // I am its upper neighbour
-                p.flag_from_up = h->sync_dev + 0;
-                p.flag_from_dn = h->sync_dev + 1;
-                p.done_first = (unsigned int *)(h->sync_dev + 2);
-                p.done_last = (unsigned int *)(h->sync_dev + 3);
-                p.status = (unsigned int *)(h->sync_dev + 4);
-                p.push_up_grow = p.up_ghost ? h->row_begin : -1;
-                p.push_dn_grow = p.dn_ghost ? h->row_end - 1 : -1;
+                fill_peer(h, a.peer);
                 pushed = true;
             }
         }
@@ -978,6 +1038,58 @@ static int32_t step_cpu_sem(sbx_drainage *h, double dt, const RgbArgs &rgb)
             a.mm_cur = h->mm_track[set];
             a.mm_next = h->mm_track[1 - set];
             h->mm_track_set = set;
+        }
+        // NCCL halo path (the modes the peer push does not cover, or SBX halo = nccl): boundary first.  The bands next
+        // to a neighbour run on a second, high-priority stream and their rows are exchanged there with ncclSend/ncclRecv
+        // while the interior bands run on the handle's stream; the step ends when both are done.
+        const int edge = 32;  // rows of a boundary launch
+        const bool up_nb = h->comm && h->row_begin > 0, dn_nb = h->comm && h->row_end < h->num_theta;
+        if (!pushed && (up_nb || dn_nb) && h->batch == 1 && !tracked && a.l_last - a.l_first + 1 >= 4 * edge &&
+            !getenv("SBX_NO_BOUNDARY_FIRST")) {
+            if (!h->halo_stream) {
+                int lo = 0, hi = 0;
+                CU(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+                CU(cudaStreamCreateWithPriority(&h->halo_stream, cudaStreamNonBlocking, hi));
+                CU(cudaEventCreateWithFlags(&h->ev_prev, cudaEventDisableTiming));
+                CU(cudaEventCreateWithFlags(&h->ev_halo, cudaEventDisableTiming));
+            }
+            CU(cudaEventRecord(h->ev_prev, h->stream));
+            CU(cudaStreamWaitEvent(h->halo_stream, h->ev_prev, 0));
+            const int lf = a.l_first, ll = a.l_last;
+            int int_first = lf, int_last = ll;
+            auto launch_part = [&](int p_first, int p_last, cudaStream_t st) -> int32_t {
+                StepArgs<T> ap = a;
+                ap.l_first = p_first;
+                ap.l_last = p_last;
+                // the pole rows are written by the launch that holds the ring next to them
+                const bool top = has_top && p_first == lf, bottom = has_bottom && p_last == ll;
+                set_pole_fold<T>(h, ap, top, bottom);
+                CU(launch_step<T>(ap, 1, ft.count > 0, false, top, bottom, h->band_rows, h->use_tma, st, &n));
+                commit_pole_fold<T>(h, ap);
+                return SBX_OK;
+            };
+            int32_t rc = SBX_OK;
+            if (up_nb) { rc = launch_part(lf, lf + edge - 1, h->halo_stream); int_first = lf + edge; }
+            if (rc == SBX_OK && dn_nb) { rc = launch_part(ll - edge + 1, ll, h->halo_stream); int_last = ll - edge; }
+            if (rc != SBX_OK) return rc;
+            h->cur = 1 - h->cur;
+            {   // exchange the new boundary rows on the halo stream
+                cudaStream_t keep = h->stream;
+                h->stream = h->halo_stream;
+                rc = halo_exchange(h);
+                h->stream = keep;
+                if (rc != SBX_OK) return rc;
+            }
+            CU(cudaEventRecord(h->ev_halo, h->halo_stream));
+            h->cur = 1 - h->cur;
+            rc = launch_part(int_first, int_last, h->stream);
+            if (rc != SBX_OK) return rc;
+            CU(cudaStreamWaitEvent(h->stream, h->ev_halo, 0));
+            h->cur = 1 - h->cur;
+            h->mm_kernel_valid = false;
+            h->launches += n;
+            h->time += dt;
+            return SBX_OK;
         }
         CU(launch_step<T>(a, h->batch, ft.count > 0, false, has_top, has_bottom, h->band_rows, h->use_tma, h->stream, &n));
         commit_pole_fold<T>(h, a);
@@ -1024,6 +1136,8 @@ static int32_t step_wgsl_sem(sbx_drainage *h, double dt, const RgbArgs &rgb)
     fill_wgsl_args(h, a, rgb);
     int n = 0;
     a.l2_keep_edges = h->l2_keep_edges ? 1 : 0;
+    const bool pushed = h->peer_enabled && h->use_tma && wgsl_tma_supported(a);
+    if (pushed) fill_peer(h, a.peer);
     CU(launch_wgsl(a, h->batch, h->band_rows, h->use_tma, h->stream, &n));
     if (rgb.mode != SBX_RGB_NONE && (h->row_begin == 0 || h->row_end == h->num_theta)) {
         // frozen pole rows still need their colour: shade them from the (unchanged) pole values
@@ -1036,6 +1150,7 @@ static int32_t step_wgsl_sem(sbx_drainage *h, double dt, const RgbArgs &rgb)
     h->cur = 1 - h->cur;
     h->launches += n;
     h->time += dt;  // gpu_drainage.rs:368
+    if (pushed) return SBX_OK;  // ghost rows of both fields were filled by the neighbours' kernels
     return halo_exchange(h);
 }
 
@@ -1048,8 +1163,9 @@ static bool resident_possible(const sbx_drainage *h)
 
 constexpr int kResidentChunk = 1024;
 
+// `rgb` (mode != NONE): the last launch of the call also writes the colour frame of the final field
 template <typename T>
-static int32_t steps_resident(sbx_drainage *h, double dt, int nsteps, int *taken)
+static int32_t steps_resident(sbx_drainage *h, double dt, int nsteps, int *taken, const RgbArgs &rgb)
 {
     *taken = 0;
     RgbArgs none;
@@ -1100,6 +1216,7 @@ static int32_t steps_resident(sbx_drainage *h, double dt, int nsteps, int *taken
         } else {
             for (int s = 0; s < n; ++s) h->time += dt;
         }
+        if (n == nsteps) a.rgb = rgb;  // last launch: colour epilogue
         CU(launch_resident<T>(a, h->batch, h->strict, tabs, n, h->stream));
         h->launches++;
         *taken += n;
@@ -1108,13 +1225,11 @@ static int32_t steps_resident(sbx_drainage *h, double dt, int nsteps, int *taken
     return SBX_OK;
 }
 
-static int32_t steps_resident_wgsl(sbx_drainage *h, double dt, int nsteps, int *taken)
+static int32_t steps_resident_wgsl(sbx_drainage *h, double dt, int nsteps, int *taken, const RgbArgs &rgb)
 {
     *taken = 0;
-    RgbArgs none;
-    memset(&none, 0, sizeof none);
     WgslArgs a;
-    fill_wgsl_args(h, a, none);
+    fill_wgsl_args(h, a, rgb);
     if (!resident_possible(h) || nsteps < 2 || resident_cluster_wgsl(a, h->batch) == 0) return SBX_OK;
     CU(launch_resident_wgsl(a, h->batch, nsteps, h->stream));  // in place on the current buffers
     for (int s = 0; s < nsteps; ++s) h->time += dt;             // gpu_drainage.rs:368
@@ -1122,6 +1237,8 @@ static int32_t steps_resident_wgsl(sbx_drainage *h, double dt, int nsteps, int *
     *taken = nsteps;
     return SBX_OK;
 }
+
+static int32_t shade_current(sbx_drainage *h, const RgbArgs &rgb);
 
 static int32_t do_steps(sbx_drainage *h, double dt, int32_t nsteps, const sbx_view *view)
 {
@@ -1138,12 +1255,21 @@ static int32_t do_steps(sbx_drainage *h, double dt, int32_t nsteps, const sbx_vi
     RgbArgs rgb;
     rc = prepare_rgb(h, view, rgb);
     if (rc != SBX_OK) return rc;
+    // SBX_RGB_SPECTRAL is a colour pass of its own (SFU-bound, ~10x the step): steps run without a colour stage
+    const bool colour_pass_after = rgb.mode == SBX_RGB_SPECTRAL;
+    const RgbArgs rgb_after = rgb;
+    if (colour_pass_after) memset(&rgb, 0, sizeof rgb);
     // only the last step's colour frame is observable: the steps before it may run without the colour stage
-    const int plain = rgb.mode == SBX_RGB_NONE ? nsteps : nsteps - 1;
+    // ... unless the resident kernels can shade the final field themselves (one launch for the whole call)
+    const bool epilogue = rgb.mode != SBX_RGB_NONE && resident_shades(rgb);
+    const int plain = rgb.mode == SBX_RGB_NONE || epilogue ? nsteps : nsteps - 1;
     if (plain >= 2) {
         int taken = 0;
-        rc = h->wgsl ? steps_resident_wgsl(h, dt, plain, &taken)
-                     : (h->f64 ? steps_resident<double>(h, dt, plain, &taken) : steps_resident<float>(h, dt, plain, &taken));
+        RgbArgs none;
+        memset(&none, 0, sizeof none);
+        const RgbArgs &last = epilogue ? rgb : none;
+        rc = h->wgsl ? steps_resident_wgsl(h, dt, plain, &taken, last)
+                     : (h->f64 ? steps_resident<double>(h, dt, plain, &taken, last) : steps_resident<float>(h, dt, plain, &taken, last));
         if (rc != SBX_OK) return rc;
         nsteps -= taken;
     }
@@ -1151,6 +1277,7 @@ static int32_t do_steps(sbx_drainage *h, double dt, int32_t nsteps, const sbx_vi
         rc = h->wgsl ? step_wgsl_sem(h, dt, rgb) : (h->f64 ? step_cpu_sem<double>(h, dt, rgb) : step_cpu_sem<float>(h, dt, rgb));
         if (rc != SBX_OK) return rc;
     }
+    if (colour_pass_after) return shade_current(h, rgb_after);
     return SBX_OK;
 }
 
@@ -1176,6 +1303,12 @@ extern "C" int32_t sbx_drainage_shade(sbx_drainage *h, const sbx_view *view)
     RgbArgs rgb;
     rc = prepare_rgb(h, view, rgb);
     if (rc != SBX_OK) return rc;
+    return shade_current(h, rgb);
+}
+
+// colour frame of the current field (all owned rows)
+static int32_t shade_current(sbx_drainage *h, const RgbArgs &rgb)
+{
     int n = 0;
     if (h->f64) {
         StepArgs<double> s;
@@ -1338,6 +1471,7 @@ extern "C" int32_t sbx_drainage_step_host(sbx_drainage *h, double dt, int32_t ns
     CHECK_H(h);
     int32_t rc = SBX_OK;
     if (host_in && nsteps == 1 && !h->wgsl && !h->f64 && h->batch == 1 && h->href_zero &&
+        !(view && view->mode == SBX_RGB_SPECTRAL) &&
         in_dtype == SBX_F32 && (!host_out_h || out_dtype == SBX_F32) && h->num_phi % 4 == 0 && h->rows_local >= 8 &&
         !getenv("SBX_NO_HOST_PIPELINE"))
         return step_host_pipelined(h, dt, view, (const float *)host_in, (float *)host_out_h, host_out_rgb);
@@ -1628,6 +1762,17 @@ extern "C" int32_t sbx_drainage_device_ptr(sbx_drainage *h, int32_t kind, void *
         return SBX_OK;
     }
     return fail(SBX_ERR_INVALID, "bad pointer kind %d", kind);
+}
+
+extern "C" int32_t sbx_drainage_set_spectrum(sbx_drainage *h, const float *wl, int32_t n)
+{
+    if (!h || !wl) return fail(SBX_ERR_INVALID, "null argument");
+    if (n < 1 || n > 256) return fail(SBX_ERR_INVALID, "n must be in [1,256] (got %d)", n);
+    for (int k = 0; k < n; ++k)
+        if (!(wl[k] > 0.f) || !std::isfinite(wl[k])) return fail(SBX_ERR_INVALID, "wavelength %d is not a positive number", k);
+    h->spec_wl.assign(wl, wl + n);
+    h->n_spec = -1;  // rebuilt on next use
+    return SBX_OK;
 }
 
 extern "C" int32_t sbx_drainage_launch_count(sbx_drainage *h, int64_t *out)
@@ -2078,8 +2223,9 @@ extern "C" int32_t sbx_drainage_attach_comm(sbx_drainage *h, sbx_comm *c)
 
 struct IpcBlob {
     cudaIpcMemHandle_t buf[2];
+    cudaIpcMemHandle_t conc[2];  // SBX_SEM_WGSL only
     cudaIpcMemHandle_t sync;
-    int32_t rows_local, num_phi, esz, magic;
+    int32_t rows_local, num_phi, esz, magic, wgsl, pad[3];
 };
 static_assert(sizeof(IpcBlob) <= SBX_IPC_BYTES, "IPC blob too large");
 
@@ -2092,6 +2238,11 @@ extern "C" int32_t sbx_drainage_ipc_export(sbx_drainage *h, uint8_t out[SBX_IPC_
     CU(cudaIpcGetMemHandle(&b.buf[0], h->buf[0]));
     CU(cudaIpcGetMemHandle(&b.buf[1], h->buf[1]));
     CU(cudaIpcGetMemHandle(&b.sync, h->sync_dev));
+    if (h->wgsl) {
+        CU(cudaIpcGetMemHandle(&b.conc[0], h->conc[0]));
+        CU(cudaIpcGetMemHandle(&b.conc[1], h->conc[1]));
+    }
+    b.wgsl = h->wgsl ? 1 : 0;
     b.rows_local = h->rows_local;
     b.num_phi = h->num_phi;
     b.esz = (int32_t)h->esz;
@@ -2105,15 +2256,18 @@ extern "C" int32_t sbx_drainage_ipc_attach(sbx_drainage *h, const uint8_t *up, c
 {
     CHECK_H(h);
     if (!h->comm) return fail(SBX_ERR_INVALID, "attach a communicator first (sbx_drainage_attach_comm)");
-    if (h->wgsl || h->f64 || h->batch != 1) return fail(SBX_ERR_UNSUPPORTED, "peer halo push covers the f32 CPU-semantics fast path, one bubble");
+    if (h->strict || h->batch != 1)
+        return fail(SBX_ERR_UNSUPPORTED, "peer halo push covers the TMA ring kernels (f32 / f64 CPU semantics, WGSL semantics), one bubble");
     if ((up == nullptr) != (h->row_begin == 0) || (down == nullptr) != (h->row_end == h->num_theta))
         return fail(SBX_ERR_INVALID, "neighbour blobs do not match this band's position");
-    auto open_one = [&](const uint8_t *blob, void *bufs[2], unsigned long long **sync, int *rows) -> int32_t {
+    auto open_one = [&](const uint8_t *blob, void *bufs[2], void *concs[2], unsigned long long **sync, int *rows) -> int32_t {
         IpcBlob b;
         memcpy(&b, blob, sizeof b);
-        if (b.magic != 0x53425831 || b.num_phi != h->num_phi || b.esz != (int32_t)h->esz)
+        if (b.magic != 0x53425831 || b.num_phi != h->num_phi || b.esz != (int32_t)h->esz || b.wgsl != (h->wgsl ? 1 : 0))
             return fail(SBX_ERR_INVALID, "neighbour blob is not a matching libsbx band");
         for (int i = 0; i < 2; ++i) CU(cudaIpcOpenMemHandle(&bufs[i], b.buf[i], cudaIpcMemLazyEnablePeerAccess));
+        if (h->wgsl)
+            for (int i = 0; i < 2; ++i) CU(cudaIpcOpenMemHandle(&concs[i], b.conc[i], cudaIpcMemLazyEnablePeerAccess));
         void *s = nullptr;
         CU(cudaIpcOpenMemHandle(&s, b.sync, cudaIpcMemLazyEnablePeerAccess));
         *sync = (unsigned long long *)s;
@@ -2121,8 +2275,8 @@ extern "C" int32_t sbx_drainage_ipc_attach(sbx_drainage *h, const uint8_t *up, c
         return SBX_OK;
     };
     int32_t rc = SBX_OK;
-    if (up) rc = open_one(up, h->peer_up_buf, &h->peer_up_sync, &h->peer_up_rows);
-    if (rc == SBX_OK && down) rc = open_one(down, h->peer_dn_buf, &h->peer_dn_sync, nullptr);
+    if (up) rc = open_one(up, h->peer_up_buf, h->peer_up_conc, &h->peer_up_sync, &h->peer_up_rows);
+    if (rc == SBX_OK && down) rc = open_one(down, h->peer_dn_buf, h->peer_dn_conc, &h->peer_dn_sync, nullptr);
     if (rc != SBX_OK) return rc;
     CU(cudaStreamSynchronize(h->stream));
     h->peer_enabled = true;

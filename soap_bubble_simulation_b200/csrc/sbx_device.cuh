@@ -215,6 +215,52 @@ __device__ __forceinline__ Phase3 phase3(double d_nm, float ci, const RgbArgs &a
     return p;
 }
 
+// The same phase without f64: float-float (hi + lo pairs of f32) arithmetic on the FP32 pipe.  On this part a cell's
+// f64 phase costs ~25 half-rate DP operations plus ~10 f32<->f64 conversions on the quarter-rate pipe the SFU ops
+// share; the pairs below are ~60 full-rate f32 operations, exact products through FMA residuals (Dekker / Knuth
+// two-sum, two-product), ~2^-45 relative on the cycle count.  __fmul_rn / __fadd_rn keep nvcc from contracting the
+// error-free transformations into FMAs.  Input: the STORED thickness h and its offset h_ref (f32 storage only).
+__device__ __forceinline__ Phase3 phase3_ff(float h, float href, float ci, const RgbArgs &a)
+{
+    // d = (h + h_ref) * 1e9 nm as a pair (1e9 is exact in f32)
+    const float s = __fadd_rn(h, href);
+    const float bb = __fsub_rn(s, h);
+    const float se = __fadd_rn(__fsub_rn(h, __fsub_rn(s, bb)), __fsub_rn(href, bb));
+    const float d_hi = __fmul_rn(s, 1e9f);
+    const float d_lo = fmaf(se, 1e9f, fmaf(s, 1e9f, -d_hi));
+    // x = 1 - (1 - ci^2) / n^2   (1 - sin^2(theta_t), interference.rs:199-210)
+    const float c2 = __fmul_rn(ci, ci), c2e = fmaf(ci, ci, -c2);
+    const float t = __fsub_rn(1.0f, c2);
+    const float tl = __fsub_rn(__fsub_rn(__fsub_rn(1.0f, t), c2), c2e);  // 1 >= ci^2: fast two-sum
+    const float m = __fmul_rn(t, a.inv_n2_hi);
+    const float ml = fmaf(tl, a.inv_n2_hi, fmaf(t, a.inv_n2_lo, fmaf(t, a.inv_n2_hi, -m)));
+    const float x = __fsub_rn(1.0f, m);
+    const float xl = __fsub_rn(__fsub_rn(__fsub_rn(1.0f, x), m), ml);
+    // cos(theta_t) = sqrt(x): one SFU reciprocal square root polished by a Newton step on the pair
+    const float rs = rsqrt_approx(fmaxf(x, 1e-30f));
+    const float c0 = __fmul_rn(x, rs);
+    const float q = __fmul_rn(c0, c0), qe = fmaf(c0, c0, -q);
+    const float res = __fadd_rn(__fsub_rn(__fsub_rn(x, q), qe), xl);
+    const float cl = __fmul_rn(res, 0.5f * rs);
+    // base = d * cos(theta_t)
+    const float b_hi = __fmul_rn(d_hi, c0);
+    const float b_lo = fmaf(d_lo, c0, fmaf(d_hi, cl, fmaf(d_hi, c0, -b_hi)));
+    Phase3 p;
+    p.ct = __fadd_rn(c0, cl);
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float P = __fmul_rn(b_hi, a.w_hi[k]);
+        const float E = fmaf(b_lo, a.w_hi[k], fmaf(b_hi, a.w_lo[k], fmaf(b_hi, a.w_hi[k], -P)));
+        const float r = __fsub_rn(__fadd_rn(P, 12582912.0f), 12582912.0f);  // rint(P) for |P| < 2^22 cycles
+        const float g = __fsub_rn(P, r);                                      // exact
+        const float y0 = __fsub_rn(0.5f, fabsf(g));                           // exact where it matters (|g| >= 1/4)
+        // y = 1/2 - |g + E| = y0 - sign(g) E: the tail joins after the cancellation, so y keeps relative accuracy at the zeros
+        const float Es = __uint_as_float(__float_as_uint(E) ^ (__float_as_uint(g) & 0x80000000u));
+        p.y[k] = __fsub_rn(y0, Es);
+    }
+    return p;
+}
+
 // sin^2(pi (cyc + 1/2)) = cos^2(pi fr) = sin^2(pi (1/2 - |fr|)): the lambda/2 reflection shift
 // (interference.rs:235-237) folded in without adding 0.5 to a rounded number
 __device__ __forceinline__ float fringe_sin2(float y)
@@ -227,10 +273,22 @@ __device__ __forceinline__ float fringe_sin2(float y)
 // Snell (197-211), exact Fresnel average (266-298), OPD with lambda/2 (226-238), multi-bounce Airy
 // (344-352) with 1 - cos(phi) = 2 sin^2(phi/2).  1 - R is formed without cancellation from the
 // transmittances: 1 - r_s^2 = 4 ci n ct / (ci + n ct)^2, 1 - r_p^2 = 4 n ci ct / (n ci + ct)^2.
+__device__ __forceinline__ void rgb_exact3_from_phase(const Phase3 &ph, bool positive, float ci, const RgbArgs &a, bool gamma,
+                                                      float rgb[3]);
 __device__ __forceinline__ void rgb_exact3(double d_nm, float ci, const RgbArgs &a, bool gamma, float rgb[3])
 {
     ci = fminf(fmaxf(ci, -1.f), 1.f);
-    const Phase3 ph = phase3(d_nm, ci, a);
+    rgb_exact3_from_phase(phase3(d_nm, ci, a), d_nm > 0.0, ci, a, gamma, rgb);
+}
+// f32 storage on the fast paths: the float-float phase from the stored value and its offset
+__device__ __forceinline__ void rgb_exact3_ff(float h, float href, float ci, const RgbArgs &a, bool gamma, float rgb[3])
+{
+    ci = fminf(fmaxf(ci, -1.f), 1.f);
+    rgb_exact3_from_phase(phase3_ff(h, href, ci, a), __fadd_rn(h, href) > 0.f, ci, a, gamma, rgb);
+}
+__device__ __forceinline__ void rgb_exact3_from_phase(const Phase3 &ph, bool positive, float ci, const RgbArgs &a, bool gamma,
+                                                      float rgb[3])
+{
     const float n = a.n_film, ct = ph.ct;
     const float ds = fmaf(n, ct, ci), dp = fmaf(n, ci, ct);
     const float inv = rcp_approx(ds * dp);
@@ -243,7 +301,7 @@ __device__ __forceinline__ void rgb_exact3(double d_nm, float ci, const RgbArgs 
         const float num = 4.f * R * fringe_sin2(ph.y[k]);
         const float den = omr2 + num;
         float I = den < 1e-30f ? R : num * rcp_approx(den);  // |den| < eps -> R, interference.rs:348-350
-        I = d_nm <= 0.0 ? 0.f : clamp01(I);                   // interference.rs:319-321
+        I = positive ? clamp01(I) : 0.f;                      // d <= 0 -> 0, interference.rs:319-321
         if (gamma) I = ex2_approx(lg2_approx(I) * (1.0f / 2.2f));  // powf(1/2.2); lg2(0) = -inf -> 0
         rgb[k] = clamp01(I);
     }
@@ -294,12 +352,54 @@ __device__ __forceinline__ void rgb_lut(float d_nm, float ci, const RgbArgs &a, 
     rgb[2] = clamp01(t.z * a.intensity);
 }
 
+// Direct spectral evaluation per cell (no LUT): thin_film_interference of the fragment shaders
+// (bubble_instanced.wgsl:190-218 == interference_lut.rs:45-93) over a.n_spec wavelengths.  Per wavelength the shader's
+// sin^2(phase / 2) with phase = 2 pi opd / lambda + pi is cos^2(pi opd / lambda) = (1 + cos(2 pi opd / lambda)) / 2, and
+// the colour-matching weights are folded with the XYZ -> sRGB matrix and the 1 / n normalisation on the host, so a
+// wavelength costs one SFU cosine, half an SFU reciprocal (two Airy denominators share one) and ~10 FP32 operations.
+// f32 like the shader; the order of the (linear) accumulation differs from it by rounding only.
+__device__ __forceinline__ void rgb_spectral(float d_nm, float ci, const RgbArgs &a, float rgb[3])
+{
+    const float sin_i = sqrt_approx(fmaxf(1.0f - ci * ci, 0.0f));          // snells_law, interference_lut.rs:96-100
+    const float sin_t = sin_i * rcp_approx(a.n_film);
+    const float ct = sqrt_approx(fmaxf(1.0f - sin_t * sin_t, 0.0f));
+    const float n2ct = a.n_film * ct, n2ci = a.n_film * ci;                // fresnel_unpolarized(ci, ct, 1, n), :103-120
+    const float rs = (ci - n2ct) * rcp_approx(fmaxf(ci + n2ct, 0.0001f));
+    const float rp = (n2ci - ct) * rcp_approx(fmaxf(n2ci + ct, 0.0001f));
+    const float R = (rs * rs + rp * rp) * 0.5f;
+    const float omr = fmaxf(1.0f - R, 0.001f);                             // airy_interference, :123-133
+    const float Fh = 2.0f * R * rcp_approx(omr * omr);                     // F / 2
+    const float opd = a.two_n * d_nm * ct;                                 // :61
+    float r = 0.f, g = 0.f, b = 0.f;
+    const float4 *sp = a.spec;
+    int k = 0;
+    for (; k + 1 < a.n_spec; k += 2) {
+        const float4 s0 = __ldg(sp + k), s1 = __ldg(sp + k + 1);
+        const float f0 = fmaf(Fh, __cosf(opd * s0.x), Fh), f1 = fmaf(Fh, __cosf(opd * s1.x), Fh);  // F sin^2
+        const float d0 = 1.0f + f0, d1 = 1.0f + f1;                        // >= 1: the shader's max(., 0.001) never binds
+        const float inv = rcp_approx(d0 * d1);
+        const float i0 = f0 * (inv * d1), i1 = f1 * (inv * d0);
+        r = fmaf(i0, s0.y, r); g = fmaf(i0, s0.z, g); b = fmaf(i0, s0.w, b);
+        r = fmaf(i1, s1.y, r); g = fmaf(i1, s1.z, g); b = fmaf(i1, s1.w, b);
+    }
+    if (k < a.n_spec) {
+        const float4 s0 = __ldg(sp + k);
+        const float f0 = fmaf(Fh, __cosf(opd * s0.x), Fh);
+        const float i0 = f0 * rcp_approx(1.0f + f0);
+        r = fmaf(i0, s0.y, r); g = fmaf(i0, s0.z, g); b = fmaf(i0, s0.w, b);
+    }
+    rgb[0] = clamp01(r * a.intensity);
+    rgb[1] = clamp01(g * a.intensity);
+    rgb[2] = clamp01(b * a.intensity);
+}
+
 // thickness in nm handed to the colour stage: f32 is enough for the LUT fetch, the analytic modes need
 // the f64 phase (see phase3)
 template <int MODE> struct Dnm { using type = double; };
 template <> struct Dnm<SBX_RGB_LUT> { using type = float; };
 template <> struct Dnm<SBX_RGB_NONE> { using type = float; };
 template <> struct Dnm<SBX_RGB_SCHLICK_TWO_BEAM> { using type = float; };
+template <> struct Dnm<SBX_RGB_SPECTRAL> { using type = float; };
 
 template <int MODE>
 __device__ __forceinline__ void rgb_eval(typename Dnm<MODE>::type d_nm, float ci, const RgbArgs &a, float rgb[3])
@@ -309,6 +409,7 @@ __device__ __forceinline__ void rgb_eval(typename Dnm<MODE>::type d_nm, float ci
     else if constexpr (MODE == SBX_RGB_EXACT3_LINEAR) rgb_exact3(d_nm, ci, a, false, rgb);
     else if constexpr (MODE == SBX_RGB_SCHLICK_WALL) rgb_schlick_wall(d_nm, ci, a, rgb);
     else if constexpr (MODE == SBX_RGB_SCHLICK_TWO_BEAM) rgb_two_beam(d_nm, ci, a, rgb);
+    else if constexpr (MODE == SBX_RGB_SPECTRAL) rgb_spectral(d_nm, ci, a, rgb);
 }
 
 // RgbColor::to_u8_tuple (interference.rs:73-79): round(255 x), alpha 255
@@ -347,9 +448,15 @@ __device__ __forceinline__ uint32_t shade_px(T h, T href, float href_u, float co
                                __saturatef(t.z * rgb.intensity));
     } else {
         const float ci = fabsf(nc - R) * rsqrt_approx(len2);
+        float c[3];
+#ifndef SBX_EXACT3_F64  // A/B builds: the f64 phase on the fast paths too
+        if constexpr (sizeof(T) == 4 && (MODE == SBX_RGB_EXACT3 || MODE == SBX_RGB_EXACT3_LINEAR)) {
+            rgb_exact3_ff((float)h, (float)href, ci, rgb, MODE == SBX_RGB_EXACT3, c);
+            return pack_rgba8_fast(c[0], c[1], c[2]);
+        }
+#endif
         using DN = typename Dnm<MODE>::type;
         const DN d_nm = ((DN)h + (DN)href) * (DN)1e9;
-        float c[3];
         rgb_eval<MODE>(d_nm, ci, rgb, c);
         return pack_rgba8_fast(c[0], c[1], c[2]);
     }

@@ -55,14 +55,21 @@ struct RgbArgs {
     float two_n, r0, omr0;    // 2n, Schlick R0 = ((n-1)/(n+1))^2, 1 - R0
     double inv_n2_d;          // 1/n^2 in f64 for the phase
     double two_n_over_wl[3];  // 2 n / lambda_k at 650, 532, 450 nm (interference.rs:26-30)
+    // the same two constants split into float pairs (hi + lo == the f64 value to 2^-48) for the float-float phase
+    float inv_n2_hi, inv_n2_lo;
+    float w_hi[3], w_lo[3];
+    // SBX_RGB_SPECTRAL: per wavelength {2 pi / lambda, wr, wg, wb} with w = (XYZ -> linear sRGB)(cie(lambda)) / n
+    const float4 *spec;
+    int n_spec;
 };
 
 // Peer-memory halo push (latitude-band sharding, one process per GPU): the CTAs that update a band's first /
 // last owned row store it straight into the neighbour's ghost row over NVLink, and the neighbours order
 // their steps with two monotonic flags instead of a collective.  See sbx_march_tma.cu.
 struct PeerArgs {
-    float *up_ghost;                           // up neighbour's OUT buffer, its bottom ghost row (nullptr: none)
-    float *dn_ghost;                           // down neighbour's OUT buffer, its top ghost row (nullptr: none)
+    void *up_ghost;                            // up neighbour's OUT buffer, its bottom ghost row (nullptr: none); element = T
+    void *dn_ghost;                            // down neighbour's OUT buffer, its top ghost row (nullptr: none)
+    void *up_ghost2, *dn_ghost2;               // WGSL semantics: the same rows of the concentration field
     unsigned long long *up_flag_remote;        // up neighbour's "my lower neighbour finished step e" word
     unsigned long long *dn_flag_remote;        // down neighbour's "my upper neighbour finished step e" word
     const unsigned long long *flag_from_up;    // mine: written by the up neighbour
@@ -124,6 +131,7 @@ struct WgslArgs {
     float delta_theta, delta_phi;
     float radius_view;
     RgbArgs rgb;
+    PeerArgs peer;  // in-kernel halo push of both fields (k_wgsl_tma)
 };
 
 // arguments of one headless bubble frame (sbx_frame.cu; rows f3/f4)

@@ -1013,6 +1013,7 @@ cudaError_t launch_shade(StepArgs<T> a, int batch, int band_rows_req, cudaStream
     case SBX_RGB_EXACT3_LINEAR: SBX_SHADE(SBX_RGB_EXACT3_LINEAR); break;
     case SBX_RGB_SCHLICK_WALL: SBX_SHADE(SBX_RGB_SCHLICK_WALL); break;
     case SBX_RGB_SCHLICK_TWO_BEAM: SBX_SHADE(SBX_RGB_SCHLICK_TWO_BEAM); break;
+    case SBX_RGB_SPECTRAL: SBX_SHADE(SBX_RGB_SPECTRAL); break;
     default: return cudaErrorInvalidValue;
     }
 #undef SBX_SHADE

@@ -46,6 +46,8 @@ int resident_cluster(const StepArgs<T> &a, int batch, bool strict);
 template <typename T>
 cudaError_t launch_resident(StepArgs<T> a, int batch, bool strict, const FrontTable *tables_dev, int nsteps,
                             cudaStream_t st);
+// colour stages the resident kernels' epilogue covers (RGBA8 frame of the final field, shaded from shared memory)
+bool resident_shades(const RgbArgs &rgb);
 int resident_cluster_wgsl(const WgslArgs &a, int batch);
 cudaError_t launch_resident_wgsl(WgslArgs a, int batch, int nsteps, cudaStream_t st);
 

@@ -24,36 +24,6 @@ constexpr int kRowsPerStage = 3;  // theta rows per stage == the unroll of the t
 constexpr int kMaxBandRows = 64;
   // rows a CTA marches at most (their coefficients are staged in shared memory)
 
-__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
-{
-    unsigned long long v;
-    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
-}
-__device__ __forceinline__ unsigned long long globaltimer_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
-    return t;
-}
-// wait until a neighbour has finished the previous step (bounded: a dead neighbour must not hang the GPU)
-__device__ __forceinline__ void wait_neighbour(const unsigned long long *flag, unsigned long long want, unsigned int *status)
-{
-    const unsigned long long t0 = globaltimer_ns();
-    while (ld_acquire_sys(flag) < want) {
-        if (globaltimer_ns() - t0 > 5000000000ull) {  // 5 s
-            atomicOr(status, 1u);
-            break;
-        }
-        __nanosleep(64);
-    }
-    asm volatile("fence.proxy.async;" ::: "memory");  // the rows the neighbour pushed are read by TMA next
-}
-
 template <typename T, int VEC>
 struct Row {
     T v[VEC];
@@ -355,10 +325,8 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
             }
             stv<T, VEC>(out_p, nw);
             if (a.peer.enabled) {  // boundary rows also land in the neighbours' ghost rows (peer stores over NVLink)
-                if constexpr (sizeof(T) == 4) {
-                    if (grow == a.peer.push_up_grow) stv<T, VEC>(reinterpret_cast<T *>(a.peer.up_ghost) + jc, nw);
-                    if (grow == a.peer.push_dn_grow) stv<T, VEC>(reinterpret_cast<T *>(a.peer.dn_ghost) + jc, nw);
-                }
+                if (grow == a.peer.push_up_grow) stv<T, VEC>(reinterpret_cast<T *>(a.peer.up_ghost) + jc, nw);
+                if (grow == a.peer.push_dn_grow) stv<T, VEC>(reinterpret_cast<T *>(a.peer.dn_ghost) + jc, nw);
             }
             if constexpr (MODE != SBX_RGB_NONE) {
                 const float2 sc = *sc_p;
@@ -481,26 +449,8 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
         }
     }
 
-    if (a.peer.enabled) {
-        // when every CTA of my first (last) band is done -- ghost row consumed, boundary row pushed -- tell the up
-        // (down) neighbour that this step is finished here
-        const bool sig_up = a.peer.up_ghost && l0 == 1;
-        const bool sig_dn = a.peer.dn_ghost && l1 == a.l_last && a.peer.push_dn_grow >= 0;
-        if (sig_up || sig_dn) {
-            __threadfence_system();
-            bar_consumers(C);
-            if (tid == 0) {
-                if (sig_up && atomicAdd(a.peer.done_first, 1u) == gridDim.x - 1) {
-                    *a.peer.done_first = 0u;
-                    st_release_sys(a.peer.up_flag_remote, a.peer.epoch);
-                }
-                if (sig_dn && atomicAdd(a.peer.done_last, 1u) == gridDim.x - 1) {
-                    *a.peer.done_last = 0u;
-                    st_release_sys(a.peer.dn_flag_remote, a.peer.epoch);
-                }
-            }
-        }
-    }
+    if (a.peer.enabled)
+        peer_signal_done(a.peer, a.peer.up_ghost && l0 == 1, a.peer.dn_ghost && l1 == a.l_last && a.peer.push_dn_grow >= 0, C, tid);
 }
 
 static size_t march_tma_smem_bytes(int consumers)

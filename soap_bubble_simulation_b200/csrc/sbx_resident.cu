@@ -198,6 +198,44 @@ __device__ __noinline__ unsigned res_col_mask(const FrontTable &ft, int j)
 #define RES_ACC(acc, t0, t1)
 #endif
 
+// Colour epilogue of a resident launch: the frame of the final field is shaded straight from shared memory while the
+// band is stored, so `step_fused(dt, n, view)` -- the reference's steps_per_frame loop followed by the draw
+// (gpu_drainage.rs:338-370) -- is ONE launch.  Out of line and switched at run time: the step loop's instruction
+// footprint (the first limit of this kernel) does not grow.  RGBA8 only; `src` = the band's first owned row.
+template <int MODE, typename T>
+__device__ __noinline__ void res_shade_band(const T *src, int g0, int Rb, int N, int b, T href, float radius,
+                                            const float2 *rowSC, const RgbArgs &rgb, long long rgb_bubble_stride, unsigned magic)
+{
+    uint32_t *out = reinterpret_cast<uint32_t *>(rgb.out) + (long long)b * rgb_bubble_stride + (long long)g0 * N;
+    const float camR2 = rgb.cam2 + radius * radius;
+    const float href_u = (float)href * rgb.nm_over_max;
+#pragma unroll 1
+    for (int i = threadIdx.x; i < Rb * N; i += kResThreads) {
+        const int l = (int)__umulhi((unsigned)i, magic);  // i / N
+        const int j = i - l * N;
+        const float2 sc = __ldg(rowSC + g0 + l);
+        out[i] = shade_px<MODE, T>(src[i], href, href_u, __ldg(rgb.colA + j), sc.x, sc.y * rgb.cam_y, radius, camR2, rgb);
+    }
+}
+template <typename T>
+__device__ __forceinline__ void res_shade_dispatch(const T *src, int g0, int Rb, int N, int b, T href, float radius,
+                                                   const float2 *rowSC, const RgbArgs &rgb, long long stride, unsigned magic)
+{
+    switch (rgb.mode) {
+    case SBX_RGB_LUT: res_shade_band<SBX_RGB_LUT, T>(src, g0, Rb, N, b, href, radius, rowSC, rgb, stride, magic); break;
+    case SBX_RGB_EXACT3: res_shade_band<SBX_RGB_EXACT3, T>(src, g0, Rb, N, b, href, radius, rowSC, rgb, stride, magic); break;
+    case SBX_RGB_EXACT3_LINEAR: res_shade_band<SBX_RGB_EXACT3_LINEAR, T>(src, g0, Rb, N, b, href, radius, rowSC, rgb, stride, magic); break;
+    case SBX_RGB_SCHLICK_WALL: res_shade_band<SBX_RGB_SCHLICK_WALL, T>(src, g0, Rb, N, b, href, radius, rowSC, rgb, stride, magic); break;
+    case SBX_RGB_SCHLICK_TWO_BEAM: res_shade_band<SBX_RGB_SCHLICK_TWO_BEAM, T>(src, g0, Rb, N, b, href, radius, rowSC, rgb, stride, magic); break;
+    default: break;
+    }
+}
+// which colour stages the epilogue covers (the others keep the streaming fused step for the last step)
+bool resident_shades(const RgbArgs &rgb)
+{
+    return rgb.format == SBX_OUT_RGBA8 && rgb.mode >= SBX_RGB_LUT && rgb.mode <= SBX_RGB_SCHLICK_TWO_BEAM;
+}
+
 template <typename T, bool STRICT>
 __global__ void __launch_bounds__(kResThreads, 1)
 k_resident(const StepArgs<T> a, const FrontTable *__restrict__ tables, int nsteps, unsigned magic, int rows_max)
@@ -470,6 +508,8 @@ k_resident(const StepArgs<T> a, const FrontTable *__restrict__ tables, int nstep
         const T *src = cur + (size_t)N;
 #pragma unroll 1
         for (int i = tid; i < Rb * N; i += kResThreads) dst[i] = src[i];
+        if (a.rgb.mode != SBX_RGB_NONE)
+            res_shade_dispatch<T>(src, g0, Rb, N, b, href, bp.radius, a.rowSC, a.rgb, a.rgb_bubble_stride, magic);
     }
     cluster.sync();  // nobody leaves while a neighbour could still address its shared memory
 }
@@ -642,6 +682,8 @@ k_resident_wgsl(const WgslArgs a, int nsteps, unsigned magic, int rows_max)
             hfield[go + i] = hcur[N + i];
             cfield[go + i] = ccur[N + i];
         }
+        if (a.rgb.mode != SBX_RGB_NONE)
+            res_shade_dispatch<float>(hcur + N, g0, Rb, N, b, 0.f, a.radius_view, a.rowSC, a.rgb, a.rgb_bubble_stride, magic);
     }
     cluster.sync();
 }

@@ -180,6 +180,7 @@ cudaError_t launch_shade_tma(StepArgs<T> a, int batch, int band_rows_req, cudaSt
     case SBX_RGB_EXACT3_LINEAR: return launch_shade_one<T, SBX_RGB_EXACT3_LINEAR>(a, grid, block, smem, st);
     case SBX_RGB_SCHLICK_WALL: return launch_shade_one<T, SBX_RGB_SCHLICK_WALL>(a, grid, block, smem, st);
     case SBX_RGB_SCHLICK_TWO_BEAM: return launch_shade_one<T, SBX_RGB_SCHLICK_TWO_BEAM>(a, grid, block, smem, st);
+    case SBX_RGB_SPECTRAL: return launch_shade_one<T, SBX_RGB_SPECTRAL>(a, grid, block, smem, st);
     default: return cudaErrorInvalidValue;
     }
 }

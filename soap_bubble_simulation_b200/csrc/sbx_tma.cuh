@@ -4,6 +4,8 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 
+#include "sbx_internal.cuh"
+
 namespace sbx {
 namespace {
 
@@ -92,6 +94,56 @@ __device__ __forceinline__ void tma_bulk_g2s_hint(void *dst_smem, const void *sr
 __device__ __forceinline__ void bar_consumers(int nthreads)
 {
     asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
+}
+
+// ---- peer-memory halo push (PeerArgs): ordering between latitude neighbours, shared by the ring kernels
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
+{
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long *p, unsigned long long v)
+{
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// wait until a neighbour has finished the previous step (bounded: a dead neighbour must not hang the GPU)
+__device__ __forceinline__ void wait_neighbour(const unsigned long long *flag, unsigned long long want, unsigned int *status)
+{
+    const unsigned long long t0 = globaltimer_ns();
+    while (ld_acquire_sys(flag) < want) {
+        if (globaltimer_ns() - t0 > 5000000000ull) {  // 5 s
+            atomicOr(status, 1u);
+            break;
+        }
+        __nanosleep(64);
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");  // the rows the neighbour pushed are read by TMA next
+}
+
+// When every CTA of my first (last) band is done -- ghost row consumed, boundary row pushed -- tell the up (down)
+// neighbour that this step is finished here.  Called by all consumer threads of a CTA at the end of its band.
+__device__ __forceinline__ void peer_signal_done(const PeerArgs &p, bool sig_up, bool sig_dn, int consumers, int tid)
+{
+    if (!(sig_up || sig_dn)) return;
+    __threadfence_system();
+    bar_consumers(consumers);
+    if (tid == 0) {
+        if (sig_up && atomicAdd(p.done_first, 1u) == gridDim.x - 1) {
+            *p.done_first = 0u;
+            st_release_sys(p.up_flag_remote, p.epoch);
+        }
+        if (sig_dn && atomicAdd(p.done_last, 1u) == gridDim.x - 1) {
+            *p.done_last = 0u;
+            st_release_sys(p.dn_flag_remote, p.epoch);
+        }
+    }
 }
 
 

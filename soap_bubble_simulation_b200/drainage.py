@@ -214,6 +214,19 @@ class _DeviceField:
         vc = view.to_c()
         L.check(L.lib().sbx_drainage_shade(self._h, C.byref(vc)))
 
+    def set_spectrum(self, wavelengths_nm) -> None:
+        """Wavelength list of RGB_SPECTRAL (the reference's shaders use 400, 450, ..., 700 nm)."""
+        wl = np.ascontiguousarray(wavelengths_nm, dtype=np.float32)
+        L.check(L.lib().sbx_drainage_set_spectrum(self._h, wl.ctypes.data_as(C.POINTER(C.c_float)), len(wl)))
+
+    def shade_spectral(self, view: View, wavelengths_nm=None) -> None:
+        """Colour frame of the current field by direct per-cell spectral evaluation (no LUT):
+        thin_film_interference of bubble_instanced.wgsl:190-218 over the given wavelengths."""
+        if wavelengths_nm is not None:
+            self.set_spectrum(wavelengths_nm)
+        v = View(cam_pos=view.cam_pos, n_film=view.n_film, intensity=view.intensity, mode=L.RGB_SPECTRAL, format=view.format)
+        self.shade(v)
+
     def step_fused(self, dt: float, view: View, nsteps: int = 1) -> None:
         vc = view.to_c()
         L.check(L.lib().sbx_drainage_step_fused(self._h, dt, nsteps, C.byref(vc)))

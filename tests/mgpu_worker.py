@@ -52,14 +52,57 @@ def foam(nt, nphi, steps, prec, rank, world, local):
     return ok_all
 
 
+def wgsl(nt, nphi, steps, halo, rank, world, local):
+    """WGSL semantics (thickness + concentration, Marangoni on) sharded by latitude bands: both fields' halo rows by
+    NCCL send/recv ("wgsl_nccl") or pushed from inside k_wgsl_tma over peer memory ("wgsl_peer")."""
+    rb, re = band_partition(nt, world)[rank]
+    sim = S.GPUDrainageSimulator(500e-9, nphi, nt, device=local, row_begin=rb, row_end=re)
+    rng = np.random.default_rng(3)
+    hf = synthetic_field(nt, nphi, h0_nm=5000.0, noise_nm=20.0).astype(np.float32)
+    cf = np.clip(0.5 + 0.2 * rng.standard_normal((nt, nphi)), 0, 1).astype(np.float32)
+    sim.set_marangoni_enabled(True)
+    sim.upload(hf[rb:re])
+    sim.upload_concentration(cf[rb:re])
+    comm = Comm(rank, world, local)
+    sim.attach_comm(comm)
+    if halo == "wgsl_peer":
+        comm.enable_peer_halo(sim)
+    view = S.View(mode=S.RGB_LUT, format=S.OUT_RGBA8)
+    sim.dispatch(steps - 1)
+    sim.dispatch(1, view)
+    gh, gc, px = sim.download(np.float32)[0], sim.download_concentration()[0], sim.download_rgb()[0]
+    bad = Comm.peer_status(sim) if halo == "wgsl_peer" else 0
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (gh, gc, px, bad))
+    ok = True
+    if rank == 0:
+        p = O.wgsl_params(grid_width=nphi, grid_height=nt, marangoni_enabled=1, dt=0.001)
+        ho, co = hf, cf
+        for _ in range(steps):
+            ho, co = O.wgsl_step(p, ho, co)
+        fh = np.concatenate([g[0] for g in gathered])
+        fc = np.concatenate([g[1] for g in gathered])
+        fpx = np.concatenate([g[2] for g in gathered])
+        eh = float(np.abs(fh.astype(np.float64) / ho - 1).max())
+        ec = float(np.abs(fc.astype(np.float64) - co).max())
+        ref = O.shade_field(ho.astype(np.float64), nt, 0, 0.025, view.cam_pos, intensity=4.0, mode=1)
+        dpx = int(np.abs(fpx.astype(int) - ref.astype(int)).max())
+        ok = eh <= 1e-5 and ec <= 1e-5 and dpx <= 1 and not any(g[3] for g in gathered)
+        print(f"MGPU world={world} wgsl grid={nt}x{nphi} halo={halo}: err_h={eh:.3e} err_c={ec:.3e} rgba_max_diff={dpx} ok={ok}", flush=True)
+    flag = torch.tensor([1 if ok else 0], device="cuda")
+    dist.broadcast(flag, src=0)
+    comm.close()
+    return int(flag.item()) == 1
+
+
 def main():
     nt, nphi, steps, prec = int(sys.argv[1]), int(sys.argv[2]), int(sys.argv[3]), int(sys.argv[4])
     halo = sys.argv[5] if len(sys.argv) > 5 else "nccl"
     rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
     torch.cuda.set_device(local)
     dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    if halo == "foam":
-        ok = foam(nt, nphi, steps, prec, rank, world, local)
+    if halo == "foam" or halo.startswith("wgsl"):
+        ok = foam(nt, nphi, steps, prec, rank, world, local) if halo == "foam" else wgsl(nt, nphi, steps, halo, rank, world, local)
         dist.destroy_process_group()
         sys.exit(0 if ok else 1)
     rb, re = band_partition(nt, world)[rank]

@@ -177,7 +177,16 @@ COLOUR_SHIMS = r"""
 #include <cmath>
 #define __device__
 #define __forceinline__ inline
-struct RgbArgs { float n_film, inv_n2, two_n, r0, omr0; double inv_n2_d; double two_n_over_wl[3]; float two_pi_over_wl_f[3]; };
+#include <cstring>
+#include <cstdint>
+struct RgbArgs { float n_film, inv_n2, two_n, r0, omr0; double inv_n2_d; double two_n_over_wl[3]; float two_pi_over_wl_f[3];
+                 float inv_n2_hi, inv_n2_lo, w_hi[3], w_lo[3]; };
+static inline float __fmul_rn(float a, float b) { return a * b; }  // plain IEEE ops under -ffp-contract=off
+static inline float __fadd_rn(float a, float b) { return a + b; }
+static inline float __fsub_rn(float a, float b) { return a - b; }
+static inline uint32_t __float_as_uint(float f) { uint32_t u; std::memcpy(&u, &f, 4); return u; }
+static inline float __uint_as_float(uint32_t u) { float f; std::memcpy(&f, &u, 4); return f; }
+static inline float rsqrt_approx(float x) { return (float)(1.0 / std::sqrt((double)x)) * (1.0f + 1.2e-7f); }  // ~1 ulp off, like the SFU
 static inline float clamp01(float x) { return std::fmin(std::fmax(x, 0.f), 1.f); }
 static inline float rcp_approx(float x) { return 1.0f / x; }       // the SFU approximations, exact here: this test
 static inline float sqrt_approx(float x) { return std::sqrt(x); }  // checks the algebra, the GPU tests the hardware
@@ -205,12 +214,24 @@ extern "C" void eval(int mode, double n, const double *d, const float *ci, int c
   a.r0 = (float)(((n - 1.0) / (n + 1.0)) * ((n - 1.0) / (n + 1.0))); a.omr0 = 1.0f - a.r0;
   const double wl[3] = {650.0, 532.0, 450.0};
   for (int k = 0; k < 3; ++k) { a.two_n_over_wl[k] = 2.0 * n / wl[k]; a.two_pi_over_wl_f[k] = (float)(2.0 * 3.14159265358979323846 / wl[k]); }
+  a.inv_n2_hi = (float)a.inv_n2_d; a.inv_n2_lo = (float)(a.inv_n2_d - (double)a.inv_n2_hi);
+  for (int k = 0; k < 3; ++k) { a.w_hi[k] = (float)a.two_n_over_wl[k]; a.w_lo[k] = (float)(a.two_n_over_wl[k] - (double)a.w_hi[k]); }
   for (int i = 0; i < cnt; ++i) {
     if (mode == 0) rgb_exact3(d[i], ci[i], a, true, out + 3 * i);
     else if (mode == 1) rgb_exact3(d[i], ci[i], a, false, out + 3 * i);
     else if (mode == 2) rgb_schlick_wall(d[i], ci[i], a, out + 3 * i);
     else rgb_two_beam((float)d[i], ci[i], a, out + 3 * i);
   }
+}
+// the float-float phase of the f32 fast paths: stored thickness h and offset h_ref in metres
+extern "C" void eval_ff(int gamma, double n, const float *h, const float *href, const float *ci, int cnt, float *out) {
+  RgbArgs a{};
+  a.n_film = (float)n; a.inv_n2_d = 1.0 / (n * n);
+  const double wl[3] = {650.0, 532.0, 450.0};
+  for (int k = 0; k < 3; ++k) a.two_n_over_wl[k] = 2.0 * n / wl[k];
+  a.inv_n2_hi = (float)a.inv_n2_d; a.inv_n2_lo = (float)(a.inv_n2_d - (double)a.inv_n2_hi);
+  for (int k = 0; k < 3; ++k) { a.w_hi[k] = (float)a.two_n_over_wl[k]; a.w_lo[k] = (float)(a.two_n_over_wl[k] - (double)a.w_hi[k]); }
+  for (int i = 0; i < cnt; ++i) rgb_exact3_ff(h[i], href[i], ci[i], a, gamma != 0, out + 3 * i);
 }
 """)
     so = tmp_path / "libcolour.so"
@@ -229,6 +250,18 @@ extern "C" void eval(int mode, double n, const double *d, const float *ci, int c
     ora = O.OracleInterference(1.33)
     assert np.abs(run(0) - ora.batch(d, ci.astype(np.float64), gamma=True)).max() <= 1e-4
     assert np.abs(run(1) - ora.batch(d, ci.astype(np.float64), gamma=False)).max() <= 1e-4
+    # float-float phase (the f32 fast paths): thickness given as stored value + offset, plain (h_ref = 0), offset
+    # storage (h_ref = 500 nm) and a thick film (30 um, ~180 fringe orders); the oracle sees the thickness the pair holds
+    for href_m, scale in ((0.0, 1.0), (500e-9, 1.0), (0.0, 15.0)):
+        href = np.full(len(d), href_m, np.float32)
+        hs = (d * scale * 1e-9 - href.astype(np.float64)).astype(np.float32)
+        d_pair = (hs.astype(np.float64) + href.astype(np.float64)) * 1e9
+        for gamma in (1, 0):
+            lib.eval_ff(gamma, ctypes.c_double(1.33), hs.ctypes.data_as(ctypes.c_void_p), href.ctypes.data_as(ctypes.c_void_p),
+                        ci.ctypes.data_as(ctypes.c_void_p), len(d), out.ctypes.data_as(ctypes.c_void_p))
+            ref = ora.batch(d_pair, ci.astype(np.float64), gamma=bool(gamma))
+            err = np.abs(out.astype(np.float64) - ref).max()
+            assert err <= 1e-4, (href_m, scale, gamma, err)
     sub = np.r_[0:2000, len(d) - 4:len(d)]  # the scalar oracle entry points: a subset
     wall, two = run(2).copy(), run(3).copy()
     for i in sub:

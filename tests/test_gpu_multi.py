@@ -28,7 +28,12 @@ def _free_port():
                                                      (64, 128, 120, 0, "peer"), (256, 1024, 60, 0, "peer"),
                                                      (16, 256, 40, 0, "peer"),
                                                      (64, 128, 120, 0, "host"), (1300, 256, 12, 0, "host"),
-                                                     (64, 128, 40, 0, "foam"), (32, 64, 30, 1, "foam")])
+                                                     (64, 128, 40, 0, "foam"), (32, 64, 30, 1, "foam"),
+                                                     (64, 128, 120, 1, "peer"), (256, 1024, 40, 1, "peer"),
+                                                     (64, 128, 12, 0, "wgsl_nccl"), (64, 128, 12, 0, "wgsl_peer"),
+                                                     (256, 1024, 30, 0, "wgsl_peer"),
+                                                     # tall bands: the NCCL path runs boundary bands + exchange beside the interior
+                                                     (1536, 256, 10, 0, "nccl"), (1536, 256, 10, 1, "nccl"), (1030, 100, 6, 2, "nccl")])
 def test_sharded_matches_oracle(world, nt, nphi, steps, prec, halo):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")

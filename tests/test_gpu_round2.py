@@ -229,3 +229,83 @@ def test_strict_mode_reproduces_reference_vectors(S, path):
         sim.step(v.dt, steps - done)
         done = steps
         assert np.array_equal(sim.download()[0], field), (path, steps)
+
+
+# ------------------------------------------------------------------ direct per-cell spectral evaluation (config 5's SFU-bound half)
+@pytest.mark.parametrize("nl", [7, 64])
+def test_spectral_direct_evaluation_matches_the_oracle(S, nl):
+    """SBX_RGB_SPECTRAL: thin_film_interference of the fragment shaders (bubble_instanced.wgsl:190-218) per cell over
+    nl wavelengths, against the oracle's f32 restatement of the same function.  Away from grazing incidence
+    (cos theta_i > 0.15; at the limb the Airy fringes are needle-sharp and the shader's own f32 sine is ill-conditioned)
+    RGBA8 within 1 LSB and float colour within 1e-4."""
+    nt, nphi = 96, 512
+    f = synthetic_field(nt, nphi, h0_nm=900.0, noise_nm=40.0)
+    f *= np.linspace(0.05, 2.0, nt)[:, None]  # 45 nm ... 1.8 um over the sphere
+    wl = (380.0 + 400.0 * np.arange(64) / 63.0) if nl == 64 else np.arange(400.0, 701.0, 50.0)
+    sim = make_sim(S, nt, nphi, S.PREC_F32, h_ref=0.0)
+    sim.upload(f)
+    view = S.View(mode=S.RGB_SPECTRAL, format=S.OUT_RGBA8)
+    if nl == 7:
+        sim.shade(view)  # the handle's default spectrum is the reference's seven wavelengths
+    else:
+        sim.shade_spectral(view, wl)
+    px = sim.download_rgb()[0]
+    f32 = f.astype(np.float32).astype(np.float64)
+    ref = O.shade_field_spectral(f32, nt, 0, 0.025, view.cam_pos, wl)
+    th = (np.arange(nt) * math.pi / (nt - 1))[:, None]
+    ph = (np.arange(nphi) * 2 * math.pi / nphi)[None, :]
+    ci = np.vectorize(lambda t, p: O.view_cos(t, p, 0.025, view.cam_pos))(th, ph)
+    ok = ci > 0.15
+    d = np.abs(px.astype(int) - ref.astype(int))[..., :3].max(axis=-1)
+    assert d[ok].max() <= 1, int(d[ok].max())
+    assert (px[..., 3] == 255).all()
+    assert np.count_nonzero(d[ok]) <= 0.02 * ok.sum()
+    viewf = S.View(mode=S.RGB_SPECTRAL, format=S.OUT_RGB_F32)
+    sim.shade(viewf)
+    rgbf = sim.download_rgb(S.OUT_RGB_F32)[0]
+    reff = O.shade_field_spectral(f32, nt, 0, 0.025, view.cam_pos, wl, as_float=True)
+    assert float(np.abs(rgbf - reff)[ok].max()) <= 1e-4
+    # the fused entry point with this mode = drainage steps, then the colour pass
+    sim.step_fused(1e-6, view, 2)
+    assert sim.download_rgb().shape == (1, nt, nphi, 4)
+    with pytest.raises(S.SbxError):
+        sim.set_spectrum(np.zeros(3))
+
+
+# ------------------------------------------------------------------ one launch per frame on small grids (resident colour epilogue)
+def test_steps_per_frame_loop_is_one_launch_with_the_frame(S):
+    """step_fused(dt, view, n >= 2) on a grid that fits shared memory: n steps AND the colour frame of the final field in
+    ONE launch (the reference's steps_per_frame loop + draw, gpu_drainage.rs:338-370); the frame is the one a separate
+    colour pass of the same field produces, bit for bit, pole rows included."""
+    view = S.View(mode=S.RGB_LUT, format=S.OUT_RGBA8)
+    sim = make_sim(S, 128, 256, S.PREC_F32)  # config/default.json, offset storage
+    sim.step_fused(1e-3, view, 10)            # builds the LUT, column table, ...
+    l0 = sim.launch_count()
+    sim.step_fused(1e-3, view, 10)
+    assert sim.launch_count() - l0 == 1
+    frame = sim.download_rgb()
+    sim.shade(view)
+    assert np.array_equal(frame, sim.download_rgb())
+    ora = O.OracleDrainage(128, 256)
+    ora.step(1e-3, 20)
+    ref = O.shade_field(ora.data, 128, 0, 0.025, view.cam_pos, intensity=4.0, mode=1)
+    assert int(np.abs(frame[0].astype(int) - ref.astype(int)).max()) <= 1
+    # EXACT3 epilogue, f64 storage
+    v3 = S.View(mode=S.RGB_EXACT3, format=S.OUT_RGBA8)
+    s64 = make_sim(S, 64, 128, S.PREC_F64)
+    s64.step_fused(1e-3, v3, 5)
+    l0 = s64.launch_count()
+    s64.step_fused(1e-3, v3, 5)
+    assert s64.launch_count() - l0 == 1
+    fr = s64.download_rgb()
+    s64.shade(v3)
+    assert np.array_equal(fr, s64.download_rgb())
+    # the reference's GPU grid, WGSL semantics: steps_per_frame dispatches + frame
+    g = S.GPUDrainageSimulator(500e-9, 128, 64)
+    g.dispatch(10, view)
+    l0 = g.launch_count()
+    g.dispatch(10, view)
+    assert g.launch_count() - l0 == 1
+    fr = g.download_rgb()
+    g.shade(view)
+    assert np.array_equal(fr, g.download_rgb())
