@@ -1162,6 +1162,7 @@ static bool resident_possible(const sbx_drainage *h)
 }
 
 constexpr int kResidentChunk = 1024;
+constexpr int kResidentZeroCopy = 32;  // launches of at most this many steps read their TFE tables from pinned host memory
 
 // `rgb` (mode != NONE): the last launch of the call also writes the colour frame of the final field
 template <typename T>
@@ -1186,6 +1187,7 @@ static int32_t steps_resident(sbx_drainage *h, double dt, int nsteps, int *taken
     while (nsteps > 0) {
         const int n = std::min(nsteps, kChunk);
         const FrontTable *tabs = nullptr;
+        int zero_copy_slot = -1;
         if (h->tfe_enabled) {
             const int slot = h->res_slot;
             h->res_slot ^= 1;
@@ -1209,15 +1211,29 @@ static int32_t steps_resident(sbx_drainage *h, double dt, int nsteps, int *taken
                     t.cols_changed = cols;
                 }
             }
-            // stream order keeps the device buffer safe: this copy runs after the kernel that read it two chunks ago
-            CU(cudaMemcpyAsync(h->res_tabs_dev[slot], host, (size_t)n * sizeof(FrontTable), cudaMemcpyHostToDevice, h->stream));
-            CU(cudaEventRecord(h->res_tabs_ev[slot], h->stream));
-            tabs = h->res_tabs_dev[slot];
+            bool any_front = false;
+            for (int s = 0; s < n; ++s) any_front |= host[s].count > 0;
+            if (!any_front) {
+                // no front alive in any of these steps (e.g. the first 0.5 s of a simulator): the launch needs no tables
+                tabs = nullptr;
+            } else if (n <= kResidentZeroCopy) {
+                // a frame's worth of steps (steps_per_frame, gpu_drainage.rs:328): the kernel reads the few KB of tables
+                // straight from the pinned host buffer (UVA) -- one PCIe read instead of a memcpy node in front of every
+                // launch; the buffer is free again when the kernel has finished (event below)
+                tabs = host;
+                zero_copy_slot = slot;
+            } else {
+                // stream order keeps the device buffer safe: this copy runs after the kernel that read it two chunks ago
+                CU(cudaMemcpyAsync(h->res_tabs_dev[slot], host, (size_t)n * sizeof(FrontTable), cudaMemcpyHostToDevice, h->stream));
+                CU(cudaEventRecord(h->res_tabs_ev[slot], h->stream));
+                tabs = h->res_tabs_dev[slot];
+            }
         } else {
             for (int s = 0; s < n; ++s) h->time += dt;
         }
         if (n == nsteps) a.rgb = rgb;  // last launch: colour epilogue
         CU(launch_resident<T>(a, h->batch, h->strict, tabs, n, h->stream));
+        if (zero_copy_slot >= 0) CU(cudaEventRecord(h->res_tabs_ev[zero_copy_slot], h->stream));
         h->launches++;
         *taken += n;
         nsteps -= n;

@@ -767,11 +767,20 @@ template int resident_cluster<double>(const StepArgs<double> &, int, bool);
 template <typename K, typename... Args>
 static cudaError_t launch_cluster(K kernel, int C, int batch, size_t smem, cudaStream_t st, Args... args)
 {
-    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
-    if (C > 8) {
-        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    // the attributes are sticky per kernel and device: set them when they change, not on every launch (a frame loop
+    // launches this kernel thousands of times with the same shape)
+    static thread_local struct { const void *k; int dev; size_t smem; int c; } last = {nullptr, -1, 0, 0};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaError_t e = cudaSuccess;
+    if (last.k != (const void *)kernel || last.dev != dev || last.smem != smem || last.c != C) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
+        if (C > 8) {
+            e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+            if (e != cudaSuccess) return e;
+        }
+        last = {(const void *)kernel, dev, smem, C};
     }
     cudaLaunchConfig_t cfg;
     cudaLaunchAttribute attr[1];
