@@ -94,6 +94,14 @@ impl DrainageSimulator {
     pub fn set_tfe_thickness_ratio(&mut self, ratio: f64) { check(unsafe { sbx_drainage_set_tfe_ratio(self.h, ratio) }); }
     pub fn tfe_thickness_ratio(&self) -> f64 { let mut r = 0.0; check(unsafe { sbx_drainage_tfe_ratio(self.h, &mut r) }); r }
     pub fn active_tfe_count(&self) -> usize { let mut n = 0; check(unsafe { sbx_drainage_active_tfe_count(self.h, &mut n) }); n as usize }
+    /// Not in the reference (its fields are private and it has no serialisation): current_time, next_tfe_spawn_time
+    /// and tfe_fronts (drainage.rs:237-255) for checkpoint / resume; the field itself travels through thickness_field().
+    pub fn tfe_state(&self) -> sbx_tfe_state {
+        let mut st: sbx_tfe_state = unsafe { std::mem::zeroed() };
+        check(unsafe { sbx_drainage_get_state(self.h, &mut st) });
+        st
+    }
+    pub fn restore_tfe_state(&mut self, st: &sbx_tfe_state) { check(unsafe { sbx_drainage_set_state(self.h, st) }); }
 }
 
 impl Drop for DrainageSimulator { fn drop(&mut self) { unsafe { sbx_drainage_destroy(self.h) }; } }
