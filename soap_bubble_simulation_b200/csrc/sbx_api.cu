@@ -183,7 +183,8 @@ struct sbx_drainage {
     bool use_resident = true;            // SBX_NO_RESIDENT=1: always use the streaming kernels
     FrontTable *res_tabs_host[2] = {nullptr, nullptr};  // pinned: per-step TFE tables of a resident launch
     FrontTable *res_tabs_dev[2] = {nullptr, nullptr};
-    cudaEvent_t res_tabs_ev[2] = {nullptr, nullptr};
+    cudaEvent_t res_tabs_ev[2] = {nullptr, nullptr}, res_copy_ev[2] = {nullptr, nullptr};
+    cudaStream_t tab_stream = nullptr;  // uploads the next resident launch's TFE tables beside the running one
     int res_slot = 0;
     int64_t launches = 0;
 };
@@ -203,6 +204,7 @@ static void free_all(sbx_drainage *h)
         if (h->res_tabs_host[i]) cudaFreeHost(h->res_tabs_host[i]);
         cudaFree(h->res_tabs_dev[i]);
         if (h->res_tabs_ev[i]) cudaEventDestroy(h->res_tabs_ev[i]);
+        if (h->res_copy_ev[i]) cudaEventDestroy(h->res_copy_ev[i]);
     }
     cudaFree(h->coefS);
     cudaFree(h->coefF);
@@ -239,6 +241,7 @@ static void free_all(sbx_drainage *h)
     if (h->copy_in) cudaStreamDestroy(h->copy_in);
     if (h->copy_out) cudaStreamDestroy(h->copy_out);
     if (h->halo_stream) cudaStreamDestroy(h->halo_stream);
+    if (h->tab_stream) cudaStreamDestroy(h->tab_stream);
     if (h->ev_prev) cudaEventDestroy(h->ev_prev);
     if (h->ev_halo) cudaEventDestroy(h->ev_halo);
     for (auto e : h->ev_in) cudaEventDestroy(e);
@@ -1162,7 +1165,6 @@ static bool resident_possible(const sbx_drainage *h)
 }
 
 constexpr int kResidentChunk = 1024;
-constexpr int kResidentZeroCopy = 32;  // launches of at most this many steps read their TFE tables from pinned host memory
 
 // `rgb` (mode != NONE): the last launch of the call also writes the colour frame of the final field
 template <typename T>
@@ -1182,12 +1184,14 @@ static int32_t steps_resident(sbx_drainage *h, double dt, int nsteps, int *taken
             CU(cudaMallocHost(&h->res_tabs_host[i], (size_t)kChunk * sizeof(FrontTable)));
             CU(cudaMalloc(&h->res_tabs_dev[i], (size_t)kChunk * sizeof(FrontTable)));
             CU(cudaEventCreateWithFlags(&h->res_tabs_ev[i], cudaEventDisableTiming));
+            CU(cudaEventCreateWithFlags(&h->res_copy_ev[i], cudaEventDisableTiming));
         }
+        CU(cudaStreamCreateWithFlags(&h->tab_stream, cudaStreamNonBlocking));
     }
     while (nsteps > 0) {
         const int n = std::min(nsteps, kChunk);
         const FrontTable *tabs = nullptr;
-        int zero_copy_slot = -1;
+        int used_slot = -1;
         if (h->tfe_enabled) {
             const int slot = h->res_slot;
             h->res_slot ^= 1;
@@ -1216,24 +1220,24 @@ static int32_t steps_resident(sbx_drainage *h, double dt, int nsteps, int *taken
             if (!any_front) {
                 // no front alive in any of these steps (e.g. the first 0.5 s of a simulator): the launch needs no tables
                 tabs = nullptr;
-            } else if (n <= kResidentZeroCopy) {
-                // a frame's worth of steps (steps_per_frame, gpu_drainage.rs:328): the kernel reads the few KB of tables
-                // straight from the pinned host buffer (UVA) -- one PCIe read instead of a memcpy node in front of every
-                // launch; the buffer is free again when the kernel has finished (event below)
-                tabs = host;
-                zero_copy_slot = slot;
             } else {
-                // stream order keeps the device buffer safe: this copy runs after the kernel that read it two chunks ago
-                CU(cudaMemcpyAsync(h->res_tabs_dev[slot], host, (size_t)n * sizeof(FrontTable), cudaMemcpyHostToDevice, h->stream));
-                CU(cudaEventRecord(h->res_tabs_ev[slot], h->stream));
+                // The tables travel on a stream of their own, so the copy for launch k + 1 runs while launch k computes
+                // instead of sitting between two launches (a frame loop calls this every 10 steps: the serialised copy was
+                // a third of the frame).  Safe: the host waited above for the launch that last read this slot, and the
+                // launch below waits for the copy.  (Reading the tables straight from pinned host memory was measured
+                // and rejected: the per-step prefetch then pays a PCIe round trip, 42 us per 10-step frame instead of 29.)
+                CU(cudaMemcpyAsync(h->res_tabs_dev[slot], host, (size_t)n * sizeof(FrontTable), cudaMemcpyHostToDevice, h->tab_stream));
+                CU(cudaEventRecord(h->res_copy_ev[slot], h->tab_stream));
+                CU(cudaStreamWaitEvent(h->stream, h->res_copy_ev[slot], 0));
                 tabs = h->res_tabs_dev[slot];
+                used_slot = slot;
             }
         } else {
             for (int s = 0; s < n; ++s) h->time += dt;
         }
         if (n == nsteps) a.rgb = rgb;  // last launch: colour epilogue
         CU(launch_resident<T>(a, h->batch, h->strict, tabs, n, h->stream));
-        if (zero_copy_slot >= 0) CU(cudaEventRecord(h->res_tabs_ev[zero_copy_slot], h->stream));
+        if (used_slot >= 0) CU(cudaEventRecord(h->res_tabs_ev[used_slot], h->stream));  // slot free again when this launch is done
         h->launches++;
         *taken += n;
         nsteps -= n;

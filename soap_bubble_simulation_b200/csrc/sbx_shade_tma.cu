@@ -120,9 +120,23 @@ __global__ void __launch_bounds__(288, 5) k_shade_tma(const StepArgs<T> a)
                     const float2 sc = *sc_p;
                     const float ccy = sc.y * a.rgb.cam_y;
                     uint32_t px[VEC];
+                    if constexpr (MODE == SBX_RGB_SPECTRAL) {
+                        // the thread's VEC cells share one pass over the wavelength table (rgb_spectral_vec)
+                        float dn[VEC], civ[VEC], c3[VEC][3];
 #pragma unroll
-                    for (int k = 0; k < VEC; ++k)
-                        px[k] = shade_px<MODE, T>(v[r][k], href, href_u, colA[k], sc.x, ccy, Rv, camR2, a.rgb);
+                        for (int k = 0; k < VEC; ++k) {
+                            const float nc = fmaf(sc.x, colA[k], ccy);
+                            civ[k] = fabsf(nc - Rv) * rsqrt_approx(fmaf(-2.f * Rv, nc, camR2));
+                            dn[k] = ((float)v[r][k] + (float)href) * 1e9f;
+                        }
+                        rgb_spectral_vec<VEC>(dn, civ, a.rgb, c3);
+#pragma unroll
+                        for (int k = 0; k < VEC; ++k) px[k] = pack_rgba8_fast(c3[k][0], c3[k][1], c3[k][2]);
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < VEC; ++k)
+                            px[k] = shade_px<MODE, T>(v[r][k], href, href_u, colA[k], sc.x, ccy, Rv, camR2, a.rgb);
+                    }
                     if constexpr (VEC == 4) *reinterpret_cast<uint4 *>(rgb_p) = make_uint4(px[0], px[1], px[2], px[3]);
                     else *reinterpret_cast<uint2 *>(rgb_p) = make_uint2(px[0], px[1]);
                 }
