@@ -478,13 +478,17 @@ static bool use_pdl()
 template <typename T, int MODE, bool TFE>
 static cudaError_t launch_one(const StepArgs<T> &a, dim3 grid, dim3 block, size_t smem, cudaStream_t st)
 {
-    // ask for the large shared-memory carveout once per device so that four 37 KB rings fit on an SM
+    // Shared-memory carveout, once per device: four 37 KB rings (+ 3 KB of static and reserved shared memory each) need the
+    // 164 KB configuration.  Asking for the MAXIMUM (228 KB, round 1) left 28 KB of L1 for the 64 KB LUT texture the colour
+    // stage samples; 72 % of the maximum = 164 KB leaves 92 KB.  Same-box A/B (profiles/r02_ab_carveout.txt): 8192 x 16384
+    // fused 500.6 / 483.4 -> 503.0 / 504.6 Gcell/s, the L2-resident 2048 x 4096 grid 430.5 / 435.6 -> 464.4 / 465.1 (+8 %).
     static bool configured[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_march_tma<T, MODE, TFE>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                             (int)cudaSharedmemCarveoutMaxShared);
+        static const int carve_env = [] { const char *e = getenv("SBX_SMEM_CARVEOUT"); return e ? atoi(e) : -1; }();
+        const int carve = carve_env >= 0 ? carve_env : (MODE == SBX_RGB_NONE ? (int)cudaSharedmemCarveoutMaxShared : 72);
+        cudaError_t e = cudaFuncSetAttribute(k_march_tma<T, MODE, TFE>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }

@@ -163,8 +163,9 @@ static cudaError_t launch_shade_one(const StepArgs<T> &a, dim3 grid, dim3 block,
     int dev = 0;
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {
-        cudaError_t e = cudaFuncSetAttribute(k_shade_tma<T, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                             (int)cudaSharedmemCarveoutMaxShared);
+        // the carveout that just holds the resident rings leaves the rest of the SM's 256 KB to L1, where the LUT texture lives
+        static const int carve = [] { const char *e = getenv("SBX_SHADE_CARVEOUT"); return e ? atoi(e) : (int)cudaSharedmemCarveoutMaxShared; }();
+        cudaError_t e = cudaFuncSetAttribute(k_shade_tma<T, MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }

@@ -286,9 +286,13 @@ static cudaError_t launch_wgsl_one(const WgslArgs &a, dim3 grid, dim3 block, siz
     cudaGetDevice(&dev);
     if (dev >= 0 && dev < 64 && !configured[dev]) {
         cudaError_t e = cudaFuncSetAttribute(k_wgsl_tma<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_max);
-        if (e == cudaSuccess)
-            e = cudaFuncSetAttribute(k_wgsl_tma<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                                     (int)cudaSharedmemCarveoutMaxShared);
+        {
+            // three 50 KB rings need the 164 KB configuration (72 % of the maximum); the maximum would leave the LUT texture
+            // 28 KB of L1 instead of 92 KB: + 3.5 % on the Marangoni + LUT step (profiles/r02_ab_carveout.txt)
+            static const int carve_env = [] { const char *e = getenv("SBX_WGSL_CARVEOUT"); return e ? atoi(e) : -1; }();
+            const int carve = carve_env >= 0 ? carve_env : (MODE == SBX_RGB_NONE ? (int)cudaSharedmemCarveoutMaxShared : 72);
+            if (e == cudaSuccess) e = cudaFuncSetAttribute(k_wgsl_tma<MODE>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        }
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
