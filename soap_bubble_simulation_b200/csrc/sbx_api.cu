@@ -1484,17 +1484,114 @@ static int32_t step_host_pipelined(sbx_drainage *h, double dt, const sbx_view *v
     return SBX_OK;
 }
 
+// The same round trip for a foam batch (independent whole-sphere bubbles, BASELINE config 4): pipelined over groups of
+// bubbles.  With offset storage (h_ref != 0) the uploaded absolute thickness is converted in place after it lands and
+// the new field is converted back into the (now free) input half before it leaves, so the device keeps its
+// sub-ulp-preserving representation and the host sees metres.
+static int32_t step_host_pipelined_foam(sbx_drainage *h, double dt, const sbx_view *view, const float *host_in,
+                                        float *host_out_h, void *host_out_rgb)
+{
+    h->mm_valid = h->mm_kernel_valid = false;
+    int32_t rc = ensure_tables(h);
+    if (rc != SBX_OK) return rc;
+    RgbArgs rgb;
+    rc = prepare_rgb(h, view, rgb);
+    if (rc != SBX_OK) return rc;
+    const int N = h->num_phi, rows = h->rows_local, B = h->batch;
+    const size_t cells_b = (size_t)rows * N;  // owned cells per bubble
+    int group = (int)std::max<size_t>(1, ((size_t)32 << 20) / (cells_b * 4));
+    if (const char *e = getenv("SBX_HOST_CHUNK_BUBBLES")) group = std::max(1, atoi(e));
+    const int nchunks = (B + group - 1) / group;
+    if (!h->copy_in) {
+        CU(cudaStreamCreateWithFlags(&h->copy_in, cudaStreamNonBlocking));
+        CU(cudaStreamCreateWithFlags(&h->copy_out, cudaStreamNonBlocking));
+        CU(cudaEventCreateWithFlags(&h->ev_start, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_out, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&h->ev_all, cudaEventDisableTiming));
+    }
+    while ((int)h->ev_in.size() < nchunks) {
+        cudaEvent_t a, b;
+        CU(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+        CU(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+        h->ev_in.push_back(a);
+        h->ev_comp.push_back(b);
+    }
+    FrontTable ft;
+    memset(&ft, 0, sizeof ft);
+    ft.row_min = 1; ft.row_max = 0;
+    if (h->tfe_enabled) { tfe_advance(h, dt); tfe_table(h, ft); }
+    StepArgs<float> a;
+    fill_step_args<float>(h, a, dt, rgb);
+    a.fronts = ft;
+    set_pole_fold<float>(h, a, true, true);  // every chunk of this step waits for the same arrival count (one per bubble)
+    float *in = tbuf<float>(h, h->cur), *out = tbuf<float>(h, 1 - h->cur);
+    const size_t px = rgb.mode == SBX_RGB_NONE ? 0 : (rgb.format == SBX_OUT_RGBA8 ? 4 : 12);
+    const double *href = h->href_zero ? nullptr : h->href_dev;
+    CU(cudaEventRecord(h->ev_start, h->stream));
+    CU(cudaStreamWaitEvent(h->copy_in, h->ev_start, 0));
+    CU(cudaStreamWaitEvent(h->copy_out, h->ev_start, 0));
+    for (int c = 0; c < nchunks; ++c) {
+        const int b0 = c * group, nb = std::min(group, B - b0);
+        CU(cudaMemcpy2DAsync(in + (size_t)b0 * h->bubble_stride + N, (size_t)h->bubble_stride * 4, host_in + (size_t)b0 * cells_b,
+                             cells_b * 4, cells_b * 4, (size_t)nb, cudaMemcpyHostToDevice, h->copy_in));
+        CU(cudaEventRecord(h->ev_in[c], h->copy_in));
+    }
+    int n = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        const int b0 = c * group, nb = std::min(group, B - b0);
+        const long long off = (long long)b0 * h->bubble_stride, cnt = (long long)nb * h->bubble_stride;
+        CU(cudaStreamWaitEvent(h->stream, h->ev_in[c], 0));
+        if (href) { CU((launch_convert_in<float, float>(in + off, in + off, cnt, h->bubble_stride, href + b0, h->stream))); ++n; }
+        StepArgs<float> ac = a;
+        ac.in = in + off;
+        ac.out = out + off;
+        ac.bub = a.bub + b0;
+        ac.pole_count = a.pole_count + 2 * b0;  // per-bubble arrival counters; the partial-sum slots are reused chunk after chunk
+        if (px) ac.rgb.out = (char *)h->rgb_buf + (size_t)b0 * cells_b * px;
+        CU(launch_step<float>(ac, nb, ft.count > 0, false, true, true, h->band_rows, h->use_tma, h->stream, &n));
+        const float *src_h = out + off;
+        if (href && host_out_h) {  // metres for the host: into the input half, which this step no longer needs
+            CU((launch_convert_out<float, float>(in + off, out + off, cnt, h->bubble_stride, href + b0, h->stream)));
+            ++n;
+            src_h = in + off;
+        }
+        CU(cudaEventRecord(h->ev_comp[c], h->stream));
+        CU(cudaStreamWaitEvent(h->copy_out, h->ev_comp[c], 0));
+        if (host_out_rgb && px)
+            CU(cudaMemcpyAsync((char *)host_out_rgb + (size_t)b0 * cells_b * px, (char *)h->rgb_buf + (size_t)b0 * cells_b * px,
+                               (size_t)nb * cells_b * px, cudaMemcpyDeviceToHost, h->copy_out));
+        if (host_out_h)
+            CU(cudaMemcpy2DAsync(host_out_h + (size_t)b0 * cells_b, cells_b * 4, src_h + N, (size_t)h->bubble_stride * 4, cells_b * 4,
+                                 (size_t)nb, cudaMemcpyDeviceToHost, h->copy_out));
+    }
+    commit_pole_fold<float>(h, a);
+    h->launches += n;
+    h->cur = 1 - h->cur;
+    h->time += dt;
+    CU(cudaEventRecord(h->ev_out, h->copy_out));
+    CU(cudaStreamWaitEvent(h->stream, h->ev_out, 0));
+    CU(cudaStreamSynchronize(h->stream));
+    return SBX_OK;
+}
+
 extern "C" int32_t sbx_drainage_step_host(sbx_drainage *h, double dt, int32_t nsteps, const sbx_view *view,
                                           const void *host_in, int32_t in_dtype, void *host_out_h, int32_t out_dtype,
                                           void *host_out_rgb)
 {
     CHECK_H(h);
     int32_t rc = SBX_OK;
+    // (on a sharded handle the choice must be the same on every rank -- the two paths issue different NCCL calls -- so
+    // it is made from the global grid, not from this rank's band height)
+    const bool tall = h->comm ? h->num_theta >= 9 * sbx_comm_size(h->comm) : h->rows_local >= 8;
     if (host_in && nsteps == 1 && !h->wgsl && !h->f64 && h->batch == 1 && h->href_zero &&
         !(view && view->mode == SBX_RGB_SPECTRAL) &&
-        in_dtype == SBX_F32 && (!host_out_h || out_dtype == SBX_F32) && h->num_phi % 4 == 0 && h->rows_local >= 8 &&
+        in_dtype == SBX_F32 && (!host_out_h || out_dtype == SBX_F32) && h->num_phi % 4 == 0 && tall &&
         !getenv("SBX_NO_HOST_PIPELINE"))
         return step_host_pipelined(h, dt, view, (const float *)host_in, (float *)host_out_h, host_out_rgb);
+    if (host_in && nsteps == 1 && !h->wgsl && !h->f64 && h->batch > 1 && !h->comm && h->rows_local == h->num_theta &&
+        !(view && view->mode == SBX_RGB_SPECTRAL) && in_dtype == SBX_F32 && (!host_out_h || out_dtype == SBX_F32) &&
+        h->num_phi % 4 == 0 && !getenv("SBX_NO_HOST_PIPELINE"))
+        return step_host_pipelined_foam(h, dt, view, (const float *)host_in, (float *)host_out_h, host_out_rgb);
     if (host_in) rc = sbx_drainage_upload(h, host_in, in_dtype);
     if (rc != SBX_OK) return rc;
     rc = do_steps(h, dt, nsteps, view);

@@ -309,3 +309,37 @@ def test_steps_per_frame_loop_is_one_launch_with_the_frame(S):
     fr = g.download_rgb()
     g.shade(view)
     assert np.array_equal(fr, g.download_rgb())
+
+
+# ------------------------------------------------------------------ host-buffer step of a foam batch, pipelined over groups of bubbles
+@pytest.mark.parametrize("offset_storage", [False, True])
+def test_foam_step_host_pipelined_equals_separate_calls(S, monkeypatch, offset_storage):
+    """sbx_drainage_step_host on a batch of independent bubbles (H2D / [convert] / step / [convert] / D2H pipelined over
+    groups of bubbles) against upload + step_fused + download, plain f32 and offset storage, pole rows folded per bubble."""
+    monkeypatch.setenv("SBX_HOST_CHUNK_BUBBLES", "2")  # 5 bubbles: groups of 2, 2, 1
+    nt, nphi, B = 48, 256, 5
+    h0 = np.linspace(300e-9, 700e-9, B)
+    rad = np.linspace(0.0125, 0.1, B)
+    kw = dict(batch=B, batch_h0_m=h0, batch_radius_m=rad, h_ref=1.0 if offset_storage else 0.0)
+    view = S.View(mode=S.RGB_LUT, format=S.OUT_RGBA8)
+    rng = np.random.default_rng(7)
+    cur = (h0[:, None, None] * (1.0 + 0.01 * rng.standard_normal((B, nt, nphi)))).astype(np.float32)
+    sim, ref = make_sim(S, nt, nphi, S.PREC_F32, **kw), make_sim(S, nt, nphi, S.PREC_F32, **kw)
+    out_h = np.empty((B, nt, nphi), np.float32)
+    out_px = np.empty((B, nt, nphi, 4), np.uint8)
+    for step in range(3):
+        ref.upload(cur)
+        ref.step_fused(1e-3, view, 1)
+        want_h, want_px = ref.download(np.float32), ref.download_rgb()
+        sim.step_host(1e-3, 1, view, cur, out_h, out_px)
+        assert np.array_equal(out_h, want_h), step
+        assert np.array_equal(out_px, want_px), step
+        cur = want_h.copy()
+    # and against the oracle, bubble by bubble
+    for b in (0, B - 1):
+        ora = O.OracleDrainage(nt, nphi, h0_m=float(h0[b]), radius_m=float(rad[b]))
+        ora.data[:] = cur[b].astype(np.float64)
+        ora.step(1e-3, 1)
+        sim.step_host(1e-3, 1, view, cur, out_h, out_px)
+        assert float(np.abs(out_h[b] / ora.data - 1).max()) <= 1e-5
+        break
