@@ -73,6 +73,29 @@ assert sim.active_tfe_count() >= 1
 S.HeadlessRenderPipeline.new(96, 64).render_to_buffer()
 S.render_drainage_frame(sim, 64, 64, bubble=2)
 sim.close()
+# round 2: resident colour epilogue (CPU + WGSL semantics, fronts alive), direct spectral pass, foam host-buffer step
+# (offset storage: in-place conversions), checkpoint / resume
+sim = S.DrainageSimulator(S.SimulationConfig.default(), num_theta=64, num_phi=256)
+sim.step_fused(5e-3, view, 120)
+sim.step_fused(5e-3, S.View(mode=S.RGB_EXACT3), 10)
+st = sim.get_state()
+sim.set_state(*st)
+sim.shade_spectral(view, 380.0 + 400.0 * np.arange(9) / 8.0)
+sim.step_fused(5e-3, S.View(mode=S.RGB_SPECTRAL), 2)
+sim.download_rgb()
+sim.close()
+g = S.GPUDrainageSimulator(500e-9, 128, 64)
+g.dispatch(10, view)
+g.download_rgb()
+g.close()
+os.environ["SBX_HOST_CHUNK_BUBBLES"] = "2"
+B = 5
+sim = S.DrainageSimulator(S.SimulationConfig.default(), num_theta=48, num_phi=256, batch=B, h_ref=1.0,
+                          batch_h0_m=np.linspace(300e-9, 700e-9, B))
+hin = np.full((B, 48, 256), 4e-7, np.float32)
+hout, hpx = np.empty_like(hin), np.empty((B, 48, 256, 4), np.uint8)
+sim.step_host(1e-3, 1, view, hin, hout, hpx)
+sim.close()
 S.generate_interference_lut(1.33, 1.0)
 S.InterferenceCalculator(1.33).batch(np.linspace(0, 2000, 100), np.linspace(0, 1, 100))
 print("SANITIZE_TARGET_DONE")

@@ -1,0 +1,54 @@
+"""bench.py's bookkeeping that needs no GPU: the ncu traffic figure is tied to the kernel sources it was captured from, the
+oracle is only reachable from the checker / CPU-baseline legs, and the reference arm prints the CUDA arm's config."""
+import json
+import os
+import re
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run_py(code: str) -> str:
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    return r.stderr + r.stdout  # bench.py points fd 1 at stderr on import
+
+
+def test_traffic_figure_is_refused_when_the_kernel_sources_changed(tmp_path):
+    out = run_py("import bench, json; print('RESULT', json.dumps([bench.kernel_source_hash(), *bench.ncu_traffic()]))")
+    sha, traffic, note = json.loads(re.search(r"RESULT (.*)", out).group(1))
+    with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+        t = json.load(f)
+    if t.get("kernel_source_sha16") == sha:
+        assert traffic == t["k_march_dram_bytes_per_launch"] and "stale" not in note
+    else:  # the capture is of another kernel: no number, and the note says which hashes disagree
+        assert traffic is None and "stale" in note and sha in note
+    # a capture of other sources is refused
+    out = run_py("import bench; bench.KERNEL_SOURCES = ('sbx_api.cu',); print('RESULT', bench.ncu_traffic()[0])")
+    assert "RESULT None" in out
+
+
+def test_bench_reaches_the_oracle_only_from_checker_and_baseline_legs():
+    with open(os.path.join(ROOT, "bench.py")) as f:
+        src = f.read()
+    assert "sys.path.insert(0, os.path.join(ROOT, \"tests\"))" not in src  # helpers live in the package / oracle/ now
+    uses = [m.start() for m in re.finditer(r"oracle_module\(\)", src)]
+    owners = set()
+    for pos in uses[1:]:  # the first hit is the definition
+        head = src[:pos]
+        owners.add(re.findall(r"\ndef (\w+)|\nclass (\w+)", head)[-1])
+    names = {a or b for a, b in owners}
+    assert names <= {"CpuReference", "check_sphere", "run_sbx"}, names  # run_sbx: the foam parity_check block only
+    assert "oracle" not in open(os.path.join(ROOT, "soap_bubble_simulation_b200", "__init__.py")).read()
+
+
+def test_reference_arm_prints_the_cuda_arms_config():
+    code = ("import bench, argparse, json\n"
+            "a = argparse.Namespace(workload='sphere', scaling='weak', rows=8192, phi=16384, rgb='lut', halo='peer', bubbles=4096)\n"
+            "print('RESULT', json.dumps(bench.workload(a, 1)['config']))")
+    cfg = json.loads(re.search(r"RESULT (.*)", run_py(code)).group(1))
+    assert "8192x16384" in cfg["workload"] and cfg["grid_per_gpu"] == [8192, 16384]
+    with open(os.path.join(ROOT, "bench.py")) as f:
+        src = f.read()
+    assert src.count('"config": wl["config"]') == 2  # both arms emit the same object
