@@ -56,12 +56,18 @@ template <> struct MinBlocks<double> { static constexpr int value = 3; };
 
 }  // namespace
 
-// T = float (VEC 4) or double (VEC 2): a thread always owns one 16-byte packet of a row, a strip is 16*C bytes
-// wide plus a 16-byte halo each side, so ring geometry and copy sizes are identical for both types.
-template <typename T, int MODE, bool TFE>
-__global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const StepArgs<T> a)
+// T = float (VEC 4) or double (VEC 2): a row travels in 16-byte packets; a thread owns PK consecutive packets of a row
+// (W = VEC * PK cells), a strip is 16 * PK * C bytes wide plus a 16-byte halo each side, so ring geometry and copy sizes
+// are identical for both types.  PK = 2 (f32; A/B builds with -DSBX_ENABLE_PK2 and SBX_PK=2): half the consumer threads
+// with twice the cells each, so the per-row bookkeeping is amortised over 8 cells and eight texture fetches per thread are
+// in flight.  Measured and NOT adopted (profiles/r02_ab_pk_rejected.txt): 8192 x 16384 unchanged (506.7 vs 508.9 Gcell/s --
+// the step is bound by the memory system there, not by issue slots), while every launch with short bands loses the
+// latency hiding of the second set of warps (2048 x 4096: 400 vs 464, foam 4096 bubbles: 396 vs 498).
+template <typename T, int MODE, bool TFE, int PK>
+__global__ void __launch_bounds__(PK == 2 ? 160 : 288, MinBlocks<T>::value) k_march_tma(const StepArgs<T> a)
 {
     constexpr int VEC = 16 / (int)sizeof(T);
+    constexpr int W = VEC * PK;  // cells per thread and row
     constexpr int HALO = VEC;
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ double warp_part[8];
@@ -72,7 +78,7 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
     __shared__ unsigned s_rm[kMaxBandRows];  // TFE: which fronts cover each row of the band (bit per front)
     const int C = blockDim.x - 32;  // consumer threads
     const int N = a.num_phi;
-    const int strip_w_max = VEC * C;
+    const int strip_w_max = W * C;
     const int c0 = blockIdx.x * strip_w_max;
     const int w = min(strip_w_max, N - c0);   // multiple of VEC
     const int rowf = strip_w_max + 2 * HALO;  // elements per ring row
@@ -171,7 +177,7 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
         if constexpr (TFE) s_rm[r] = front_row_mask(a.fronts, (int)g);
     }
     bar_consumers(C);
-    const int jloc = tid * VEC;  // column offset inside the strip
+    const int jloc = tid * W;  // column offset inside the strip
     const bool active = jloc < w;
     const int jc = c0 + (active ? jloc : 0);
     const int soff = HALO + (active ? jloc : 0);  // element offset of this thread's packet in a ring row
@@ -183,21 +189,23 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
     const T dt = a.dt;
     const T crit = a.crit;
 
-    float colA[VEC];
+    float colA[W];
 #pragma unroll
-    for (int k = 0; k < VEC; ++k) colA[k] = 0.f;
+    for (int k = 0; k < W; ++k) colA[k] = 0.f;
     if constexpr (MODE != SBX_RGB_NONE) {
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) colA[k] = __ldg(a.rgb.colA + jc + k);
+        for (int k = 0; k < W; ++k) colA[k] = __ldg(a.rgb.colA + jc + k);
     }
     // TFE: a front's phi interval does not depend on the row, and a thread keeps its columns for the whole band, so
     // the column half of TfeFront::contains (drainage.rs:55-71) is taken once: byte k of colmask = fronts covering
     // column jc + k.  A cell is then in a front iff (row mask & its byte) != 0 -- one AND per row plus a test per cell
     // instead of 8 x 4 compares per cell (C3 with 8 fronts alive was 164 Gcell/s with the per-cell compares).
-    unsigned colmask = 0;
+    unsigned colmask[PK];  // one byte per cell, one word per packet
+#pragma unroll
+    for (int p = 0; p < PK; ++p) colmask[p] = 0;
     if constexpr (TFE) {
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) colmask |= front_col_mask(a.fronts, jc + k) << (8 * k);
+        for (int k = 0; k < W; ++k) colmask[k / VEC] |= front_col_mask(a.fronts, jc + k) << (8 * (k % VEC));
     }
     const float Rv = bp.radius;
     const float camR2 = a.rgb.cam2 + Rv * Rv;
@@ -211,19 +219,22 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
     const T *ring_t = ring + soff;                 // this thread's packet in ring row 0
     const uint32_t stage_elems = kRowsPerStage * rowf;
     const T *stage_p = ring_t;                     // this thread's packet in slot 0 of the current stage
-    using RowT = Row<T, VEC>;
+    using RowT = Row<T, W>;
 
     auto load_slot = [&](RowT &r, int slot) {
         const T *src = stage_p + slot * rowf;
-        if constexpr (VEC == 4) {
-            const float4 q = *reinterpret_cast<const float4 *>(src);
-            r.v[0] = q.x; r.v[1] = q.y; r.v[2] = q.z; r.v[3] = q.w;
-        } else {
-            const double2 q = *reinterpret_cast<const double2 *>(src);
-            r.v[0] = q.x; r.v[1] = q.y;
+#pragma unroll
+        for (int p = 0; p < PK; ++p) {
+            if constexpr (VEC == 4) {
+                const float4 q = *reinterpret_cast<const float4 *>(src + p * VEC);
+                r.v[p * VEC + 0] = q.x; r.v[p * VEC + 1] = q.y; r.v[p * VEC + 2] = q.z; r.v[p * VEC + 3] = q.w;
+            } else {
+                const double2 q = *reinterpret_cast<const double2 *>(src + p * VEC);
+                r.v[p * VEC + 0] = q.x; r.v[p * VEC + 1] = q.y;
+            }
         }
         r.eL = src[-1];
-        r.eR = src[VEC];
+        r.eR = src[W];
     };
     // `bits`: OR of the registers whose loads have not been consumed by an instruction yet (see mbar_arrive_after)
     auto release_stage = [&](uint32_t bits) {
@@ -235,13 +246,23 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
     auto row_bits = [&](const RowT &r) {
         uint32_t b = dep_bits(r.eL) | dep_bits(r.eR);
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) b |= dep_bits(r.v[k]);
+        for (int k = 0; k < W; ++k) b |= dep_bits(r.v[k]);
         return b;
     };
     auto store_px = [&](uint32_t *dst, const uint32_t *px) {
         // (streaming __stcs stores for the frame and/or h' were measured: -0.8 % / -1 %, so plain stores)
-        if constexpr (VEC == 4) *reinterpret_cast<uint4 *>(dst) = make_uint4(px[0], px[1], px[2], px[3]);
-        else *reinterpret_cast<uint2 *>(dst) = make_uint2(px[0], px[1]);
+#pragma unroll
+        for (int p = 0; p < PK; ++p) {
+            if constexpr (VEC == 4) *reinterpret_cast<uint4 *>(dst + p * VEC) = make_uint4(px[p * VEC], px[p * VEC + 1], px[p * VEC + 2], px[p * VEC + 3]);
+            else *reinterpret_cast<uint2 *>(dst + p * VEC) = make_uint2(px[p * VEC], px[p * VEC + 1]);
+        }
+    };
+    auto store_h = [&](T *dst, const T *v) {  // PK 16-byte packets
+#pragma unroll
+        for (int p = 0; p < PK; ++p) {
+            if constexpr (VEC == 4) *reinterpret_cast<float4 *>(dst + p * VEC) = make_float4(v[p * VEC], v[p * VEC + 1], v[p * VEC + 2], v[p * VEC + 3]);
+            else *reinterpret_cast<double2 *>(dst + p * VEC) = make_double2(v[p * VEC], v[p * VEC + 1]);
+        }
     };
 
     // running output pointers (bumped by one row per sub-step)
@@ -280,12 +301,12 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
             const double2 c23 = *(reinterpret_cast<const double2 *>(cf_p) + 1);
             cApB = c01.x; cAmB = c01.y; cE = c23.x; cG = c23.y;
         }
-        Vec<T, VEC> nw;
+        struct { T v[W]; } nw;
 #pragma unroll
-        for (int k = 0; k < VEC; ++k) {
+        for (int k = 0; k < W; ++k) {
             const T h = cur.v[k];
             const T lf = k == 0 ? cur.eL : cur.v[k - 1];
-            const T rt = k == VEC - 1 ? cur.eR : cur.v[k + 1];
+            const T rt = k == W - 1 ? cur.eR : cur.v[k + 1];
             const T habs = h + href;
             // A (dN + dS) + B (dN - dS) + E (dE + dW) with neighbour-minus-centre differences
             T diff = cApB * (dn.v[k] - h);
@@ -301,7 +322,7 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
             double s = 0.0;
             if (active) {
 #pragma unroll
-                for (int k = 0; k < VEC; ++k) s += (double)nw.v[k];
+                for (int k = 0; k < W; ++k) s += (double)nw.v[k];
             }
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) s += __shfl_down_sync(0xffffffffu, s, o);
@@ -322,29 +343,28 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
         if constexpr (TFE) {
             const unsigned rm = *rm_p;
             if (rm) {  // uniform over the CTA
-                const unsigned m = (rm * 0x01010101u) & colmask;
 #pragma unroll
-                for (int k = 0; k < VEC; ++k)
-                    if (m & (0xffu << (8 * k))) nw.v[k] = fma(-(nw.v[k] + href), a.tfe_rdt, nw.v[k]);
+                for (int k = 0; k < W; ++k)
+                    if ((rm * 0x01010101u) & colmask[k / VEC] & (0xffu << (8 * (k % VEC)))) nw.v[k] = fma(-(nw.v[k] + href), a.tfe_rdt, nw.v[k]);
             }
             ++rm_p;
         }
         if (active) {
             if (track) {
 #pragma unroll
-                for (int k = 0; k < VEC; ++k) { run_lo = tmin<T>(run_lo, nw.v[k]); run_hi = tmax<T>(run_hi, nw.v[k]); }
+                for (int k = 0; k < W; ++k) { run_lo = tmin<T>(run_lo, nw.v[k]); run_hi = tmax<T>(run_hi, nw.v[k]); }
             }
-            stv<T, VEC>(out_p, nw);
+            store_h(out_p, nw.v);
             if (a.peer.enabled) {  // boundary rows also land in the neighbours' ghost rows (peer stores over NVLink)
-                if (grow == a.peer.push_up_grow) stv<T, VEC>(reinterpret_cast<T *>(a.peer.up_ghost) + jc, nw);
-                if (grow == a.peer.push_dn_grow) stv<T, VEC>(reinterpret_cast<T *>(a.peer.dn_ghost) + jc, nw);
+                if (grow == a.peer.push_up_grow) store_h(reinterpret_cast<T *>(a.peer.up_ghost) + jc, nw.v);
+                if (grow == a.peer.push_dn_grow) store_h(reinterpret_cast<T *>(a.peer.dn_ghost) + jc, nw.v);
             }
             if constexpr (MODE != SBX_RGB_NONE) {
                 const float2 sc = *sc_p;
                 const float ccy = sc.y * a.rgb.cam_y;
-                uint32_t px[VEC];
+                uint32_t px[W];
 #pragma unroll
-                for (int k = 0; k < VEC; ++k)
+                for (int k = 0; k < W; ++k)
                     px[k] = shade_px<MODE, T>(nw.v[k], href, href_u, colA[k], sc.x, ccy, Rv, camR2, a.rgb);
                 store_px(rgb_p, px);
             }
@@ -412,26 +432,26 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
             if (active) {
                 const int prow = which == 0 ? 0 : a.num_theta - 1;
                 const int pl = prow - a.row_begin + 1;
-                Vec<T, VEC> pv;
+                struct { T v[W]; } pv;
 #pragma unroll
-                for (int k = 0; k < VEC; ++k) pv.v[k] = v;
+                for (int k = 0; k < W; ++k) pv.v[k] = v;
                 if constexpr (TFE) {
-                    const unsigned m = (front_row_mask(a.fronts, prow) * 0x01010101u) & colmask;
+                    const unsigned prm = front_row_mask(a.fronts, prow) * 0x01010101u;
 #pragma unroll
-                    for (int k = 0; k < VEC; ++k)
-                        if (m & (0xffu << (8 * k))) pv.v[k] = fma(-(pv.v[k] + href), a.tfe_rdt, pv.v[k]);
+                    for (int k = 0; k < W; ++k)
+                        if (prm & colmask[k / VEC] & (0xffu << (8 * (k % VEC)))) pv.v[k] = fma(-(pv.v[k] + href), a.tfe_rdt, pv.v[k]);
                 }
                 if (track) {
 #pragma unroll
-                    for (int k = 0; k < VEC; ++k) { run_lo = tmin<T>(run_lo, pv.v[k]); run_hi = tmax<T>(run_hi, pv.v[k]); }
+                    for (int k = 0; k < W; ++k) { run_lo = tmin<T>(run_lo, pv.v[k]); run_hi = tmax<T>(run_hi, pv.v[k]); }
                 }
-                stv<T, VEC>(out + (long long)pl * N + jc, pv);
+                store_h(out + (long long)pl * N + jc, pv.v);
                 if constexpr (MODE != SBX_RGB_NONE) {
                     const float2 sc = __ldg(a.rowSC + prow);
                     const float ccy = sc.y * a.rgb.cam_y;
-                    uint32_t px[VEC];
+                    uint32_t px[W];
 #pragma unroll
-                    for (int k = 0; k < VEC; ++k)
+                    for (int k = 0; k < W; ++k)
                         px[k] = shade_px<MODE, T>(pv.v[k], href, href_u, colA[k], sc.x, ccy, Rv, camR2, a.rgb);
                     store_px(reinterpret_cast<uint32_t *>(a.rgb.out) + (long long)b * a.rgb_bubble_stride +
                                  (long long)(pl - 1) * N + jc, px);
@@ -464,9 +484,9 @@ __global__ void __launch_bounds__(288, MinBlocks<T>::value) k_march_tma(const St
         peer_signal_done(a.peer, a.peer.up_ghost && l0 == 1, a.peer.dn_ghost && l1 == a.l_last && a.peer.push_dn_grow >= 0, C, tid);
 }
 
-static size_t march_tma_smem_bytes(int consumers)
+static size_t march_tma_smem_bytes(int packets)  // 16-byte packets per strip row
 {
-    return (size_t)kStages * kRowsPerStage * (16 * consumers + 32) + 2 * kStages * sizeof(uint64_t);
+    return (size_t)kStages * kRowsPerStage * (16 * packets + 32) + 2 * kStages * sizeof(uint64_t);
 }
 
 static bool use_pdl()
@@ -475,7 +495,7 @@ static bool use_pdl()
     return on;
 }
 
-template <typename T, int MODE, bool TFE>
+template <typename T, int MODE, bool TFE, int PK>
 static cudaError_t launch_one(const StepArgs<T> &a, dim3 grid, dim3 block, size_t smem, cudaStream_t st)
 {
     // Shared-memory carveout, once per device: four 37 KB rings (+ 3 KB of static and reserved shared memory each) need the
@@ -488,7 +508,7 @@ static cudaError_t launch_one(const StepArgs<T> &a, dim3 grid, dim3 block, size_
     if (dev >= 0 && dev < 64 && !configured[dev]) {
         static const int carve_env = [] { const char *e = getenv("SBX_SMEM_CARVEOUT"); return e ? atoi(e) : -1; }();
         const int carve = carve_env >= 0 ? carve_env : (MODE == SBX_RGB_NONE ? (int)cudaSharedmemCarveoutMaxShared : 72);
-        cudaError_t e = cudaFuncSetAttribute(k_march_tma<T, MODE, TFE>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+        cudaError_t e = cudaFuncSetAttribute(k_march_tma<T, MODE, TFE, PK>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
         if (e != cudaSuccess) return e;
         configured[dev] = true;
     }
@@ -504,21 +524,42 @@ static cudaError_t launch_one(const StepArgs<T> &a, dim3 grid, dim3 block, size_
     // PDL pays when the grid has several waves (measured: +1 % at 8192x16384, -10 % at the single-wave 2048x4096)
     static const size_t pdl_min = [] { const char *e = getenv("SBX_PDL_MIN_CTAS"); return e ? (size_t)atoll(e) : (size_t)500; }();
     cfg.numAttrs = (use_pdl() && (size_t)grid.x * grid.y * grid.z >= pdl_min) ? 1 : 0;
-    return cudaLaunchKernelEx(&cfg, k_march_tma<T, MODE, TFE>, a);
+    return cudaLaunchKernelEx(&cfg, k_march_tma<T, MODE, TFE, PK>, a);
 }
 
-template <typename T, bool TFE>
+template <typename T, bool TFE, int PK>
 static cudaError_t launch_tma_mode(const StepArgs<T> &a, dim3 grid, dim3 block, size_t smem, cudaStream_t st)
 {
     switch (a.rgb.mode) {
-    case SBX_RGB_NONE: return launch_one<T, SBX_RGB_NONE, TFE>(a, grid, block, smem, st);
-    case SBX_RGB_LUT: return launch_one<T, SBX_RGB_LUT, TFE>(a, grid, block, smem, st);
-    case SBX_RGB_EXACT3: return launch_one<T, SBX_RGB_EXACT3, TFE>(a, grid, block, smem, st);
-    case SBX_RGB_EXACT3_LINEAR: return launch_one<T, SBX_RGB_EXACT3_LINEAR, TFE>(a, grid, block, smem, st);
-    case SBX_RGB_SCHLICK_WALL: return launch_one<T, SBX_RGB_SCHLICK_WALL, TFE>(a, grid, block, smem, st);
-    case SBX_RGB_SCHLICK_TWO_BEAM: return launch_one<T, SBX_RGB_SCHLICK_TWO_BEAM, TFE>(a, grid, block, smem, st);
-    default: return cudaErrorInvalidValue;
+    case SBX_RGB_NONE: return launch_one<T, SBX_RGB_NONE, TFE, PK>(a, grid, block, smem, st);
+    case SBX_RGB_LUT: return launch_one<T, SBX_RGB_LUT, TFE, PK>(a, grid, block, smem, st);
+    default: break;
     }
+    if constexpr (PK == 1) {  // the analytic colour modes are arithmetic-bound: one packet per thread only
+        switch (a.rgb.mode) {
+        case SBX_RGB_EXACT3: return launch_one<T, SBX_RGB_EXACT3, TFE, 1>(a, grid, block, smem, st);
+        case SBX_RGB_EXACT3_LINEAR: return launch_one<T, SBX_RGB_EXACT3_LINEAR, TFE, 1>(a, grid, block, smem, st);
+        case SBX_RGB_SCHLICK_WALL: return launch_one<T, SBX_RGB_SCHLICK_WALL, TFE, 1>(a, grid, block, smem, st);
+        case SBX_RGB_SCHLICK_TWO_BEAM: return launch_one<T, SBX_RGB_SCHLICK_TWO_BEAM, TFE, 1>(a, grid, block, smem, st);
+        default: break;
+        }
+    }
+    return cudaErrorInvalidValue;
+}
+
+// packets per thread of this launch: 2 for f32 storage with the LUT (or no) colour stage on strips of at least 64 packets
+template <typename T>
+static int tma_packets_per_thread(const StepArgs<T> &a, int packets)
+{
+#ifdef SBX_ENABLE_PK2
+    static const int env = [] { const char *e = getenv("SBX_PK"); return e ? atoi(e) : 1; }();
+    constexpr int VEC = 16 / (int)sizeof(T);
+    if (sizeof(T) != 4 || env < 2 || packets < 64 || a.num_phi % (2 * VEC) != 0) return 1;
+    return (a.rgb.mode == SBX_RGB_NONE || a.rgb.mode == SBX_RGB_LUT) ? 2 : 1;
+#else
+    (void)a; (void)packets;
+    return 1;
+#endif
 }
 
 // The fast path handles: non-strict f32/f64 storage, RGBA8 output (or no colour), rows of whole 16-byte packets.
@@ -559,17 +600,28 @@ cudaError_t launch_march_tma(StepArgs<T> a, int batch, bool tfe, int band_rows_r
 {
     constexpr int VEC = 16 / (int)sizeof(T);
     const int rows = a.l_last - a.l_first + 1;
-    const int consumers = tma_consumers<T>(a.num_phi);
-    const int strip = consumers * VEC;
+    const int packets = tma_consumers<T>(a.num_phi);  // 16-byte packets per strip row
+    const int strip = packets * VEC;
     const int gx = (a.num_phi + strip - 1) / strip;
-    const size_t smem = march_tma_smem_bytes(consumers);
+    const size_t smem = march_tma_smem_bytes(packets);
+    const int pk = tma_packets_per_thread<T>(a, packets);
+    const int consumers = packets / pk;
     // resident CTAs per SM of this launch shape (narrow strips have smaller CTAs and more of them fit), asked once
-    static int occ_cache[9] = {0};  // by consumers / 32
-    int &occ = occ_cache[consumers / 32];
+    static int occ_cache[2][9] = {{0}};  // by packets per thread, packets / 32
+    int &occ = occ_cache[pk - 1][packets / 32];
     if (occ == 0) {
         int nb = 0;
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_march_tma<T, SBX_RGB_LUT, false>, consumers + 32, smem) != cudaSuccess || nb <= 0)
-            nb = MinBlocks<T>::value;
+        cudaError_t oe;
+#ifdef SBX_ENABLE_PK2
+        if constexpr (sizeof(T) == 4) {
+            oe = pk == 2 ? cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_march_tma<T, SBX_RGB_LUT, false, 2>, consumers + 32, smem)
+                         : cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_march_tma<T, SBX_RGB_LUT, false, 1>, consumers + 32, smem);
+        } else
+#endif
+        {
+            oe = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_march_tma<T, SBX_RGB_LUT, false, 1>, consumers + 32, smem);
+        }
+        if (oe != cudaSuccess || nb <= 0) nb = MinBlocks<T>::value;
         occ = nb;
     }
     // Sharded with the in-kernel halo push: short bands next to the neighbours, dispatched first (see StepArgs).  The
@@ -599,7 +651,12 @@ cudaError_t launch_march_tma(StepArgs<T> a, int batch, bool tfe, int band_rows_r
     a.pole_slots = gx;
     *pole_slots = gx;
     const dim3 grid((unsigned)gx, (unsigned)gy, (unsigned)batch), block((unsigned)(consumers + 32));
-    return tfe ? launch_tma_mode<T, true>(a, grid, block, smem, st) : launch_tma_mode<T, false>(a, grid, block, smem, st);
+#ifdef SBX_ENABLE_PK2
+    if constexpr (sizeof(T) == 4) {
+        if (pk == 2) return tfe ? launch_tma_mode<T, true, 2>(a, grid, block, smem, st) : launch_tma_mode<T, false, 2>(a, grid, block, smem, st);
+    }
+#endif
+    return tfe ? launch_tma_mode<T, true, 1>(a, grid, block, smem, st) : launch_tma_mode<T, false, 1>(a, grid, block, smem, st);
 }
 
 template bool march_tma_supported<float>(const StepArgs<float> &);
