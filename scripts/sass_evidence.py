@@ -10,7 +10,7 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 SO = os.path.join(ROOT, "soap_bubble_simulation_b200", "csrc", "libsbx.so")
-FUN = "_ZN3sbx11k_march_tmaIfLi1ELb0EEEvNS_8StepArgsIT_EE"  # k_march_tma<float, SBX_RGB_LUT, false>
+FUN = "_ZN3sbx11k_march_tmaIfLi1ELb0ELi1EEEvNS_8StepArgsIT_EE"  # k_march_tma<float, SBX_RGB_LUT, false>
 
 txt = subprocess.run(["cuobjdump", "-sass", "-fun", FUN, SO], capture_output=True, text=True).stdout
 ins = [re.sub(r"\s+/\*.*", "", re.sub(r"^\s+/\*([0-9a-f]{4})\*/\s+", r"\1  ", l))
