@@ -39,7 +39,14 @@ impl ThicknessField {
 }
 
 /// DrainageSimulator (drainage.rs:212-614) over libsbx.
-pub struct DrainageSimulator { h: *mut sbx_drainage, mirror: RefCell<ThicknessField>, stale: Cell<bool> }
+pub struct DrainageSimulator {
+    h: *mut sbx_drainage,
+    mirror: RefCell<ThicknessField>,
+    stale: Cell<bool>,
+    /// per-frame statistics, fetched behind one synchronisation by the first query after a step (sbx_drainage_frame_stats)
+    stats: Cell<Option<(sbx_frame_stats, (f64, f64))>>,
+    last_query: Cell<(f64, f64)>,
+}
 
 impl DrainageSimulator {
     pub fn new(config: &SimulationConfig) -> Self {
@@ -59,16 +66,28 @@ impl DrainageSimulator {
         let mut h = std::ptr::null_mut();
         check(unsafe { sbx_drainage_create(&cfg, 0, &mut h) });
         let mirror = ThicknessField::new(cfg.num_theta as usize, cfg.num_phi as usize, cfg.h0_m);
-        Self { h, mirror: RefCell::new(mirror), stale: Cell::new(true) }
+        Self { h, mirror: RefCell::new(mirror), stale: Cell::new(true), stats: Cell::new(None),
+               last_query: Cell::new((std::f64::consts::FRAC_PI_2, 0.0)) }  // what pipeline.rs:1303-1306 asks for
     }
-    pub fn step(&mut self, dt: f64) { check(unsafe { sbx_drainage_step(self.h, dt, 1) }); self.stale.set(true); }
+    /// The frame loop (pipeline.rs:1289-1322) calls step, min_thickness, max_thickness, get_thickness(pi/2, 0) and
+    /// has_critical_region one after the other; the first of those queries after a step fetches all of them at once.
+    fn frame(&self, query: Option<(f64, f64)>) -> sbx_frame_stats {
+        if let Some((st, q)) = self.stats.get() {
+            if query.map_or(true, |want| want == q) { return st; }
+        }
+        let q = query.unwrap_or(self.last_query.get());
+        let mut st: sbx_frame_stats = unsafe { std::mem::zeroed() };
+        check(unsafe { sbx_drainage_frame_stats(self.h, 0, q.0, q.1, &mut st) });
+        self.stats.set(Some((st, q)));
+        st
+    }
+    pub fn step(&mut self, dt: f64) { check(unsafe { sbx_drainage_step(self.h, dt, 1) }); self.stale.set(true); self.stats.set(None); }
     /// n applications of `step(dt)` in one call.  On grids that fit in shared memory (the default 128 x 256 does) the
     /// library takes all n steps inside one kernel launch: ~1.8 us per step instead of ~14 us.
-    pub fn step_many(&mut self, dt: f64, n: usize) { check(unsafe { sbx_drainage_step(self.h, dt, n as i32) }); self.stale.set(true); }
+    pub fn step_many(&mut self, dt: f64, n: usize) { check(unsafe { sbx_drainage_step(self.h, dt, n as i32) }); self.stale.set(true); self.stats.set(None); }
     pub fn get_thickness(&self, theta: f64, phi: f64) -> f64 {
-        let mut out = 0.0;
-        check(unsafe { sbx_drainage_get_thickness(self.h, 0, theta, phi, &mut out) });
-        out
+        self.last_query.set((theta, phi));
+        self.frame(Some((theta, phi))).thickness
     }
     /// `&ThicknessField` has to be host memory: download on demand (this is why sbx_drainage_download exists).
     pub fn thickness_field(&self) -> std::cell::Ref<'_, ThicknessField> {
@@ -81,14 +100,13 @@ impl DrainageSimulator {
     }
     /// device-side reductions for the two folds `RenderPipeline::update` does every frame (pipeline.rs:1298-1300)
     pub fn min_max_thickness(&self) -> (f64, f64) {
-        let (mut a, mut b) = (0.0, 0.0);
-        check(unsafe { sbx_drainage_minmax(self.h, &mut a, &mut b) });
-        (a, b)
+        let st = self.frame(None);
+        (st.min_thickness, st.max_thickness)
     }
     pub fn current_time(&self) -> f64 { let mut t = 0.0; check(unsafe { sbx_drainage_current_time(self.h, &mut t) }); t }
-    pub fn has_critical_region(&self) -> bool { let mut f = 0; check(unsafe { sbx_drainage_has_critical(self.h, &mut f) }); f != 0 }
+    pub fn has_critical_region(&self) -> bool { self.frame(None).has_critical != 0 }
     pub fn critical_thickness(&self) -> f64 { let mut t = 0.0; check(unsafe { sbx_drainage_critical_thickness(self.h, &mut t) }); t }
-    pub fn reset(&mut self, initial_thickness: f64) { check(unsafe { sbx_drainage_reset(self.h, initial_thickness) }); self.stale.set(true); }
+    pub fn reset(&mut self, initial_thickness: f64) { check(unsafe { sbx_drainage_reset(self.h, initial_thickness) }); self.stale.set(true); self.stats.set(None); }
     pub fn set_marginal_regeneration(&mut self, enabled: bool) { check(unsafe { sbx_drainage_set_marginal_regeneration(self.h, enabled as i32) }); }
     pub fn marginal_regeneration_enabled(&self) -> bool { let mut f = 0; check(unsafe { sbx_drainage_marginal_regeneration(self.h, &mut f) }); f != 0 }
     pub fn set_tfe_thickness_ratio(&mut self, ratio: f64) { check(unsafe { sbx_drainage_set_tfe_ratio(self.h, ratio) }); }

@@ -32,6 +32,11 @@ pub struct sbx_view { pub cam_pos: [f64; 3], pub n_film: f64, pub intensity: f32
 #[derive(Debug, Clone, Copy)]
 pub struct sbx_tfe_front { pub phi_center: f64, pub extent: f64, pub width: f64, pub velocity: f64 }
 
+/// what RenderPipeline::update reads after a step (pipeline.rs:1298-1312), fetched behind one synchronisation
+#[repr(C)]
+#[derive(Debug, Clone, Copy)]
+pub struct sbx_frame_stats { pub min_thickness: f64, pub max_thickness: f64, pub thickness: f64, pub time: f64, pub has_critical: i32, pub _pad: i32 }
+
 /// current_time, next_tfe_spawn_time and tfe_fronts of DrainageSimulator (drainage.rs:237-255): checkpoint / resume
 #[repr(C)]
 #[derive(Debug, Clone, Copy)]
@@ -124,6 +129,7 @@ extern "C" {
                                   in_dtype: i32, host_out_h: *mut c_void, out_dtype: i32, host_out_rgb: *mut c_void) -> i32;
     pub fn sbx_drainage_download_rgb(h: *mut sbx_drainage, host: *mut c_void) -> i32;
     pub fn sbx_drainage_fronts(h: *mut sbx_drainage, out8: *mut sbx_tfe_front, count: *mut i32) -> i32;
+    pub fn sbx_drainage_frame_stats(h: *mut sbx_drainage, bubble: i32, theta: f64, phi: f64, out: *mut sbx_frame_stats) -> i32;
     pub fn sbx_drainage_get_state(h: *mut sbx_drainage, out: *mut sbx_tfe_state) -> i32;
     pub fn sbx_drainage_set_state(h: *mut sbx_drainage, state: *const sbx_tfe_state) -> i32;
     pub fn sbx_drainage_params_get(h: *mut sbx_drainage, out: *mut sbx_drainage_params) -> i32;

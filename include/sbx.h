@@ -208,6 +208,18 @@ int32_t sbx_drainage_minmax(sbx_drainage *h, double *min_out, double *max_out);
  * Results are identical either way; no reference equivalent (its folds are separate passes, drainage.rs:180-193). */
 int32_t sbx_drainage_track_minmax(sbx_drainage *h, int32_t mode);
 int32_t sbx_drainage_has_critical(sbx_drainage *h, int32_t *out);
+/* Everything RenderPipeline::update reads after a step (src/render/pipeline.rs:1298-1312: min_thickness, max_thickness,
+ * get_thickness(theta, phi), has_critical_region; plus current_time) in ONE call and one synchronisation of the handle's
+ * stream instead of one per query.  Same values as the separate entry points.  A shim that keeps the reference's
+ * separate methods calls this from the first query after a step (with the (theta, phi) its caller asked for last
+ * frame) and serves the others from the result. */
+typedef struct {
+    double min_thickness, max_thickness; /* metres, over the owned rows of all bubbles */
+    double thickness;                    /* get_thickness(theta, phi) of `bubble` */
+    double time;                         /* current_time */
+    int32_t has_critical, _pad;
+} sbx_frame_stats;
+int32_t sbx_drainage_frame_stats(sbx_drainage *h, int32_t bubble, double theta, double phi, sbx_frame_stats *out);
 int32_t sbx_drainage_critical_thickness(sbx_drainage *h, double *out); /* drainage.rs:570-572 */
 int32_t sbx_drainage_current_time(sbx_drainage *h, double *out);       /* drainage.rs:560-562; gpu_drainage.rs:464-466 */
 /* reset (drainage.rs:575-583; gpu_drainage.rs:415-432: also concentration := 0.5) */

@@ -82,6 +82,11 @@ class TfeFrontC(C.Structure):
                 ("velocity", C.c_double)]
 
 
+class FrameStatsC(C.Structure):
+    _fields_ = [("min_thickness", C.c_double), ("max_thickness", C.c_double), ("thickness", C.c_double),
+                ("time", C.c_double), ("has_critical", C.c_int32), ("_pad", C.c_int32)]
+
+
 class TfeStateC(C.Structure):
     _fields_ = [("time", C.c_double), ("next_spawn", C.c_double), ("count", C.c_int32), ("_pad", C.c_int32),
                 ("fronts", TfeFrontC * 8)]
@@ -121,6 +126,7 @@ _SIGS = {
     "sbx_drainage_tfe_ratio": [C.c_void_p, C.POINTER(C.c_double)],
     "sbx_drainage_active_tfe_count": [C.c_void_p, C.POINTER(C.c_int32)],
     "sbx_drainage_fronts": [C.c_void_p, C.POINTER(TfeFrontC), C.POINTER(C.c_int32)],
+    "sbx_drainage_frame_stats": [C.c_void_p, C.c_int32, C.c_double, C.c_double, C.POINTER(FrameStatsC)],
     "sbx_drainage_get_state": [C.c_void_p, C.POINTER(TfeStateC)],
     "sbx_drainage_set_state": [C.c_void_p, C.POINTER(TfeStateC)],
     "sbx_drainage_update_params": [C.c_void_p, C.POINTER(DrainageParamsC)],

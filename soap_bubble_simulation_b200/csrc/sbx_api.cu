@@ -1607,10 +1607,10 @@ extern "C" int32_t sbx_drainage_step_host(sbx_drainage *h, double dt, int32_t ns
 }
 
 // ------------------------------------------------------------------ queries
-extern "C" int32_t sbx_drainage_get_thickness(sbx_drainage *h, int32_t bubble, double theta, double phi, double *out)
+// get_thickness (drainage.rs:516-552): index arithmetic on the host, the blend itself on the device.  Enqueues the
+// sample kernel and the 8-byte copy into scalar_host[0]; the caller synchronises.
+static int32_t enqueue_sample(sbx_drainage *h, int32_t bubble, double theta, double phi)
 {
-    CHECK_H(h);
-    if (!out) return fail(SBX_ERR_INVALID, "out is null");
     if (bubble < 0 || bubble >= h->batch) return fail(SBX_ERR_INVALID, "bubble %d out of range", bubble);
     // index arithmetic of get_thickness (drainage.rs:516-540); the blend itself runs on the device
     const int NT = h->num_theta, NP = h->num_phi;
@@ -1636,26 +1636,55 @@ extern "C" int32_t sbx_drainage_get_thickness(sbx_drainage *h, int32_t bubble, d
     else CU(launch_sample<float>(tbuf<float>(h, h->cur), r0 + pj, r0 + pj_hi, r1 + pj, r1 + pj_hi, tf, pf, h->b_href[bubble], h->scalar_dev, h->stream));
     h->launches++;
     CU(cudaMemcpyAsync(h->scalar_host, h->scalar_dev, sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    return SBX_OK;
+}
+
+extern "C" int32_t sbx_drainage_get_thickness(sbx_drainage *h, int32_t bubble, double theta, double phi, double *out)
+{
+    CHECK_H(h);
+    if (!out) return fail(SBX_ERR_INVALID, "out is null");
+    int32_t rc = enqueue_sample(h, bubble, theta, phi);
+    if (rc != SBX_OK) return rc;
     CU(cudaStreamSynchronize(h->stream));
     *out = h->scalar_host[0];
     return SBX_OK;
 }
 
-extern "C" int32_t sbx_drainage_minmax(sbx_drainage *h, double *min_out, double *max_out)
+// min / max of the current field in two halves around ONE synchronisation of the handle's stream:
+// enqueue_minmax() queues whatever has to run (nothing if cached; a 16-byte-per-bubble fetch if the last step kernel
+// left the extremes behind; else one reduction pass + the fetch of its partials), finish_minmax() decodes afterwards.
+static int32_t enqueue_minmax(sbx_drainage *h, int *pending)
 {
-    CHECK_H(h);
     // The reference's frame loop asks for min, max and has_critical_region one after the other (pipeline.rs:1298-1312,
     // three full passes on the CPU); here the first query after the field changed runs ONE pass over the owned rows
     // of all bubbles and the others reuse it.
+    *pending = 0;
     if (!h->mm_valid && h->stepped_since_mm) {
         h->stepped_since_mm = false;
         h->mm_auto_misses = 0;
         if (++h->mm_auto_hits >= 2) h->mm_auto_on = true;
     }
-    if (!h->mm_valid && h->mm_kernel_valid) {  // the last step kernel left them behind: 16 bytes per bubble to fetch
+    if (h->mm_valid) return SBX_OK;
+    if (h->mm_kernel_valid) {  // the last step kernel left them behind: 16 bytes per bubble to fetch
         const size_t wb = h->f64 ? 8 : 4, set_bytes = (size_t)h->batch * 2 * wb;
         CU(cudaMemcpyAsync(h->mm_track_host, h->mm_track[h->mm_track_set], set_bytes, cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
+        *pending = 1;
+        return SBX_OK;
+    }
+    const int nb = sbx_drainage::kMinmaxBlocks;
+    const long long n = (long long)h->rows_local * h->num_phi;  // owned rows only (ghost rows are skipped)
+    const double *href = h->href_zero || h->f64 ? nullptr : h->href_dev;
+    if (h->f64) CU(launch_minmax<double>(tbuf<double>(h, h->cur), h->batch, h->bubble_stride, h->num_phi, n, href, h->mm_part, nb, h->stream));
+    else CU(launch_minmax<float>(tbuf<float>(h, h->cur), h->batch, h->bubble_stride, h->num_phi, n, href, h->mm_part, nb, h->stream));
+    h->launches++;
+    CU(cudaMemcpyAsync(h->mm_host, h->mm_part, 2 * nb * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
+    *pending = 2;
+    return SBX_OK;
+}
+
+static void finish_minmax(sbx_drainage *h, int pending)
+{
+    if (pending == 1) {
         double mn = INFINITY, mx = -INFINITY;
         for (int b = 0; b < h->batch; ++b) {
             double lo, hi;
@@ -1674,24 +1703,49 @@ extern "C" int32_t sbx_drainage_minmax(sbx_drainage *h, double *min_out, double 
         h->mm_cached[0] = mn;
         h->mm_cached[1] = mx;
         h->mm_valid = true;
-    }
-    if (!h->mm_valid) {
+    } else if (pending == 2) {
         const int nb = sbx_drainage::kMinmaxBlocks;
-        const long long n = (long long)h->rows_local * h->num_phi;  // owned rows only (ghost rows are skipped)
-        const double *href = h->href_zero || h->f64 ? nullptr : h->href_dev;
-        if (h->f64) CU(launch_minmax<double>(tbuf<double>(h, h->cur), h->batch, h->bubble_stride, h->num_phi, n, href, h->mm_part, nb, h->stream));
-        else CU(launch_minmax<float>(tbuf<float>(h, h->cur), h->batch, h->bubble_stride, h->num_phi, n, href, h->mm_part, nb, h->stream));
-        h->launches++;
-        CU(cudaMemcpyAsync(h->mm_host, h->mm_part, 2 * nb * sizeof(double), cudaMemcpyDeviceToHost, h->stream));
-        CU(cudaStreamSynchronize(h->stream));
         double mn = INFINITY, mx = -INFINITY;
         for (int i = 0; i < nb; ++i) { mn = fmin(mn, h->mm_host[2 * i]); mx = fmax(mx, h->mm_host[2 * i + 1]); }
         h->mm_cached[0] = mn;
         h->mm_cached[1] = mx;
         h->mm_valid = true;
     }
+}
+
+extern "C" int32_t sbx_drainage_minmax(sbx_drainage *h, double *min_out, double *max_out)
+{
+    CHECK_H(h);
+    int pending = 0;
+    int32_t rc = enqueue_minmax(h, &pending);
+    if (rc != SBX_OK) return rc;
+    if (pending) {
+        CU(cudaStreamSynchronize(h->stream));
+        finish_minmax(h, pending);
+    }
     if (min_out) *min_out = h->mm_cached[0];
     if (max_out) *max_out = h->mm_cached[1];
+    return SBX_OK;
+}
+
+// The values RenderPipeline::update reads after every step (pipeline.rs:1298-1312: min_thickness, max_thickness,
+// get_thickness(pi/2, 0), has_critical_region, current_time) behind ONE synchronisation instead of one per query.
+extern "C" int32_t sbx_drainage_frame_stats(sbx_drainage *h, int32_t bubble, double theta, double phi, sbx_frame_stats *out)
+{
+    CHECK_H(h);
+    if (!out) return fail(SBX_ERR_INVALID, "out is null");
+    int pending = 0;
+    int32_t rc = enqueue_minmax(h, &pending);
+    if (rc == SBX_OK) rc = enqueue_sample(h, bubble, theta, phi);
+    if (rc != SBX_OK) return rc;
+    CU(cudaStreamSynchronize(h->stream));
+    finish_minmax(h, pending);
+    out->min_thickness = h->mm_cached[0];
+    out->max_thickness = h->mm_cached[1];
+    out->thickness = h->scalar_host[0];
+    out->time = h->time;
+    out->has_critical = h->mm_cached[0] < (h->wgsl ? (double)h->wp.critical_thickness : h->critical) ? 1 : 0;  // drainage.rs:565-567
+    out->_pad = 0;
     return SBX_OK;
 }
 

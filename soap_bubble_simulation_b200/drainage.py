@@ -121,6 +121,17 @@ class ThicknessField:
 class _DeviceField:
     """Shared handle plumbing for the two simulator mirrors."""
 
+    # every path that changes the device field sets _host_stale = True; the per-frame statistics cache follows it
+    @property
+    def _host_stale(self):
+        return self.__dict__.get("_host_stale_flag", True)
+
+    @_host_stale.setter
+    def _host_stale(self, v):
+        self.__dict__["_host_stale_flag"] = v
+        if v:
+            self.__dict__["_host_stale_stats"] = True
+
     def __init__(self, cfg: L.DrainageCfgC, device: int, keep=()):
         self._keep = keep  # keeps numpy arrays behind cfg pointers alive during create
         self._h = C.c_void_p()
@@ -179,6 +190,14 @@ class _DeviceField:
         L.check(L.lib().sbx_drainage_minmax(self._h, C.byref(mn), C.byref(mx)))
         return mn.value, mx.value
 
+    def frame_stats(self, theta: float, phi: float, bubble: int = 0) -> dict:
+        """min_thickness, max_thickness, get_thickness(theta, phi), has_critical_region and current_time -- what
+        RenderPipeline::update reads after every step (pipeline.rs:1298-1312) -- behind one synchronisation."""
+        st = L.FrameStatsC()
+        L.check(L.lib().sbx_drainage_frame_stats(self._h, bubble, theta, phi, C.byref(st)))
+        return {"min_thickness": st.min_thickness, "max_thickness": st.max_thickness, "thickness": st.thickness,
+                "time": st.time, "has_critical": bool(st.has_critical)}
+
     def track_minmax(self, mode: int) -> None:
         """0 off, 1 on, 2 auto (default): min/max as a by-product of the step kernel instead of a pass over the field."""
         L.check(L.lib().sbx_drainage_track_minmax(self._h, int(mode)))
@@ -192,6 +211,8 @@ class _DeviceField:
     def device_ptr(self, kind: int) -> int:
         p = C.c_void_p()
         L.check(L.lib().sbx_drainage_device_ptr(self._h, kind, C.byref(p)))
+        if kind == L.PTR_THICKNESS:
+            self._host_stale = True  # the caller may write through the pointer
         return p.value
 
     def launch_count(self) -> int:
@@ -337,6 +358,28 @@ class DrainageSimulator(_DeviceField):
     def new(cls, config: SimulationConfig, **kw) -> "DrainageSimulator":  # drainage.rs:263
         return cls(config, **kw)
 
+    # The reference's frame loop calls step, thickness_field().min_thickness(), .max_thickness(), get_thickness(pi/2, 0)
+    # and has_critical_region() one after the other (pipeline.rs:1289-1322).  The mirror keeps those separate methods
+    # but serves them from ONE sbx_drainage_frame_stats call: the first query after the field changed fetches all of
+    # them, with the (theta, phi) the caller asked for last frame.
+    def _frame(self, theta=None, phi=None, bubble=0):
+        self._field._flush()
+        c = getattr(self, "_frame_cache", None)
+        if self._host_stale_stats or c is None or (theta is not None and c["args"] != (theta, phi, bubble)):
+            if theta is None:
+                theta, phi, bubble = getattr(self, "_last_query", (math.pi / 2.0, 0.0, 0))
+                if not (self.row_begin * math.pi / (self.num_theta - 1) <= theta <= (self.row_end - 2) * math.pi / (self.num_theta - 1)):
+                    theta = (self.row_begin + 0.5 * (self.rows_local - 1)) * math.pi / (self.num_theta - 1)  # a row this band owns
+            c = self.frame_stats(theta, phi, bubble)
+            c["args"] = (theta, phi, bubble)
+            self._frame_cache = c
+            self._host_stale_stats = False
+        return c
+
+    def minmax(self):
+        c = self._frame()
+        return c["min_thickness"], c["max_thickness"]
+
     def step(self, dt: float, nsteps: int = 1) -> None:  # drainage.rs:298-392
         self._field._flush()
         L.check(L.lib().sbx_drainage_step(self._h, dt, nsteps))
@@ -347,10 +390,8 @@ class DrainageSimulator(_DeviceField):
         super().step_fused(dt, view, nsteps)
 
     def get_thickness(self, theta: float, phi: float, bubble: int = 0) -> float:  # drainage.rs:516-552
-        self._field._flush()
-        out = C.c_double()
-        L.check(L.lib().sbx_drainage_get_thickness(self._h, bubble, theta, phi, C.byref(out)))
-        return out.value
+        self._last_query = (theta, phi, bubble)
+        return self._frame(theta, phi, bubble)["thickness"]
 
     def thickness_field(self) -> ThicknessField:  # drainage.rs:555-557
         return self._field
@@ -361,10 +402,7 @@ class DrainageSimulator(_DeviceField):
         return out.value
 
     def has_critical_region(self) -> bool:  # drainage.rs:565-567
-        self._field._flush()
-        out = C.c_int32()
-        L.check(L.lib().sbx_drainage_has_critical(self._h, C.byref(out)))
-        return bool(out.value)
+        return self._frame()["has_critical"]
 
     def critical_thickness(self) -> float:  # drainage.rs:570-572
         out = C.c_double()
@@ -425,3 +463,4 @@ class DrainageSimulator(_DeviceField):
     def set_physics(self, density, gravity, viscosity, diffusion, critical_thickness_m, radius_m) -> None:
         L.check(L.lib().sbx_drainage_set_physics(self._h, density, gravity, viscosity, diffusion,
                                                  critical_thickness_m, radius_m))
+        self._host_stale_stats = True  # has_critical_region depends on the critical thickness

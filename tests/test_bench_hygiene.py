@@ -52,3 +52,37 @@ def test_reference_arm_prints_the_cuda_arms_config():
     with open(os.path.join(ROOT, "bench.py")) as f:
         src = f.read()
     assert src.count('"config": wl["config"]') == 2  # both arms emit the same object
+
+
+def test_parity_check_logic_accepts_the_oracle_and_rejects_a_wrong_row():
+    """bench.py's check_sphere (the driver-visible parity gate of sharded runs) on CPU: fed with the whole-sphere oracle's
+    own rows it must pass; with one band's boundary row shifted by one row (a stale ghost row) it must fail."""
+    code = r'''
+import bench, json, numpy as np
+import soap_bubble_simulation_b200  # noqa: F401  (package import only: no device needed for the host-side helpers)
+from soap_bubble_simulation_b200.synth import synthetic_field, dt_max
+from soap_bubble_simulation_b200.sharding import band_partition
+from soap_bubble_simulation_b200.drainage import View
+O = bench.oracle_module()
+nt, nphi, steps, world = 96, 64, 5, 3
+dt = 0.25 * dt_max(nt, nphi)
+view = View()
+ora = O.OracleDrainage(nt, nphi)
+ora.data[:] = synthetic_field(nt, nphi, dtype=np.float32).astype(np.float64)
+ora.step(dt, steps)
+full = ora.data.astype(np.float32)
+px = O.shade_field(ora.data, nt, 0, 0.025, view.cam_pos, intensity=view.intensity, mode=1)
+bands = band_partition(nt, world)
+edges = [bench.sphere_edges(full[a:b], px[a:b]) for a, b in bands]
+good = bench.check_sphere(view, nt, nphi, dt, steps, bands, edges, "unit test")
+bad_field = full.copy()
+a1 = bands[1][0]
+bad_field[a1] = full[a1 + 1]  # rank 1's first row computed from a stale ghost row would look like this
+edges_bad = [bench.sphere_edges(bad_field[a:b], px[a:b]) for a, b in bands]
+bad = bench.check_sphere(view, nt, nphi, dt, steps, bands, edges_bad, "unit test")
+print("RESULT", json.dumps([good["ok"], good["max_rel"], good["rgba_max_lsb"], good["rows_checked"], bad["ok"], bad["max_rel"]]))
+'''
+    out = run_py(code)
+    ok, rel, lsb, rows, bad_ok, bad_rel = json.loads(re.search(r"RESULT (.*)", out).group(1))
+    assert ok and rel <= 1.2e-7 and lsb <= 1 and rows == 3 * 2 * 8
+    assert not bad_ok and bad_rel > 1e-5

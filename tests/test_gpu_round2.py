@@ -343,3 +343,39 @@ def test_foam_step_host_pipelined_equals_separate_calls(S, monkeypatch, offset_s
         sim.step_host(1e-3, 1, view, cur, out_h, out_px)
         assert float(np.abs(out_h[b] / ora.data - 1).max()) <= 1e-5
         break
+
+
+# ------------------------------------------------------------------ the reference's frame loop behind one synchronisation
+def test_frame_stats_equal_the_separate_queries(S):
+    """sbx_drainage_frame_stats = min_thickness, max_thickness, get_thickness, has_critical_region, current_time of
+    RenderPipeline::update (pipeline.rs:1298-1312) in one call; the Python mirror serves its separate methods from it."""
+    from soap_bubble_simulation_b200 import _lib as L
+    import ctypes as C
+
+    nt, nphi = 96, 1024
+    sim = make_sim(S, nt, nphi, S.PREC_F32, h_ref=0.0)
+    f = synthetic_field(nt, nphi, dtype=np.float32)
+    f[40, 7] = 4e-9  # one sub-critical cell
+    sim.upload(f)
+    ora = O.OracleDrainage(nt, nphi)
+    ora.data[:] = f.astype(np.float64)
+    dt = 0.25 * dt_max(nt, nphi)
+    view = S.View()
+    for frame in range(4):  # the tracked min/max of the step kernel switches itself on after two frames
+        sim.step_fused(dt, view, 1)
+        ora.step(dt, 1)
+        st = sim.frame_stats(math.pi / 2, 0.3)
+        # the separate C entry points give the same numbers
+        mn, mx, th, crit = C.c_double(), C.c_double(), C.c_double(), C.c_int32()
+        L.check(L.lib().sbx_drainage_minmax(sim._h, C.byref(mn), C.byref(mx)))
+        L.check(L.lib().sbx_drainage_get_thickness(sim._h, 0, math.pi / 2, 0.3, C.byref(th)))
+        L.check(L.lib().sbx_drainage_has_critical(sim._h, C.byref(crit)))
+        assert (st["min_thickness"], st["max_thickness"], st["thickness"], st["has_critical"]) == (mn.value, mx.value, th.value, bool(crit.value))
+        assert st["time"] == sim.current_time() and st["has_critical"]
+        assert abs(st["thickness"] / ora.get_thickness(math.pi / 2, 0.3) - 1) <= 1e-5
+        assert abs(st["max_thickness"] / ora.max_thickness() - 1) <= 1e-5
+        # the mirror's reference-shaped methods: served from one fetch per frame
+        fld = sim.thickness_field()
+        assert (fld.min_thickness(), fld.max_thickness()) == (mn.value, mx.value)
+        assert sim.get_thickness(math.pi / 2, 0.3) == th.value and sim.has_critical_region()
+    assert sim.get_thickness(1.0, 2.0) == pytest.approx(ora.get_thickness(1.0, 2.0), rel=1e-5)  # other arguments: refetched
