@@ -105,6 +105,7 @@ struct StepArgs {
     // bot_rows rows; 0 = no special band) and, with boundary_first, dispatched before the interior bands, so that its
     // boundary row reaches the neighbour -- and the "step finished here" flag is released -- early in the launch
     int top_rows, bot_rows, boundary_first;
+    int ring_stages;         // TMA kernel: stages of the shared-memory ring in this launch (2 or 3)
     int l2_keep_edges;       // TMA kernel: L2 evict_last policy on the rows neighbouring bands share (fields larger than L2)
     // TMA kernel: min / max of the stored values this launch writes, as a by-product (nullptr: off).  Two
     // order-preserving unsigned words {min, max} per bubble (32-bit for f32 storage, 64-bit for f64), merged with

@@ -19,7 +19,7 @@ namespace sbx {
 
 namespace {
 
-constexpr int kStages = 3;        // ring depth
+constexpr int kStages = 3;        // ring depth at most (barriers are laid out for it); StepArgs::ring_stages = 2 or 3 per launch
 constexpr int kRowsPerStage = 3;  // theta rows per stage == the unroll of the three-row register window
 constexpr int kMaxBandRows = 64;
   // rows a CTA marches at most (their coefficients are staged in shared memory)
@@ -82,8 +82,9 @@ __global__ void __launch_bounds__(PK == 2 ? 160 : 288, MinBlocks<T>::value) k_ma
     const int c0 = blockIdx.x * strip_w_max;
     const int w = min(strip_w_max, N - c0);   // multiple of VEC
     const int rowf = strip_w_max + 2 * HALO;  // elements per ring row
+    const int stages = a.ring_stages;  // 2 or 3 (uniform)
     T *ring = reinterpret_cast<T *>(smem_raw);
-    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)kStages * kRowsPerStage * rowf * sizeof(T));
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem_raw + (size_t)stages * kRowsPerStage * rowf * sizeof(T));
     uint64_t *empty = full + kStages;
 
     const int b = blockIdx.z;
@@ -110,7 +111,7 @@ __global__ void __launch_bounds__(PK == 2 ? 160 : 288, MinBlocks<T>::value) k_ma
     // own set-up (barrier init) before waiting for the previous step's grid to finish and flush its writes.
     asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
     if (threadIdx.x == 0) {
-        for (int s = 0; s < kStages; ++s) {
+        for (int s = 0; s < stages; ++s) {
             mbar_init(&full[s], 1);
             mbar_init(&empty[s], nwarps_c);
         }
@@ -134,9 +135,9 @@ __global__ void __launch_bounds__(PK == 2 ? 160 : 288, MinBlocks<T>::value) k_ma
             // 8192 x 16384; on an L2-resident field (2048 x 4096) the same hint costs 7 %, so the host decides.
             const bool keep_edges = a.l2_keep_edges != 0;
             const uint64_t pol = keep_edges ? l2_policy_evict_last() : 0ull;
-            for (int c = 0; c < nchunks; ++c) {
-                const int s = c % kStages;
-                if (c >= kStages) mbar_wait(&empty[s], (uint32_t)(((c / kStages) - 1) & 1));
+            int s = 0, round = 0;  // stage of chunk c and how often the ring has wrapped
+            for (int c = 0; c < nchunks; ++c, s = (s + 1 == stages ? 0 : s + 1), round += (s == 0)) {
+                if (round > 0) mbar_wait(&empty[s], (uint32_t)((round - 1) & 1));
                 const int r_begin = c * kRowsPerStage;
                 const int r_end = min(r_begin + kRowsPerStage, rows_load);
                 mbar_expect_tx(&full[s], row_bytes * (uint32_t)(r_end - r_begin));
@@ -240,7 +241,7 @@ __global__ void __launch_bounds__(PK == 2 ? 160 : 288, MinBlocks<T>::value) k_ma
     auto release_stage = [&](uint32_t bits) {
         __syncwarp();
         if (lane == 0) mbar_arrive_after(&empty[stage], bits);  // every lane of this warp has read the stage
-        if (++stage == kStages) { stage = 0; full_parity ^= 1u; stage_p = ring_t; }
+        if (++stage == stages) { stage = 0; full_parity ^= 1u; stage_p = ring_t; }
         else stage_p += stage_elems;
     };
     auto row_bits = [&](const RowT &r) {
@@ -484,9 +485,9 @@ __global__ void __launch_bounds__(PK == 2 ? 160 : 288, MinBlocks<T>::value) k_ma
         peer_signal_done(a.peer, a.peer.up_ghost && l0 == 1, a.peer.dn_ghost && l1 == a.l_last && a.peer.push_dn_grow >= 0, C, tid);
 }
 
-static size_t march_tma_smem_bytes(int packets)  // 16-byte packets per strip row
+static size_t march_tma_smem_bytes(int packets, int stages)  // 16-byte packets per strip row
 {
-    return (size_t)kStages * kRowsPerStage * (16 * packets + 32) + 2 * kStages * sizeof(uint64_t);
+    return (size_t)stages * kRowsPerStage * (16 * packets + 32) + 2 * kStages * sizeof(uint64_t);
 }
 
 static bool use_pdl()
@@ -603,7 +604,17 @@ cudaError_t launch_march_tma(StepArgs<T> a, int batch, bool tfe, int band_rows_r
     const int packets = tma_consumers<T>(a.num_phi);  // 16-byte packets per strip row
     const int strip = packets * VEC;
     const int gx = (a.num_phi + strip - 1) / strip;
-    const size_t smem = march_tma_smem_bytes(packets);
+    // Ring depth: three stages (9 rows in flight per CTA) by default; two stages for the f32 LUT / colourless step of a
+    // single bubble on many-wave launches, where the shorter ring is faster (same-box A/B, profiles/r02_ab_ring_stages.txt:
+    // 8192 x 16384 fused 508.3 -> 516.5 Gcell/s (+1.6 %), drainage only 787.5 -> 806.7 (+2.4 %)) -- and nowhere else:
+    // f64 fused 296.0 -> 288.2, two-beam 445.9 -> 443.3, foam 4096 bubbles 492 -> 486, 2048 x 4096 455 -> 447 (short bands
+    // and heavier rows want the deeper prefetch).  SBX_RING_STAGES=2/3 overrides.
+    static const int stages_env = [] { const char *e = getenv("SBX_RING_STAGES"); return e ? atoi(e) : 0; }();
+    const long long ctas_est = (long long)gx * ((rows + 23) / 24);
+    const bool shallow = sizeof(T) == 4 && batch == 1 && (a.rgb.mode == SBX_RGB_NONE || a.rgb.mode == SBX_RGB_LUT) &&
+                         ctas_est >= 3LL * device_sm_count() * MinBlocks<T>::value;
+    a.ring_stages = stages_env == 2 || stages_env == 3 ? stages_env : (shallow ? 2 : 3);
+    const size_t smem = march_tma_smem_bytes(packets, a.ring_stages);
     const int pk = tma_packets_per_thread<T>(a, packets);
     const int consumers = packets / pk;
     // resident CTAs per SM of this launch shape (narrow strips have smaller CTAs and more of them fit), asked once
