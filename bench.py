@@ -49,7 +49,7 @@ NUM_PHI = 16384
 FOAM_BUBBLES, FOAM_NT, FOAM_NPHI = 4096, 256, 512
 BYTES_PER_CELL = 12  # read h (4) + write h' (4) + write RGBA8 (4); SURVEY.md section 8d
 FALLBACK_HBM_GBS = 6650.0  # B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
-KERNEL_SOURCES = ("sbx_march_tma.cu", "sbx_device.cuh", "sbx_tma.cuh", "sbx_internal.cuh")
+KERNEL_SOURCES = ("sbx_march_tma.cu", "sbx_device.cuh", "sbx_tma.cuh", "sbx_internal.cuh", "sbx_launch.h")
 
 
 def log(*a):

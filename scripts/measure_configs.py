@@ -121,6 +121,10 @@ if "hl" in which:  # headline only (A/B runs)
     single("C3 8192x16384 f32 fused LUT->RGBA8 (headline)", 8192, 16384, S.PREC_F32, S.RGB_LUT, 200, 12)
     single("C2 2048x4096 f32 fused LUT->RGBA8", 2048, 4096, S.PREC_F32, S.RGB_LUT, 400, 12)
 
+if "exact_hl" in which:  # the headline alone (A/B of run-time knobs)
+    single("C3 8192x16384 f32 fused LUT->RGBA8 (headline)", 8192, 16384, S.PREC_F32, S.RGB_LUT, 200, 12)
+    single("C3 8192x16384 f32 drainage only", 8192, 16384, S.PREC_F32, S.RGB_NONE, 100, 8)
+
 if "tfe" in which:
     # The headline run starts at t = 0, where no marginal-regeneration front exists yet (first spawn at t = 0.5 s,
     # drainage.rs:397-403), so it runs the kernel's no-front instantiation.  This line times the TFE = true

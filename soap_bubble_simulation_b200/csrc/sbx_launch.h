@@ -5,14 +5,17 @@
 
 namespace sbx {
 
-// Rows per latitude band for the marching kernels.  Large grids run many waves of CTAs and the band height does not
-// matter (24 rows measured flat at 8192 x 16384); when the whole launch is only a few waves (< 16), a band height that leaves
-// the last wave half empty costs its full time -- 2048 x 4096 at 24 rows is 344 CTAs on 592 slots, at 14 rows 588:
-// +30 %.  Cost model: waves x (band rows + ring fill / halo overhead).
+// Rows per latitude band for the marching kernels.  Launches of many waves of CTAs (>= 8) take the default height: with
+// the L1-friendly carveout of round 2, 24-row bands measured best at 8192 x 16384 (fused 528 Gcell/s against 511-517 at the
+// 56 rows the whole-wave model picked; drainage only 820 against 788-807; profiles/r02_ab_band_rows.txt) -- a partial last
+// wave is cheap when there are nine of them, shorter bands keep the band-edge rows in L2 and start more CTAs' streams early.
+// When the whole launch is only a few waves, a band height that leaves the last wave half empty costs its full time --
+// 2048 x 4096 at 24 rows is 344 CTAs on 592 slots, at 14 rows 588: +30 %.  Cost model there: waves x (band
+// rows + ring fill / halo overhead).
 inline int auto_band_rows(int rows, long long ctas_per_band, int slots, int dflt)
 {
     if (rows <= 0) return 1;
-    if (slots <= 0 || ctas_per_band * ((rows + dflt - 1) / dflt) >= 16LL * slots) return dflt < rows ? dflt : rows;
+    if (slots <= 0 || ctas_per_band * ((rows + dflt - 1) / dflt) >= 8LL * slots) return dflt < rows ? dflt : rows;
     int best = dflt < rows ? dflt : rows;
     double best_cost = 1e300;
     for (int b = 6; b <= 64 && b <= rows; ++b) {

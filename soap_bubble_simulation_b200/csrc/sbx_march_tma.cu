@@ -604,16 +604,12 @@ cudaError_t launch_march_tma(StepArgs<T> a, int batch, bool tfe, int band_rows_r
     const int packets = tma_consumers<T>(a.num_phi);  // 16-byte packets per strip row
     const int strip = packets * VEC;
     const int gx = (a.num_phi + strip - 1) / strip;
-    // Ring depth: three stages (9 rows in flight per CTA) by default; two stages for the f32 LUT / colourless step of a
-    // single bubble on many-wave launches, where the shorter ring is faster (same-box A/B, profiles/r02_ab_ring_stages.txt:
-    // 8192 x 16384 fused 508.3 -> 516.5 Gcell/s (+1.6 %), drainage only 787.5 -> 806.7 (+2.4 %)) -- and nowhere else:
-    // f64 fused 296.0 -> 288.2, two-beam 445.9 -> 443.3, foam 4096 bubbles 492 -> 486, 2048 x 4096 455 -> 447 (short bands
-    // and heavier rows want the deeper prefetch).  SBX_RING_STAGES=2/3 overrides.
+    // Ring depth: three stages (9 rows in flight per CTA).  A two-stage ring looked better while the bands were 56 rows high
+    // (508 -> 516 Gcell/s); at the 24-row bands many-wave launches use now the deeper ring is as fast for the fused step and
+    // faster for the colourless one (528.3 / 819.9 vs 528.9 / 798.0, profiles/r02_ab_band_rows.txt).  SBX_RING_STAGES=2
+    // keeps the variant for A/B runs.
     static const int stages_env = [] { const char *e = getenv("SBX_RING_STAGES"); return e ? atoi(e) : 0; }();
-    const long long ctas_est = (long long)gx * ((rows + 23) / 24);
-    const bool shallow = sizeof(T) == 4 && batch == 1 && (a.rgb.mode == SBX_RGB_NONE || a.rgb.mode == SBX_RGB_LUT) &&
-                         ctas_est >= 3LL * device_sm_count() * MinBlocks<T>::value;
-    a.ring_stages = stages_env == 2 || stages_env == 3 ? stages_env : (shallow ? 2 : 3);
+    a.ring_stages = stages_env == 2 ? 2 : 3;
     const size_t smem = march_tma_smem_bytes(packets, a.ring_stages);
     const int pk = tma_packets_per_thread<T>(a, packets);
     const int consumers = packets / pk;

@@ -270,9 +270,10 @@ extern "C" void eval_ff(int gamma, double n, const float *h, const float *href, 
 
 
 def test_band_height_model_picks_whole_waves(tmp_path):
-    """auto_band_rows (csrc/sbx_launch.h, host code): the band height that fills whole waves of CTAs.  The documented
-    choices -- 56 rows at 8192 x 16384 (16 strips, 592 CTA slots: 3.97 waves), 14 rows at 2048 x 4096 (4 strips: one
-    wave of 588 CTAs), the default for launches of 16 waves or more -- are what DESIGN.md 4.1 / BASELINE.md quote."""
+    """auto_band_rows (csrc/sbx_launch.h, host code): the band height that fills whole waves of CTAs on launches of a few
+    waves, the default (24 rows) from 8 waves up.  The documented choices -- 24 rows at 8192 x 16384 (16 strips, 592 CTA
+    slots: 9.2 waves; round 1 used the whole-wave model's 56 rows there), 14 rows at 2048 x 4096 (4 strips: one wave of
+    588 CTAs) -- are what DESIGN.md 4.1 / BASELINE.md quote."""
     cpp = tmp_path / "band.cpp"
     cpp.write_text('#include "sbx_launch.h"\nextern "C" int band(int rows, long long per_band, int slots, int dflt)\n'
                    "{ return sbx::auto_band_rows(rows, per_band, slots, dflt); }\n")
@@ -283,7 +284,9 @@ def test_band_height_model_picks_whole_waves(tmp_path):
     lib.band.argtypes = [ctypes.c_int, ctypes.c_longlong, ctypes.c_int, ctypes.c_int]
     slots = 148 * 4
     b3 = lib.band(8190, 16, slots, 24)
-    assert b3 == 56 and math.ceil(8190 / b3) * 16 <= 4 * slots
+    assert b3 == 24  # 9.2 waves: the default height (measured best, profiles/r02_ab_band_rows.txt)
+    b4 = lib.band(4094, 16, slots, 24)  # 4.6 waves at 24 rows: still the whole-wave model
+    assert math.ceil(4094 / b4) * 16 <= math.ceil(math.ceil(4094 / b4) * 16 / slots) * slots and b4 != 24
     b2 = lib.band(2046, 4, slots, 24)
     assert b2 == 14 and math.ceil(2046 / b2) * 4 <= slots
     assert lib.band(254, 4096, slots, 24) == 24   # foam of 4096 bubbles: far more than 16 waves, default height
