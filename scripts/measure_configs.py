@@ -125,6 +125,11 @@ if "exact_hl" in which:  # the headline alone (A/B of run-time knobs)
     single("C3 8192x16384 f32 fused LUT->RGBA8 (headline)", 8192, 16384, S.PREC_F32, S.RGB_LUT, 200, 12)
     single("C3 8192x16384 f32 drainage only", 8192, 16384, S.PREC_F32, S.RGB_NONE, 100, 8)
 
+for w in which:  # "grid:<rows>:<cols>": the fused f32 step on any grid (band-height / launch-shape studies)
+    if w.startswith("grid:"):
+        _, gnt, gnphi = w.split(":")
+        single(f"grid {gnt}x{gnphi} f32 fused LUT->RGBA8", int(gnt), int(gnphi), S.PREC_F32, S.RGB_LUT, 300, 12)
+
 if "tfe" in which:
     # The headline run starts at t = 0, where no marginal-regeneration front exists yet (first spawn at t = 0.5 s,
     # drainage.rs:397-403), so it runs the kernel's no-front instantiation.  This line times the TFE = true

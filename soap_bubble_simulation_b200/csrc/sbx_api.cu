@@ -973,6 +973,10 @@ static void fill_peer(sbx_drainage *h, PeerArgs &p)
     p.status = (unsigned int *)(h->sync_dev + 4);
     p.push_up_grow = p.up_ghost ? h->row_begin : -1;
     p.push_dn_grow = p.dn_ghost ? h->row_end - 1 : -1;
+#ifdef SBX_PEER_DEBUG
+    static const unsigned dbg = [] { const char *e = getenv("SBX_PEER_DEBUG_BITS"); return e ? (unsigned)atoi(e) : 0u; }();
+    p.debug = dbg;
+#endif
 }
 
 // decide whether this launch writes the pole rows inside the TMA kernel, and which arrival count it waits for.

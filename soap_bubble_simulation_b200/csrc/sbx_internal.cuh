@@ -79,6 +79,9 @@ struct PeerArgs {
     unsigned long long epoch;                  // number of this step, >= 1
     int push_up_grow, push_dn_grow;            // global row whose new values go to the up / down neighbour (-1: none)
     int enabled;
+#ifdef SBX_PEER_DEBUG
+    unsigned debug;  // timing experiments only (results are wrong): 1 no wait, 2 no push, 4 no signal, 8 no system fence
+#endif
 };
 
 // arguments of one drainage step (CPU semantics)

@@ -5,17 +5,32 @@
 
 namespace sbx {
 
-// Rows per latitude band for the marching kernels.  Launches of many waves of CTAs (>= 8) take the default height: with
-// the L1-friendly carveout of round 2, 24-row bands measured best at 8192 x 16384 (fused 528 Gcell/s against 511-517 at the
-// 56 rows the whole-wave model picked; drainage only 820 against 788-807; profiles/r02_ab_band_rows.txt) -- a partial last
-// wave is cheap when there are nine of them, shorter bands keep the band-edge rows in L2 and start more CTAs' streams early.
-// When the whole launch is only a few waves, a band height that leaves the last wave half empty costs its full time --
-// 2048 x 4096 at 24 rows is 344 CTAs on 592 slots, at 14 rows 588: +30 %.  Cost model there: waves x (band
-// rows + ring fill / halo overhead).
+// Rows per latitude band for the marching kernels, from same-box scans on B200 (profiles/r02_ab_band_rows*.txt):
+//  * launches of four waves of CTAs or more take the default height.  With the L1-friendly carveout of round 2, 24-row bands
+//    measured best at 8192 x 16384 (fused 528 Gcell/s against 511-517 at the 56 rows the whole-wave model used to pick;
+//    drainage only 820 against 788-807) and at 4096 x 16384 (511 against 492): a partial last wave is cheap when there are
+//    several, shorter bands start more streams early and keep the band-edge rows in L2;
+//  * two to four waves: the height in [default, default + 8] that fills its last wave best (2048 x 16384: 28 rows = exactly
+//    two waves, 494 Gcell/s against 441 for one wave of 56-row bands and 474 at 24 rows);
+//  * fewer: a band height that leaves the last wave half empty costs its full time -- 2048 x 4096 at 24 rows is 344 CTAs on
+//    592 slots, at 14 rows 588: +30 %; 1024 x 16384: 28 rows = one full wave.  Cost model there: waves x (band rows + ring
+//    fill / halo overhead).
 inline int auto_band_rows(int rows, long long ctas_per_band, int slots, int dflt)
 {
     if (rows <= 0) return 1;
-    if (slots <= 0 || ctas_per_band * ((rows + dflt - 1) / dflt) >= 8LL * slots) return dflt < rows ? dflt : rows;
+    const long long at_dflt = ctas_per_band * ((rows + dflt - 1) / dflt);
+    if (slots <= 0 || at_dflt >= 4LL * slots) return dflt < rows ? dflt : rows;
+    if (at_dflt >= 2LL * slots) {
+        int best = dflt;
+        double best_fill = -1.0;
+        for (int b = dflt; b <= dflt + 8 && b <= rows; ++b) {
+            const long long ctas = ctas_per_band * ((rows + b - 1) / b);
+            const long long waves = (ctas + slots - 1) / slots;
+            const double fill = (double)ctas / (double)(waves * slots);
+            if (fill > best_fill + 1e-9) { best_fill = fill; best = b; }
+        }
+        return best;
+    }
     int best = dflt < rows ? dflt : rows;
     double best_cost = 1e300;
     for (int b = 6; b <= 64 && b <= rows; ++b) {

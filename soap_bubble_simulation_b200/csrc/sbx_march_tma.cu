@@ -143,8 +143,14 @@ __global__ void __launch_bounds__(PK == 2 ? 160 : 288, MinBlocks<T>::value) k_ma
                 mbar_expect_tx(&full[s], row_bytes * (uint32_t)(r_end - r_begin));
                 for (int r = r_begin; r < r_end; ++r) {
                     // ghost rows are written by the neighbours' previous step: wait for it before reading them
+#ifdef SBX_PEER_DEBUG
+                    if (!(a.peer.debug & 1u)) {
+#endif
                     if (r == 0 && touch_top) wait_neighbour(a.peer.flag_from_up, a.peer.epoch - 1, a.peer.status);
                     if (r == rows_load - 1 && touch_bot) wait_neighbour(a.peer.flag_from_dn, a.peer.epoch - 1, a.peer.status);
+#ifdef SBX_PEER_DEBUG
+                    }
+#endif
                     const T *grow_ptr = in + (long long)(l0 - 1 + r) * N;
                     T *dst = ring + ((size_t)s * kRowsPerStage + (r - r_begin)) * rowf;
                     // ring row layout: [0,HALO) left halo | [HALO, HALO+w) main | [HALO+w, 2 HALO+w) right halo
@@ -356,7 +362,11 @@ __global__ void __launch_bounds__(PK == 2 ? 160 : 288, MinBlocks<T>::value) k_ma
                 for (int k = 0; k < W; ++k) { run_lo = tmin<T>(run_lo, nw.v[k]); run_hi = tmax<T>(run_hi, nw.v[k]); }
             }
             store_h(out_p, nw.v);
+#ifdef SBX_PEER_DEBUG
+            if (a.peer.enabled && !(a.peer.debug & 2u)) {
+#else
             if (a.peer.enabled) {  // boundary rows also land in the neighbours' ghost rows (peer stores over NVLink)
+#endif
                 if (grow == a.peer.push_up_grow) store_h(reinterpret_cast<T *>(a.peer.up_ghost) + jc, nw.v);
                 if (grow == a.peer.push_dn_grow) store_h(reinterpret_cast<T *>(a.peer.dn_ghost) + jc, nw.v);
             }
@@ -635,13 +645,14 @@ cudaError_t launch_march_tma(StepArgs<T> a, int batch, bool tfe, int band_rows_r
     // neighbour's next step waits for this band's flag, and the next launch here cannot start before the band that
     // waited for the neighbour has finished; a short band makes both early instead of last.
     static const int edge_env = [] { const char *e = getenv("SBX_EDGE_ROWS"); return e ? atoi(e) : 8; }();
+    static const int edge_min_waves = [] { const char *e = getenv("SBX_EDGE_MIN_WAVES"); return e ? atoi(e) : 3; }();
     a.top_rows = a.bot_rows = a.boundary_first = 0;
     // Only when the launch runs several waves of CTAs: in a single wave every CTA lives for the whole launch anyway and
     // uneven bands only unbalance it (measured at 1024 rows x 16384 per GPU: 40.2 us uniform, 43.1 us with short bands;
     // at 4096 and 8192 rows per GPU the short bands win 0.8 % and 1.2 %).
     const long long ctas_uniform = (long long)gx * ((rows + 23) / 24);
     if (a.peer.enabled && batch == 1 && edge_env > 0 && rows >= 8 * edge_env &&
-        ctas_uniform >= 3LL * device_sm_count() * occ) {
+        ctas_uniform >= (long long)edge_min_waves * device_sm_count() * occ) {
         if (a.peer.up_ghost) a.top_rows = edge_env;
         if (a.peer.dn_ghost && a.peer.push_dn_grow >= 0) a.bot_rows = edge_env;
         a.boundary_first = 1;

@@ -132,6 +132,10 @@ __device__ __forceinline__ void wait_neighbour(const unsigned long long *flag, u
 __device__ __forceinline__ void peer_signal_done(const PeerArgs &p, bool sig_up, bool sig_dn, int consumers, int tid)
 {
     if (!(sig_up || sig_dn)) return;
+#ifdef SBX_PEER_DEBUG
+    if (p.debug & 4u) return;
+    if (!(p.debug & 8u))
+#endif
     __threadfence_system();
     bar_consumers(consumers);
     if (tid == 0) {

@@ -285,11 +285,12 @@ def test_band_height_model_picks_whole_waves(tmp_path):
     slots = 148 * 4
     b3 = lib.band(8190, 16, slots, 24)
     assert b3 == 24  # 9.2 waves: the default height (measured best, profiles/r02_ab_band_rows.txt)
-    b4 = lib.band(4094, 16, slots, 24)  # 4.6 waves at 24 rows: still the whole-wave model
-    assert math.ceil(4094 / b4) * 16 <= math.ceil(math.ceil(4094 / b4) * 16 / slots) * slots and b4 != 24
+    assert lib.band(4094, 16, slots, 24) == 24  # 4.6 waves at 24 rows: the default as well
+    assert lib.band(2046, 16, slots, 24) == 28  # 2.3 waves at 24 rows -> 28 rows = exactly two waves (1184 CTAs)
+    assert lib.band(1022, 16, slots, 24) == 28  # one wave: the whole-wave model (592 CTAs)
     b2 = lib.band(2046, 4, slots, 24)
     assert b2 == 14 and math.ceil(2046 / b2) * 4 <= slots
-    assert lib.band(254, 4096, slots, 24) == 24   # foam of 4096 bubbles: far more than 16 waves, default height
+    assert lib.band(254, 4096, slots, 24) == 24   # foam of 4096 bubbles: many waves, default height
     assert lib.band(10, 1, slots, 24) == 6    # a tiny grid is split into two bands that run side by side
     assert lib.band(0, 1, slots, 24) == 1
     for rows, per_band in ((8190, 16), (2046, 4), (1022, 2), (254, 512), (62, 1)):
