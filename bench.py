@@ -190,7 +190,7 @@ def workload(args, world: int) -> dict:
     nphi = args.phi
     dt = 0.25 * dt_max(nt, nphi)
     rows = nt // world
-    halo = ("none" if world == 1 else "in-kernel peer-memory push over NVLink" if args.halo == "peer"
+    halo = ("none" if world == 1 else "in-kernel peer-memory read over NVLink" if args.halo == "peer"
             else "nccl send/recv per step")
     return {"kind": "sphere", "scaling": "strong" if strong else "weak", "nt": nt, "nphi": nphi, "dt": dt,
             "cells_total": nt * nphi,
@@ -746,7 +746,7 @@ def main():
     ap.add_argument("--other-configs", dest="other_configs", action="store_true", default=True)
     ap.add_argument("--no-other-configs", dest="other_configs", action="store_false")
     ap.add_argument("--halo", default="peer", choices=["peer", "nccl"],
-                    help="multi-GPU halo rows: in-kernel peer-memory push (default) or NCCL send/recv per step")
+                    help="multi-GPU halo rows: in-kernel peer-memory read (default) or NCCL send/recv per step")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)

@@ -363,13 +363,15 @@ int32_t sbx_comm_destroy(sbx_comm *c);
 /* attach a communicator to a sharded handle: every step then exchanges one halo row with the
  * latitude-band neighbours (rank-1 above, rank+1 below) */
 int32_t sbx_drainage_attach_comm(sbx_drainage *h, sbx_comm *c);
-/* Peer-memory halo push (all ranks on one NVLink/NVSwitch box).  Each rank exports a descriptor of its field
+/* Peer-memory halo (all ranks on one NVLink/NVSwitch box).  Each rank exports a descriptor of its field
  * buffers (CUDA IPC handles), the caller moves the blobs between processes (torch.distributed), and attach maps
  * the neighbours' buffers.  From then on the ring kernels (f32 and f64 CPU semantics, WGSL semantics with both of
- * its fields) store each band's boundary rows directly into the neighbours' ghost rows from inside the stencil
- * kernel and order neighbouring steps with two flags in device memory -- no per-step collective.  Requires an
- * attached communicator (used for the exchanges after upload/reset and for the modes the ring kernels do not
- * cover: strict f64, ragged widths, float colour output).  up/down = blob of rank-1 / rank+1 or NULL. */
+ * its fields) read the row next to their band straight out of the neighbour's field from inside the stencil
+ * kernel (a bulk copy from the peer address over NVLink) and order neighbouring steps with two flags in device
+ * memory -- no per-step collective and no remote stores.  Requires an attached communicator (used for the
+ * exchanges around upload / reset / the host-buffer step and for the modes the ring kernels do not cover: strict
+ * f64, ragged widths, float colour output).  A neighbour may read this band's boundary rows until its own step has
+ * finished: keep the handle alive until every rank is done.  up/down = blob of rank-1 / rank+1 or NULL. */
 #define SBX_IPC_BYTES 512
 int32_t sbx_drainage_ipc_export(sbx_drainage *h, uint8_t out[SBX_IPC_BYTES]);
 int32_t sbx_drainage_ipc_attach(sbx_drainage *h, const uint8_t *up, const uint8_t *down);

@@ -97,7 +97,8 @@ struct sbx_drainage {
     cudaEvent_t ev_prev = nullptr, ev_halo = nullptr;
     std::vector<cudaEvent_t> ev_in, ev_comp;
     cudaEvent_t ev_start = nullptr, ev_out = nullptr, ev_all = nullptr;
-    bool ghost_stale = false;  // sharded host-buffer step: the ghost rows of the current buffer were not refreshed
+    bool ghost_stale = false;  // sharded: the ghost rows of the current buffer were not refreshed since the field changed
+    bool stale_by_pull = false;  // ... and only because peer-halo steps read the neighbours' rows in place (flag-ordered)
     void *buf[2] = {nullptr, nullptr};   // thickness ping-pong
     float *conc[2] = {nullptr, nullptr}; // WGSL concentration ping-pong
     int cur = 0;
@@ -595,6 +596,10 @@ static int32_t download_conv(sbx_drainage *h, TH *host, const TS *src)
 
 static int32_t halo_exchange(sbx_drainage *h);
 static int32_t ensure_ghosts(sbx_drainage *h);
+// Peer halo: a neighbour's last ring-kernel step may still be reading this band's boundary rows in place.  Anything
+// that overwrites the field outside such a step first meets the neighbours in a (stream-ordered) ghost-row exchange:
+// its receive cannot complete before the neighbour's send, which is queued behind the neighbour's step.
+static int32_t quiesce_peers(sbx_drainage *h);
 
 extern "C" int32_t sbx_drainage_upload(sbx_drainage *h, const void *host, int32_t dtype)
 {
@@ -602,7 +607,8 @@ extern "C" int32_t sbx_drainage_upload(sbx_drainage *h, const void *host, int32_
     h->mm_valid = h->mm_kernel_valid = false;
     if (!host) return fail(SBX_ERR_INVALID, "host is null");
     if (dtype != SBX_F32 && dtype != SBX_F64) return fail(SBX_ERR_INVALID, "bad dtype %d", dtype);
-    int32_t rc;
+    int32_t rc = quiesce_peers(h);
+    if (rc != SBX_OK) return rc;
     if (h->f64) {
         rc = dtype == SBX_F64 ? upload_conv<double, double>(h, tbuf<double>(h, h->cur), (const double *)host)
                               : upload_conv<double, float>(h, tbuf<double>(h, h->cur), (const float *)host);
@@ -633,6 +639,7 @@ extern "C" int32_t sbx_drainage_upload_concentration(sbx_drainage *h, const floa
     CHECK_H(h);
     if (!h->wgsl) return fail(SBX_ERR_INVALID, "concentration exists only with SBX_SEM_WGSL");
     if (!host) return fail(SBX_ERR_INVALID, "host is null");
+    { int32_t rcq = quiesce_peers(h); if (rcq != SBX_OK) return rcq; }
     const size_t rb = (size_t)h->rows_local * h->num_phi * 4;
     CU(cudaMemcpy2DAsync(h->conc[h->cur] + h->num_phi, (size_t)h->bubble_stride * 4, host, rb, rb, (size_t)h->batch,
                          cudaMemcpyHostToDevice, h->stream));
@@ -951,32 +958,34 @@ static void fill_step_args(sbx_drainage *h, StepArgs<T> &a, double dt, const Rgb
     a.l2_keep_edges = h->l2_keep_edges ? 1 : 0;
 }
 
-// arguments of the in-kernel halo push for the step that writes ping-pong half 1 - cur (every rank writes the same
-// half in the same step); element size = the handle's storage type
+// arguments of the in-kernel halo read for the step that reads ping-pong half cur (every rank reads the same half in
+// the same step); element size = the handle's storage type
 static void fill_peer(sbx_drainage *h, PeerArgs &p)
 {
     p.enabled = 1;
     p.epoch = ++h->epoch;
     const size_t N = (size_t)h->num_phi;
-    const int o = 1 - h->cur;
-    const size_t up_off = (size_t)(h->peer_up_rows + 1) * N;  // the up neighbour's bottom ghost row
-    p.up_ghost = h->peer_up_buf[o] ? (char *)h->peer_up_buf[o] + up_off * h->esz : nullptr;
-    p.dn_ghost = h->peer_dn_buf[o] ? h->peer_dn_buf[o] : nullptr;
-    p.up_ghost2 = h->peer_up_conc[o] ? (char *)h->peer_up_conc[o] + up_off * 4 : nullptr;
-    p.dn_ghost2 = h->peer_dn_conc[o] ? h->peer_dn_conc[o] : nullptr;
-    p.up_flag_remote = h->peer_up_sync ? h->peer_up_sync + 1 : nullptr;  // I am its lower neighbour
-    p.dn_flag_remote = h->peer_dn_sync ? h->peer_dn_sync + 0 : nullptr;  // I am its upper neighbour
-    p.flag_from_up = h->sync_dev + 0;
-    p.flag_from_dn = h->sync_dev + 1;
+    const int c = h->cur;
+    const size_t up_off = (size_t)h->peer_up_rows * N;  // the up neighbour's last owned row (its local row 0 is a ghost row)
+    p.up_row = h->peer_up_buf[c] ? (char *)h->peer_up_buf[c] + up_off * h->esz : nullptr;
+    p.dn_row = h->peer_dn_buf[c] ? (char *)h->peer_dn_buf[c] + N * h->esz : nullptr;  // its first owned row
+    p.up_row2 = h->peer_up_conc[c] ? (char *)h->peer_up_conc[c] + up_off * 4 : nullptr;
+    p.dn_row2 = h->peer_dn_conc[c] ? (char *)h->peer_dn_conc[c] + N * 4 : nullptr;
+    p.flag_up = h->peer_up_sync ? h->peer_up_sync + 1 : nullptr;  // its last band
+    p.flag_dn = h->peer_dn_sync ? h->peer_dn_sync + 0 : nullptr;  // its first band
+    p.my_first_done = h->sync_dev + 0;
+    p.my_last_done = h->sync_dev + 1;
     p.done_first = (unsigned int *)(h->sync_dev + 2);
     p.done_last = (unsigned int *)(h->sync_dev + 3);
     p.status = (unsigned int *)(h->sync_dev + 4);
-    p.push_up_grow = p.up_ghost ? h->row_begin : -1;
-    p.push_dn_grow = p.dn_ghost ? h->row_end - 1 : -1;
 #ifdef SBX_PEER_DEBUG
     static const unsigned dbg = [] { const char *e = getenv("SBX_PEER_DEBUG_BITS"); return e ? (unsigned)atoi(e) : 0u; }();
     p.debug = dbg;
 #endif
+    // the ghost rows of the local buffers are not written by these steps: a reader that wants them (a step that does
+    // not go through the ring kernels, the host-buffer step, get_thickness) fetches them first (ensure_ghosts)
+    if (!h->ghost_stale) h->stale_by_pull = true;
+    h->ghost_stale = true;
 }
 
 // decide whether this launch writes the pole rows inside the TMA kernel, and which arrival count it waits for.
@@ -1013,6 +1022,7 @@ static int32_t step_cpu_sem(sbx_drainage *h, double dt, const RgbArgs &rgb)
     int n = 0;
     if (h->strict) {
         // the reference's pass order: interior, poles, TFE (drainage.rs:314-389); colour afterwards
+        { int32_t rcg = ensure_ghosts(h); if (rcg != SBX_OK) return rcg; }
         RgbArgs none;
         memset(&none, 0, sizeof none);
         a.rgb = none;
@@ -1037,6 +1047,7 @@ static int32_t step_cpu_sem(sbx_drainage *h, double dt, const RgbArgs &rgb)
                 pushed = true;
             }
         }
+        if (!pushed) { int32_t rcg = ensure_ghosts(h); if (rcg != SBX_OK) return rcg; }
         const bool want_track = h->mm_track_mode == 1 || (h->mm_track_mode == 2 && h->mm_auto_on);
         const bool tracked = want_track && h->use_tma && march_tma_supported<T>(a) &&
                              ((!has_top || a.fold_top) && (!has_bottom || a.fold_bottom));  // the kernel writes every owned row
@@ -1105,7 +1116,7 @@ static int32_t step_cpu_sem(sbx_drainage *h, double dt, const RgbArgs &rgb)
         if (pushed) {
             h->launches += n;
             h->time += dt;
-            return SBX_OK;  // ghost rows were filled by the neighbours' kernels
+            return SBX_OK;  // the next step reads the neighbours' rows in place
         }
     }
     h->launches += n;
@@ -1145,6 +1156,7 @@ static int32_t step_wgsl_sem(sbx_drainage *h, double dt, const RgbArgs &rgb)
     a.l2_keep_edges = h->l2_keep_edges ? 1 : 0;
     const bool pushed = h->peer_enabled && h->use_tma && wgsl_tma_supported(a);
     if (pushed) fill_peer(h, a.peer);
+    else { int32_t rcg = ensure_ghosts(h); if (rcg != SBX_OK) return rcg; }
     CU(launch_wgsl(a, h->batch, h->band_rows, h->use_tma, h->stream, &n));
     if (rgb.mode != SBX_RGB_NONE && (h->row_begin == 0 || h->row_end == h->num_theta)) {
         // frozen pole rows still need their colour: shade them from the (unchanged) pole values
@@ -1157,7 +1169,7 @@ static int32_t step_wgsl_sem(sbx_drainage *h, double dt, const RgbArgs &rgb)
     h->cur = 1 - h->cur;
     h->launches += n;
     h->time += dt;  // gpu_drainage.rs:368
-    if (pushed) return SBX_OK;  // ghost rows of both fields were filled by the neighbours' kernels
+    if (pushed) return SBX_OK;  // the next step reads the neighbours' rows of both fields in place
     return halo_exchange(h);
 }
 
@@ -1275,7 +1287,9 @@ static int32_t do_steps(sbx_drainage *h, double dt, int32_t nsteps, const sbx_vi
     }
     int32_t rc = ensure_tables(h);
     if (rc != SBX_OK) return rc;
-    if (nsteps > 0 && (rc = ensure_ghosts(h)) != SBX_OK) return rc;
+    // (peer halo: the ring kernels read the neighbours' rows in place; the step functions fetch ghost rows only for
+    //  the launches that do not)
+    if (nsteps > 0 && !(h->peer_enabled && h->stale_by_pull) && (rc = ensure_ghosts(h)) != SBX_OK) return rc;
     RgbArgs rgb;
     rc = prepare_rgb(h, view, rgb);
     if (rc != SBX_OK) return rc;
@@ -1375,6 +1389,11 @@ static int32_t ensure_ghosts(sbx_drainage *h)
     if (!h->comm || !h->ghost_stale) return SBX_OK;
     h->ghost_stale = false;
     return halo_exchange(h);
+}
+
+static int32_t quiesce_peers(sbx_drainage *h)
+{
+    return h->peer_enabled ? ensure_ghosts(h) : SBX_OK;
 }
 
 static int host_chunk_rows(const sbx_drainage *h)
@@ -1482,6 +1501,7 @@ static int32_t step_host_pipelined(sbx_drainage *h, double dt, const sbx_view *v
     h->cur = 1 - h->cur;
     h->time += dt;
     h->ghost_stale = h->comm != nullptr;  // the new field's ghost rows are fetched when a device-resident step needs them
+    h->stale_by_pull = false;             // (and a peer-halo step must not read the neighbour's rows before that exchange)
     CU(cudaEventRecord(h->ev_out, h->copy_out));
     CU(cudaStreamWaitEvent(h->stream, h->ev_out, 0));
     CU(cudaStreamSynchronize(h->stream));
@@ -1583,7 +1603,8 @@ extern "C" int32_t sbx_drainage_step_host(sbx_drainage *h, double dt, int32_t ns
                                           void *host_out_rgb)
 {
     CHECK_H(h);
-    int32_t rc = SBX_OK;
+    int32_t rc = host_in ? quiesce_peers(h) : SBX_OK;
+    if (rc != SBX_OK) return rc;
     // (on a sharded handle the choice must be the same on every rank -- the two paths issue different NCCL calls -- so
     // it is made from the global grid, not from this rank's band height)
     const bool tall = h->comm ? h->num_theta >= 9 * sbx_comm_size(h->comm) : h->rows_local >= 8;
@@ -2346,6 +2367,7 @@ extern "C" int32_t sbx_interference_terms(double n_film, const double *d_nm, con
 static int32_t halo_exchange(sbx_drainage *h)
 {
     h->ghost_stale = false;
+    h->stale_by_pull = false;
     if (!h->comm) return SBX_OK;
     const char *err = nullptr;
     // my first owned row -> upper neighbour's bottom ghost; my last owned row -> lower neighbour's top ghost

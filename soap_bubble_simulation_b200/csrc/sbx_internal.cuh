@@ -63,24 +63,26 @@ struct RgbArgs {
     int n_spec;
 };
 
-// Peer-memory halo push (latitude-band sharding, one process per GPU): the CTAs that update a band's first /
-// last owned row store it straight into the neighbour's ghost row over NVLink, and the neighbours order
-// their steps with two monotonic flags instead of a collective.  See sbx_march_tma.cu.
+// Peer-memory halo (latitude-band sharding, one process per GPU): the band next to a neighbour reads the row it
+// needs straight out of the neighbour's field over NVLink (a bulk copy from the peer address into the shared-memory
+// ring), and the neighbours order their steps with two monotonic flags instead of a collective.  No kernel writes
+// remote memory: each band publishes "finished step e" in its own device memory and the neighbour polls that word.
+// (Round 1-2 pushed the boundary rows and the flag into the neighbour instead; remote stores made the end of every
+// launch ~5 us longer at 1024 rows per GPU, profiles/r02_peer_protocol_cost.txt.)  See sbx_march_tma.cu.
 struct PeerArgs {
-    void *up_ghost;                            // up neighbour's OUT buffer, its bottom ghost row (nullptr: none); element = T
-    void *dn_ghost;                            // down neighbour's OUT buffer, its top ghost row (nullptr: none)
-    void *up_ghost2, *dn_ghost2;               // WGSL semantics: the same rows of the concentration field
-    unsigned long long *up_flag_remote;        // up neighbour's "my lower neighbour finished step e" word
-    unsigned long long *dn_flag_remote;        // down neighbour's "my upper neighbour finished step e" word
-    const unsigned long long *flag_from_up;    // mine: written by the up neighbour
-    const unsigned long long *flag_from_dn;    // mine: written by the down neighbour
+    const void *up_row;                        // up neighbour's IN buffer of this step, its last owned row (nullptr: none); element = T
+    const void *dn_row;                        // down neighbour's IN buffer of this step, its first owned row (nullptr: none)
+    const void *up_row2, *dn_row2;             // WGSL semantics: the same rows of the concentration field
+    const unsigned long long *flag_up;         // up neighbour's "my last band finished step e" word (peer memory, polled)
+    const unsigned long long *flag_dn;         // down neighbour's "my first band finished step e" word (peer memory, polled)
+    unsigned long long *my_first_done;         // mine, local: published when every CTA of my first band has finished step e
+    unsigned long long *my_last_done;          // mine, local: the same for my last band
     unsigned int *done_first, *done_last;      // CTA counters of my first / last band
     unsigned int *status;                      // bit 0 set: a neighbour wait timed out (same word as StepArgs::dev_status)
     unsigned long long epoch;                  // number of this step, >= 1
-    int push_up_grow, push_dn_grow;            // global row whose new values go to the up / down neighbour (-1: none)
     int enabled;
 #ifdef SBX_PEER_DEBUG
-    unsigned debug;  // timing experiments only (results are wrong): 1 no wait, 2 no push, 4 no signal, 8 no system fence
+    unsigned debug;  // timing experiments only (results are wrong): 1 no wait, 4 no signal, 8 no system fence
 #endif
 };
 

@@ -124,8 +124,8 @@ __global__ void __launch_bounds__(PK == 2 ? 160 : 288, MinBlocks<T>::value) k_ma
     if (threadIdx.x >= C) {
         // ------------------------------------------------------------ producer warp (one lane issues)
         if (threadIdx.x == C) {
-            const bool touch_top = a.peer.enabled && a.peer.up_ghost && l0 == 1;
-            const bool touch_bot = a.peer.enabled && a.peer.dn_ghost && l1 == a.l_last && a.peer.push_dn_grow >= 0;
+            const bool touch_top = a.peer.enabled && a.peer.up_row && l0 == 1;
+            const bool touch_bot = a.peer.enabled && a.peer.dn_row && l1 == a.l_last;
             const bool wrapL = c0 == 0, wrapR = c0 + w >= N;
             const uint32_t main_elems = (uint32_t)w + (wrapL ? 0 : HALO) + (wrapR ? 0 : HALO);
             const uint32_t row_bytes = ((uint32_t)w + 2 * HALO) * (uint32_t)sizeof(T);
@@ -142,19 +142,29 @@ __global__ void __launch_bounds__(PK == 2 ? 160 : 288, MinBlocks<T>::value) k_ma
                 const int r_end = min(r_begin + kRowsPerStage, rows_load);
                 mbar_expect_tx(&full[s], row_bytes * (uint32_t)(r_end - r_begin));
                 for (int r = r_begin; r < r_end; ++r) {
-                    // ghost rows are written by the neighbours' previous step: wait for it before reading them
-#ifdef SBX_PEER_DEBUG
-                    if (!(a.peer.debug & 1u)) {
-#endif
-                    if (r == 0 && touch_top) wait_neighbour(a.peer.flag_from_up, a.peer.epoch - 1, a.peer.status);
-                    if (r == rows_load - 1 && touch_bot) wait_neighbour(a.peer.flag_from_dn, a.peer.epoch - 1, a.peer.status);
-#ifdef SBX_PEER_DEBUG
-                    }
-#endif
+                    // A band next to a neighbour takes that row out of the neighbour's field (peer memory): wait until the
+                    // neighbour's band has finished the previous step, then copy from there instead of the local ghost row
                     const T *grow_ptr = in + (long long)(l0 - 1 + r) * N;
+                    bool remote = false;
+                    if (r == 0 && touch_top) {
+#ifdef SBX_PEER_DEBUG
+                        if (!(a.peer.debug & 1u))
+#endif
+                        wait_neighbour(a.peer.flag_up, a.peer.epoch - 1, a.peer.status);
+                        grow_ptr = reinterpret_cast<const T *>(a.peer.up_row);
+                        remote = true;
+                    }
+                    if (r == rows_load - 1 && touch_bot) {
+#ifdef SBX_PEER_DEBUG
+                        if (!(a.peer.debug & 1u))
+#endif
+                        wait_neighbour(a.peer.flag_dn, a.peer.epoch - 1, a.peer.status);
+                        grow_ptr = reinterpret_cast<const T *>(a.peer.dn_row);
+                        remote = true;
+                    }
                     T *dst = ring + ((size_t)s * kRowsPerStage + (r - r_begin)) * rowf;
                     // ring row layout: [0,HALO) left halo | [HALO, HALO+w) main | [HALO+w, 2 HALO+w) right halo
-                    if (keep_edges && (r <= 1 || r >= rows_load - 2))
+                    if (keep_edges && !remote && (r <= 1 || r >= rows_load - 2))
                         tma_bulk_g2s_hint(dst + (wrapL ? HALO : 0), grow_ptr + c0 - (wrapL ? 0 : HALO),
                                           main_elems * (uint32_t)sizeof(T), &full[s], pol);
                     else
@@ -362,14 +372,6 @@ __global__ void __launch_bounds__(PK == 2 ? 160 : 288, MinBlocks<T>::value) k_ma
                 for (int k = 0; k < W; ++k) { run_lo = tmin<T>(run_lo, nw.v[k]); run_hi = tmax<T>(run_hi, nw.v[k]); }
             }
             store_h(out_p, nw.v);
-#ifdef SBX_PEER_DEBUG
-            if (a.peer.enabled && !(a.peer.debug & 2u)) {
-#else
-            if (a.peer.enabled) {  // boundary rows also land in the neighbours' ghost rows (peer stores over NVLink)
-#endif
-                if (grow == a.peer.push_up_grow) store_h(reinterpret_cast<T *>(a.peer.up_ghost) + jc, nw.v);
-                if (grow == a.peer.push_dn_grow) store_h(reinterpret_cast<T *>(a.peer.dn_ghost) + jc, nw.v);
-            }
             if constexpr (MODE != SBX_RGB_NONE) {
                 const float2 sc = *sc_p;
                 const float ccy = sc.y * a.rgb.cam_y;
@@ -492,7 +494,7 @@ __global__ void __launch_bounds__(PK == 2 ? 160 : 288, MinBlocks<T>::value) k_ma
     }
 
     if (a.peer.enabled)
-        peer_signal_done(a.peer, a.peer.up_ghost && l0 == 1, a.peer.dn_ghost && l1 == a.l_last && a.peer.push_dn_grow >= 0, C, tid);
+        peer_signal_done(a.peer, a.peer.up_row && l0 == 1, a.peer.dn_row && l1 == a.l_last, C, tid);
 }
 
 static size_t march_tma_smem_bytes(int packets, int stages)  // 16-byte packets per strip row
@@ -653,8 +655,8 @@ cudaError_t launch_march_tma(StepArgs<T> a, int batch, bool tfe, int band_rows_r
     const long long ctas_uniform = (long long)gx * ((rows + 23) / 24);
     if (a.peer.enabled && batch == 1 && edge_env > 0 && rows >= 8 * edge_env &&
         ctas_uniform >= (long long)edge_min_waves * device_sm_count() * occ) {
-        if (a.peer.up_ghost) a.top_rows = edge_env;
-        if (a.peer.dn_ghost && a.peer.push_dn_grow >= 0) a.bot_rows = edge_env;
+        if (a.peer.up_row) a.top_rows = edge_env;
+        if (a.peer.dn_row) a.bot_rows = edge_env;
         a.boundary_first = 1;
     }
     const int n_edge = (a.top_rows > 0) + (a.bot_rows > 0);

@@ -96,7 +96,7 @@ __device__ __forceinline__ void bar_consumers(int nthreads)
     asm volatile("bar.sync 1, %0;" ::"r"(nthreads) : "memory");
 }
 
-// ---- peer-memory halo push (PeerArgs): ordering between latitude neighbours, shared by the ring kernels
+// ---- peer-memory halo (PeerArgs): ordering between latitude neighbours, shared by the ring kernels
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long *p)
 {
     unsigned long long v;
@@ -127,8 +127,9 @@ __device__ __forceinline__ void wait_neighbour(const unsigned long long *flag, u
     asm volatile("fence.proxy.async;" ::: "memory");  // the rows the neighbour pushed are read by TMA next
 }
 
-// When every CTA of my first (last) band is done -- ghost row consumed, boundary row pushed -- tell the up (down)
-// neighbour that this step is finished here.  Called by all consumer threads of a CTA at the end of its band.
+// When every CTA of my first (last) band is done -- the neighbour's row consumed, my boundary row written and fenced --
+// publish that this step is finished here; the up (down) neighbour polls the word over NVLink before it reads my row
+// and before it overwrites the row I have just read.  Called by all consumer threads of a CTA at the end of its band.
 __device__ __forceinline__ void peer_signal_done(const PeerArgs &p, bool sig_up, bool sig_dn, int consumers, int tid)
 {
     if (!(sig_up || sig_dn)) return;
@@ -141,11 +142,11 @@ __device__ __forceinline__ void peer_signal_done(const PeerArgs &p, bool sig_up,
     if (tid == 0) {
         if (sig_up && atomicAdd(p.done_first, 1u) == gridDim.x - 1) {
             *p.done_first = 0u;
-            st_release_sys(p.up_flag_remote, p.epoch);
+            st_release_sys(p.my_first_done, p.epoch);
         }
         if (sig_dn && atomicAdd(p.done_last, 1u) == gridDim.x - 1) {
             *p.done_last = 0u;
-            st_release_sys(p.dn_flag_remote, p.epoch);
+            st_release_sys(p.my_last_done, p.epoch);
         }
     }
 }

@@ -74,8 +74,8 @@ __global__ void __launch_bounds__(288, 3) k_wgsl_tma(const WgslArgs a)
             const uint32_t row_bytes = 2u * ((uint32_t)w + 2 * kWHalo) * 4u;  // both fields
             const bool keep_edges = a.l2_keep_edges != 0;  // fields larger than L2, see k_march_tma
             const uint64_t pol = keep_edges ? l2_policy_evict_last() : 0ull;
-            const bool touch_top = a.peer.enabled && a.peer.up_ghost && l0 == 1;
-            const bool touch_bot = a.peer.enabled && a.peer.dn_ghost && l1 == a.l_last && a.peer.push_dn_grow >= 0;
+            const bool touch_top = a.peer.enabled && a.peer.up_row && l0 == 1;
+            const bool touch_bot = a.peer.enabled && a.peer.dn_row && l1 == a.l_last;
             for (int c = 0; c < nchunks; ++c) {
                 const int s = c % kWStages;
                 if (c >= kWStages) mbar_wait(&empty[s], (uint32_t)(((c / kWStages) - 1) & 1));
@@ -83,15 +83,25 @@ __global__ void __launch_bounds__(288, 3) k_wgsl_tma(const WgslArgs a)
                 const int r_end = min(r_begin + kWRowsPerStage, rows_load);
                 mbar_expect_tx(&full[s], row_bytes * (uint32_t)(r_end - r_begin));
                 for (int r = r_begin; r < r_end; ++r) {
-                    // ghost rows (both fields) are written by the neighbours' previous step: wait for it before reading them
-                    if (r == 0 && touch_top) wait_neighbour(a.peer.flag_from_up, a.peer.epoch - 1, a.peer.status);
-                    if (r == rows_load - 1 && touch_bot) wait_neighbour(a.peer.flag_from_dn, a.peer.epoch - 1, a.peer.status);
+                    // a band next to a neighbour reads that row of both fields out of the neighbour's buffers (peer memory),
+                    // once the neighbour's band has finished the previous step (see PeerArgs)
+                    const float *remote_h = nullptr, *remote_c = nullptr;
+                    if (r == 0 && touch_top) {
+                        wait_neighbour(a.peer.flag_up, a.peer.epoch - 1, a.peer.status);
+                        remote_h = reinterpret_cast<const float *>(a.peer.up_row);
+                        remote_c = reinterpret_cast<const float *>(a.peer.up_row2);
+                    }
+                    if (r == rows_load - 1 && touch_bot) {
+                        wait_neighbour(a.peer.flag_dn, a.peer.epoch - 1, a.peer.status);
+                        remote_h = reinterpret_cast<const float *>(a.peer.dn_row);
+                        remote_c = reinterpret_cast<const float *>(a.peer.dn_row2);
+                    }
                     float *slot = ring + ((size_t)s * kWRowsPerStage + (r - r_begin)) * slotf;
 #pragma unroll
                     for (int f = 0; f < 2; ++f) {
-                        const float *grow_ptr = (f == 0 ? hin : cin) + (long long)(l0 - 1 + r) * N;
+                        const float *grow_ptr = remote_h ? (f == 0 ? remote_h : remote_c) : (f == 0 ? hin : cin) + (long long)(l0 - 1 + r) * N;
                         float *dst = slot + f * rowf;
-                        if (keep_edges && (r <= 1 || r >= rows_load - 2))  // rows the neighbouring band reads again
+                        if (keep_edges && !remote_h && (r <= 1 || r >= rows_load - 2))  // rows the neighbouring band reads again
                             tma_bulk_g2s_hint(dst + (wrapL ? kWHalo : 0), grow_ptr + c0 - (wrapL ? 0 : kWHalo), main_floats * 4u, &full[s], pol);
                         else
                             tma_bulk_g2s(dst + (wrapL ? kWHalo : 0), grow_ptr + c0 - (wrapL ? 0 : kWHalo), main_floats * 4u, &full[s]);
@@ -218,16 +228,6 @@ __global__ void __launch_bounds__(288, 3) k_wgsl_tma(const WgslArgs a)
         if (active) {
             *reinterpret_cast<float4 *>(hout_p) = make_float4(hn[0], hn[1], hn[2], hn[3]);
             *reinterpret_cast<float4 *>(cout_p) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-            if (a.peer.enabled) {  // boundary rows of both fields also land in the neighbours' ghost rows (NVLink peer stores)
-                if (grow == a.peer.push_up_grow) {
-                    *reinterpret_cast<float4 *>(reinterpret_cast<float *>(a.peer.up_ghost) + jc) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-                    *reinterpret_cast<float4 *>(reinterpret_cast<float *>(a.peer.up_ghost2) + jc) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-                }
-                if (grow == a.peer.push_dn_grow) {
-                    *reinterpret_cast<float4 *>(reinterpret_cast<float *>(a.peer.dn_ghost) + jc) = make_float4(hn[0], hn[1], hn[2], hn[3]);
-                    *reinterpret_cast<float4 *>(reinterpret_cast<float *>(a.peer.dn_ghost2) + jc) = make_float4(cn[0], cn[1], cn[2], cn[3]);
-                }
-            }
             if constexpr (MODE != SBX_RGB_NONE) {
                 const float2 sc = *sc_p;
                 const float ccy = sc.y * a.rgb.cam_y;
@@ -268,7 +268,7 @@ __global__ void __launch_bounds__(288, 3) k_wgsl_tma(const WgslArgs a)
         if (--left == 0) break;
     }
     if (a.peer.enabled)
-        peer_signal_done(a.peer, a.peer.up_ghost && l0 == 1, a.peer.dn_ghost && l1 == a.l_last && a.peer.push_dn_grow >= 0, C, tid);
+        peer_signal_done(a.peer, a.peer.up_row && l0 == 1, a.peer.dn_row && l1 == a.l_last, C, tid);
 }
 
 bool wgsl_tma_supported(const WgslArgs &a)

@@ -78,7 +78,7 @@ class Comm:
 
     def enable_peer_halo(self, sim) -> None:
         """Switch `sim` (already attached to this communicator) from per-step NCCL send/recv to the in-kernel
-        peer-memory halo push: exchange CUDA IPC descriptors of the field buffers with the two latitude
+        peer-memory halo (the stencil kernel reads the neighbours' boundary rows in place over NVLink): exchange CUDA IPC descriptors of the field buffers with the two latitude
         neighbours and map them (sbx_drainage_ipc_export / _attach)."""
         import torch.distributed as dist
 

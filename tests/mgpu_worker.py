@@ -114,7 +114,7 @@ def main():
     sim.upload(band)
     comm = Comm(rank, world, local)
     sim.attach_comm(comm)
-    if halo in ("peer", "host"):
+    if halo in ("peer", "host", "peer_mix"):
         comm.enable_peer_halo(sim)
     dt = min(5e-3, 0.25 * dt_max(nt, nphi))  # 5 ms steps reach the first TFE front (t = 0.5 s) quickly
     view = S.View(mode=S.RGB_LUT, format=S.OUT_RGBA8)
@@ -132,13 +132,29 @@ def main():
         assert np.array_equal(sim.download(np.float32), cur)
         sim.step(dt, 3)
         sim.step_fused(dt, view, 1)
+    elif halo == "peer_mix":
+        # peer-halo steps read the neighbours' boundary rows in place; everything else that rewrites the field between
+        # them (upload, the host-buffer step) has to meet the neighbours first and hand fresh ghost rows to whoever
+        # wants them afterwards
+        a = steps // 3
+        sim.step(dt, a)
+        cur = sim.download(np.float32)
+        sim.upload(cur[0])                      # same values: the trajectory is unchanged
+        sim.step(dt, a)
+        cur = sim.download(np.float32).copy()
+        out_h = np.empty_like(cur)
+        for _ in range(2):
+            sim.step_host(dt, 1, view, cur, out_h, None)
+            cur, out_h = out_h, cur
+        sim.step(dt, steps - 2 * a - 3)
+        sim.step_fused(dt, view, 1)
     else:
         sim.step(dt, steps - 1)
         sim.step_fused(dt, view, 1)
     got = sim.download()[0]
     px = sim.download_rgb()[0]
     mn, mx = sim.minmax_global()
-    peer_bad = Comm.peer_status(sim) if halo in ("peer", "host") else 0
+    peer_bad = Comm.peer_status(sim) if halo in ("peer", "host", "peer_mix") else 0
     gathered = [None] * world
     dist.all_gather_object(gathered, (rb, re, got, px, sim.fronts(), peer_bad))
     ok = True

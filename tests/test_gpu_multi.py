@@ -27,6 +27,7 @@ def _free_port():
                                                      (61, 50, 30, 1, "nccl"), (256, 1024, 8, 0, "nccl"),
                                                      (64, 128, 120, 0, "peer"), (256, 1024, 60, 0, "peer"),
                                                      (16, 256, 40, 0, "peer"),
+                                                     (64, 128, 90, 0, "peer_mix"), (1300, 256, 30, 0, "peer_mix"),
                                                      (64, 128, 120, 0, "host"), (1300, 256, 12, 0, "host"),
                                                      (64, 128, 40, 0, "foam"), (32, 64, 30, 1, "foam"),
                                                      (64, 128, 120, 1, "peer"), (256, 1024, 40, 1, "peer"),
@@ -37,13 +38,16 @@ def _free_port():
 def test_sharded_matches_oracle(world, nt, nphi, steps, prec, halo):
     if _ngpu() < world:
         pytest.skip(f"needs {world} GPUs")
+    only = os.environ.get("SBX_TEST_WORLDS")  # e.g. "8": spend a big box's minutes on the sizes it alone can run
+    if only and str(world) not in only.split(","):
+        pytest.skip(f"SBX_TEST_WORLDS={only}")
     if nt < 2 * world:
         pytest.skip("fewer than two rows per band")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}",
            "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
            os.path.join(HERE, "mgpu_worker.py"), str(nt), str(nphi), str(steps), str(prec), halo]
     env = dict(os.environ)
-    if halo == "host":
+    if halo in ("host", "peer_mix"):
         env["SBX_HOST_CHUNK_ROWS"] = "56"  # several chunks per band: first / last chunk wait for the halo rows
     r = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env)
     sys.stdout.write(r.stdout[-2000:])
