@@ -1811,6 +1811,7 @@ extern "C" int32_t sbx_drainage_reset(sbx_drainage *h, double h0_m)
 {
     CHECK_H(h);
     h->mm_valid = h->mm_kernel_valid = false;
+    { int32_t rcq = quiesce_peers(h); if (rcq != SBX_OK) return rcq; }  // a neighbour may still be reading this band's rows
     std::fill(h->b_h0.begin(), h->b_h0.end(), h0_m);
     if (!h->f64 && !h->href_zero) {
         // offset storage follows the new uniform level, so the reset field is exact (delta == 0)
@@ -1829,7 +1830,8 @@ extern "C" int32_t sbx_drainage_reset(sbx_drainage *h, double h0_m)
     h->time = 0.0;
     h->fronts.clear();
     h->next_spawn = 0.5;
-    return SBX_OK;
+    // sharded: every rank resets (like upload); the exchange orders the neighbours' next in-place reads after this fill
+    return h->comm ? halo_exchange(h) : SBX_OK;
 }
 
 extern "C" int32_t sbx_drainage_set_marginal_regeneration(sbx_drainage *h, int32_t enabled)

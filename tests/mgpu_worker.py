@@ -114,7 +114,7 @@ def main():
     sim.upload(band)
     comm = Comm(rank, world, local)
     sim.attach_comm(comm)
-    if halo in ("peer", "host", "peer_mix"):
+    if halo in ("peer", "host", "peer_mix", "peer_reset"):
         comm.enable_peer_halo(sim)
     dt = min(5e-3, 0.25 * dt_max(nt, nphi))  # 5 ms steps reach the first TFE front (t = 0.5 s) quickly
     view = S.View(mode=S.RGB_LUT, format=S.OUT_RGBA8)
@@ -131,6 +131,13 @@ def main():
             cur, out_h = out_h, cur
         assert np.array_equal(sim.download(np.float32), cur)
         sim.step(dt, 3)
+        sim.step_fused(dt, view, 1)
+    elif halo == "peer_reset":
+        # reset on every rank between peer-halo steps: the ranks leave reset() at different times, and a neighbour that
+        # is ahead must not read this band's pre-reset rows (nor this band overwrite rows a neighbour is still reading)
+        sim.step(dt, 7)
+        sim.reset(5e-7)
+        sim.step(dt, steps - 1)
         sim.step_fused(dt, view, 1)
     elif halo == "peer_mix":
         # peer-halo steps read the neighbours' boundary rows in place; everything else that rewrites the field between
@@ -154,7 +161,7 @@ def main():
     got = sim.download()[0]
     px = sim.download_rgb()[0]
     mn, mx = sim.minmax_global()
-    peer_bad = Comm.peer_status(sim) if halo in ("peer", "host", "peer_mix") else 0
+    peer_bad = Comm.peer_status(sim) if halo in ("peer", "host", "peer_mix", "peer_reset") else 0
     gathered = [None] * world
     dist.all_gather_object(gathered, (rb, re, got, px, sim.fronts(), peer_bad))
     ok = True
@@ -165,7 +172,7 @@ def main():
         f0 = synthetic_field(nt, nphi)
         if prec == S.PREC_F32:
             f0 = f0.astype(np.float32).astype(np.float64)
-        ora.data[:] = f0
+        ora.data[:] = 5e-7 if halo == "peer_reset" else f0  # reset(): uniform film, clock and fronts start over
         ora.step(dt, steps)
         if prec == S.PREC_F64_STRICT:
             ok = np.array_equal(full, ora.data)

@@ -28,6 +28,7 @@ def _free_port():
                                                      (64, 128, 120, 0, "peer"), (256, 1024, 60, 0, "peer"),
                                                      (16, 256, 40, 0, "peer"),
                                                      (64, 128, 90, 0, "peer_mix"), (1300, 256, 30, 0, "peer_mix"),
+                                                     (1300, 256, 20, 0, "peer_reset"),
                                                      (64, 128, 120, 0, "host"), (1300, 256, 12, 0, "host"),
                                                      (64, 128, 40, 0, "foam"), (32, 64, 30, 1, "foam"),
                                                      (64, 128, 120, 1, "peer"), (256, 1024, 40, 1, "peer"),
