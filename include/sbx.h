@@ -361,7 +361,11 @@ int32_t sbx_comm_unique_id(uint8_t out128[128]);
 int32_t sbx_comm_init(const uint8_t id128[128], int32_t nranks, int32_t rank, int32_t device, sbx_comm **out);
 int32_t sbx_comm_destroy(sbx_comm *c);
 /* attach a communicator to a sharded handle: every step then exchanges one halo row with the
- * latitude-band neighbours (rank-1 above, rank+1 below) */
+ * latitude-band neighbours (rank-1 above, rank+1 below).  From then on the calls that change or step the field --
+ * sbx_drainage_upload / _upload_concentration / _reset / _step / _step_fused / _step_host -- and the ones that read
+ * ghost rows (_caustics) are collective over the ranks: every rank makes the same calls in the same order, as with
+ * any NCCL program (they contain the neighbour exchanges).  Queries (_download, _get_thickness, _minmax, _shade,
+ * _frame_stats, ...) are local. */
 int32_t sbx_drainage_attach_comm(sbx_drainage *h, sbx_comm *c);
 /* Peer-memory halo (all ranks on one NVLink/NVSwitch box).  Each rank exports a descriptor of its field
  * buffers (CUDA IPC handles), the caller moves the blobs between processes (torch.distributed), and attach maps
