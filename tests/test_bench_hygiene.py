@@ -86,3 +86,37 @@ print("RESULT", json.dumps([good["ok"], good["max_rel"], good["rgba_max_lsb"], g
     ok, rel, lsb, rows, bad_ok, bad_rel = json.loads(re.search(r"RESULT (.*)", out).group(1))
     assert ok and rel <= 1.2e-7 and lsb <= 1 and rows == 3 * 2 * 8
     assert not bad_ok and bad_rel > 1e-5
+
+
+def test_reference_arm_under_torchrun_runs_on_rank_zero_only():
+    """`bench.py --impl reference` launched like the CUDA arm at N = 2: rank 0 alone times the CPU path and prints the one
+    JSON line, the other rank exits 0 without work (no GPU, no rendezvous needed)."""
+    import socket
+
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
+                        "--master-addr", "127.0.0.1", "--master-port", str(port), os.path.join(ROOT, "bench.py"),
+                        "--impl", "reference", "--gpus", "2", "--steps", "1", "--warmup", "1"],
+                       capture_output=True, text=True, cwd=ROOT, timeout=900)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout[-2000:]
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["n_gpus"] == 2 and d["value"] > 0
+    assert d["cpu_baseline"]["kind"] in ("port", "reference") and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0 and d["e2e"]["value"] == d["value"]
+
+
+def test_update_traffic_reads_the_ncu_summary(tmp_path):
+    """scripts/update_traffic.py: the two dram__bytes sums of an ncu summary (with their units) become bytes per launch."""
+    sys.path.insert(0, os.path.join(ROOT, "scripts"))
+    try:
+        code = ("import sys; sys.path.insert(0, 'scripts'); import update_traffic as u\n"
+                "t = '  dram__bytes_read.sum      537.852672 Mbyte\\n  dram__bytes_write.sum   1.018144 Gbyte\\n'\n"
+                "print('RESULT', int(round(u.metric(t, 'dram__bytes_read.sum') + u.metric(t, 'dram__bytes_write.sum'))))")
+        out = run_py(code)
+    finally:
+        sys.path.pop(0)
+    assert "RESULT 1555996672" in out
