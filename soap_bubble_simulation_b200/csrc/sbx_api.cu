@@ -171,7 +171,7 @@ struct sbx_drainage {
     std::vector<float> spec_wl;
     float *caustic_buf = nullptr;
     sbx_comm *comm = nullptr;
-    // peer-memory halo push
+    // peer-memory halo (the ring kernels read the neighbours' boundary rows in place)
     bool peer_enabled = false;
     unsigned long long *sync_dev = nullptr;  // [0] flag from up, [1] flag from down, [2],[3] band counters, [4] status
     void *peer_up_buf[2] = {nullptr, nullptr}, *peer_dn_buf[2] = {nullptr, nullptr};
@@ -1057,7 +1057,7 @@ static int32_t step_cpu_sem(sbx_drainage *h, double dt, const RgbArgs &rgb)
             a.mm_next = h->mm_track[1 - set];
             h->mm_track_set = set;
         }
-        // NCCL halo path (the modes the peer push does not cover, or SBX halo = nccl): boundary first.  The bands next
+        // NCCL halo path (the modes the peer halo does not cover, or SBX halo = nccl): boundary first.  The bands next
         // to a neighbour run on a second, high-priority stream and their rows are exchanged there with ncclSend/ncclRecv
         // while the interior bands run on the handle's stream; the step ends when both are done.
         const int edge = 32;  // rows of a boundary launch
@@ -1651,7 +1651,7 @@ static int32_t enqueue_sample(sbx_drainage *h, int32_t bubble, double theta, dou
     const size_t pj_hi = (pj + 1) % (size_t)NP;
     const double tf = tc - (double)ti, pf = pc - (double)pj;
     // the lower of the two rows may be the bottom ghost row when it is kept current by the per-step NCCL exchange
-    // (with the in-kernel peer push the neighbour's store is ordered by device flags only, not by this stream)
+    // (with the in-kernel peer halo the ghost rows are not maintained at all: the kernels read the neighbour's rows in place)
     const bool ghost_ok = h->comm && !h->peer_enabled && !h->ghost_stale && h->row_end < h->num_theta;
     if ((int)ti < h->row_begin || (int)ti + 1 > h->row_end || ((int)ti + 1 == h->row_end && !ghost_ok))
         return fail(SBX_ERR_INVALID, "theta rows %zu,%zu are not owned by this band [%d,%d)", ti, ti + 1, h->row_begin, h->row_end);
@@ -2456,7 +2456,7 @@ extern "C" int32_t sbx_drainage_ipc_attach(sbx_drainage *h, const uint8_t *up, c
     CHECK_H(h);
     if (!h->comm) return fail(SBX_ERR_INVALID, "attach a communicator first (sbx_drainage_attach_comm)");
     if (h->strict || h->batch != 1)
-        return fail(SBX_ERR_UNSUPPORTED, "peer halo push covers the TMA ring kernels (f32 / f64 CPU semantics, WGSL semantics), one bubble");
+        return fail(SBX_ERR_UNSUPPORTED, "the peer halo covers the TMA ring kernels (f32 / f64 CPU semantics, WGSL semantics), one bubble");
     if ((up == nullptr) != (h->row_begin == 0) || (down == nullptr) != (h->row_end == h->num_theta))
         return fail(SBX_ERR_INVALID, "neighbour blobs do not match this band's position");
     auto open_one = [&](const uint8_t *blob, void *bufs[2], void *concs[2], unsigned long long **sync, int *rows) -> int32_t {
