@@ -223,6 +223,42 @@ def test_kat_drainage_single_step_uniform():
     assert abs((s.data[64, 0] - h0) + 4.0875e-16) < 1e-19
 
 
+def test_kat_drainage_discrete_mode_closed_form():
+    """A known answer that does not come from running any restatement: on h = a + eps * theta * cos(m phi) the reference's
+    finite differences (drainage.rs:352-367) have closed forms -- the second theta difference of a linear function is 0,
+    its central first difference is 1, and the periodic second phi difference of cos(m phi_j) is cos(m phi_j) *
+    (2 cos(m dphi) - 2) / dphi^2 -- so one Euler step (drainage.rs:346-378) is
+
+        h' = h + dt * ( -rho g / (3 eta) * h^3 sin(theta)
+                        + D / R^2 * eps cos(m phi) * (cot(theta) + theta * lam_m / sin^2(theta)) ),   lam_m = (2 cos(m dphi) - 2) / dphi^2
+
+    and each pole is the mean of the updated ring next to it (drainage.rs:480-503).  Checked on the increments."""
+    nt, nphi, m = 33, 48, 3
+    a, eps, dt = 500e-9, 40e-9, 0.05
+    p = O.DEFAULTS
+    c = p["density"] * p["gravity"] / (3.0 * p["viscosity"])
+    dth, dph = math.pi / (nt - 1), 2.0 * math.pi / nphi
+    theta = np.arange(nt) * dth
+    phi = np.arange(nphi) * dph
+    h = a + eps * theta[:, None] * np.cos(m * phi)[None, :]
+    s = O.OracleDrainage(nt, nphi)
+    s.data[:] = h
+    s.step(dt)
+    lam = (2.0 * math.cos(m * dph) - 2.0) / (dph * dph)
+    th = theta[1:-1, None]
+    lap = eps * np.cos(m * phi)[None, :] * (np.cos(th) / np.sin(th) + th * lam / np.sin(th) ** 2) / p["radius_m"] ** 2
+    inc = dt * (-c * h[1:-1] ** 3 * np.sin(th) + p["diffusion"] * lap)
+    got = s.data[1:-1] - h[1:-1]
+    # increments: diffusion up to 9e-12 m, gravity up to 3e-14 m, on a 5e-7 m field whose ulp is 1e-22 m -- the
+    # agreement (5e-23 m measured) is at the rounding of the stored field, 2e-9 of the smaller of the two terms
+    grav = dt * c * h[1:-1] ** 3 * np.sin(th)
+    assert np.abs(inc).max() > 5e-12 and grav.max() > 1e-14
+    assert np.abs(got - inc).max() <= 2e-22
+    new = h[1:-1] + inc
+    assert abs(s.data[0, 0] - new[0].mean()) <= 1e-21 and np.all(s.data[0] == s.data[0, 0])
+    assert abs(s.data[-1, 5] - new[-1].mean()) <= 1e-21 and np.all(s.data[-1] == s.data[-1, 0])
+
+
 def test_tfe_spawn_sequence():
     """First TFE front appears once 0.5 s have elapsed (drainage.rs:285,397-403) with the
     time-hashed parameters of drainage.rs:466-468 evaluated at current_time before the increment."""
