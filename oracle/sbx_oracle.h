@@ -20,7 +20,9 @@
  *     the drainage numbers are "parity unpinned" in the sense of the task statement.  What stands in for a
  *     reference output is a double entry: a second restatement of the drainage simulator, the f64 calculator, the
  *     WGSL drainage step and the LUT generator, transcribed separately from the Rust source (tests/numpy_restatement.py), agrees with this file bit for bit
- *     (tests/test_oracle_double_entry.py).
+ *     (tests/test_oracle_double_entry.py); and a known answer written down from the cited formula alone, with closed
+ *     forms of the finite differences on h = a + eps theta cos(m phi), pins every stencil coefficient and the pole means
+ *     to the rounding of the stored field (test_kat_drainage_discrete_mode_closed_form).
  *
  * All citations are file:line relative to the reference repository root.
  * Build: gcc -O2 -ffp-contract=off -fno-fast-math (Rust never contracts FMAs; glibc libm is what
