@@ -259,6 +259,45 @@ def test_kat_drainage_discrete_mode_closed_form():
     assert abs(s.data[-1, 5] - new[-1].mean()) <= 1e-21 and np.all(s.data[-1] == s.data[-1, 0])
 
 
+def test_kat_wgsl_discrete_mode_closed_form():
+    """The same kind of known answer for drainage.wgsl::drainage_step (drainage.wgsl:72-200), thickness and surfactant
+    concentration both of the form a + eps * theta * cos(m phi): Laplacians as above, the Marangoni term from the exact
+    central differences d/dtheta = eps cos(m phi), d/dphi = -eps theta sin(m phi) sin(m dphi) / dphi (:157-174), the
+    concentration update with its thickness coupling (:180-197), poles copied (:84-88).  The shader is f32, so the
+    closed form (f64) is met to a few ulps of the stored f32 values: 1e-13 m on increments up to 1.8e-8 m, 1e-7 on
+    concentration increments up to 0.023 (the 0.001 coupling term, 6e-8 at most here, is below that and not checked)."""
+    H, W, m = 33, 48, 3
+    a, eps, c0, delta = 500e-9, 40e-9, 0.4, 0.05
+    p = O.wgsl_params(grid_width=W, grid_height=H, marangoni_enabled=1, dt=1.0, diffusion_coeff=1e-7,
+                      surfactant_diffusion=1e-7, marangoni_coeff=2e3)
+    dth, dph = math.pi / (H - 1), 2.0 * math.pi / W
+    theta, phi = np.arange(H) * dth, np.arange(W) * dph
+    mode = theta[:, None] * np.cos(m * phi)[None, :]
+    h, c = (a + eps * mode).astype(np.float32), (c0 + delta * mode).astype(np.float32)
+    ho, co = O.wgsl_step(p, h, c)
+    ho, co = ho.reshape(H, W).astype(np.float64), co.reshape(H, W).astype(np.float64)
+    assert np.array_equal(ho[[0, -1]], h[[0, -1]]) and np.array_equal(co[[0, -1]], c[[0, -1]])  # poles: copied
+
+    R, dt = float(p.bubble_radius), float(p.dt)
+    th, cm, sm = theta[1:-1, None], np.cos(m * phi)[None, :], np.sin(m * phi)[None, :]
+    lam = (2.0 * math.cos(m * dph) - 2.0) / (dph * dph)
+    shape = cm * (np.cos(th) / np.sin(th) + th * lam / np.sin(th) ** 2)  # R^2 x Laplacian of theta cos(m phi)
+    hh, cc = h[1:-1].astype(np.float64), c[1:-1].astype(np.float64)
+    grav = -(float(p.density) * float(p.gravity) / (3.0 * float(p.viscosity))) * hh ** 3 * np.sin(th)
+    grad = np.sqrt((delta * cm / R) ** 2 + (-delta * th * sm * math.sin(m * dph) / dph / (R * np.sin(th))) ** 2)
+    mar = float(p.marangoni_coeff) * float(p.gamma_reduction) * grad * hh * hh
+    inc_h = dt * (grav + float(p.diffusion_coeff) * eps * shape / (R * R) + mar)
+    inc_c = dt * (float(p.surfactant_diffusion) * delta * shape / (R * R) + 0.001 * (eps * shape) * cc)
+    got_h, got_c = ho[1:-1] - hh, co[1:-1] - cc
+    # tolerances: ~4 ulp of h (5.7e-14 m) and of c (6e-8).  Leaving out the Marangoni term (4.5e-9 m), the diffusion term
+    # (1.8e-8 m) or the gravity term (6e-13 m) would each miss by more than that.
+    tol_h, tol_c = 2.5e-13, 2.5e-7
+    assert np.abs(dt * mar).max() > 1000 * tol_h and np.abs(inc_h - dt * mar).max() > 1000 * tol_h and np.abs(dt * grav).max() > 2 * tol_h
+    assert np.abs(inc_c).max() > 1000 * tol_c
+    assert np.abs(got_h - inc_h).max() <= tol_h
+    assert np.abs(got_c - inc_c).max() <= tol_c
+
+
 def test_tfe_spawn_sequence():
     """First TFE front appears once 0.5 s have elapsed (drainage.rs:285,397-403) with the
     time-hashed parameters of drainage.rs:466-468 evaluated at current_time before the increment."""
