@@ -224,39 +224,30 @@ def test_kat_drainage_single_step_uniform():
 
 
 def test_kat_drainage_discrete_mode_closed_form():
-    """A known answer that does not come from running any restatement: on h = a + eps * theta * cos(m phi) the reference's
-    finite differences (drainage.rs:352-367) have closed forms -- the second theta difference of a linear function is 0,
-    its central first difference is 1, and the periodic second phi difference of cos(m phi_j) is cos(m phi_j) *
-    (2 cos(m dphi) - 2) / dphi^2 -- so one Euler step (drainage.rs:346-378) is
+    """A known answer that does not come from running any restatement (tests/closed_form.py): on h = a + eps * theta *
+    cos(m phi) the reference's finite differences (drainage.rs:352-367) have closed forms, so one Euler step
+    (drainage.rs:346-378) is
 
         h' = h + dt * ( -rho g / (3 eta) * h^3 sin(theta)
                         + D / R^2 * eps cos(m phi) * (cot(theta) + theta * lam_m / sin^2(theta)) ),   lam_m = (2 cos(m dphi) - 2) / dphi^2
 
     and each pole is the mean of the updated ring next to it (drainage.rs:480-503).  Checked on the increments."""
-    nt, nphi, m = 33, 48, 3
-    a, eps, dt = 500e-9, 40e-9, 0.05
+    from closed_form import cpu_mode
+
+    nt, nphi, m, dt = 33, 48, 3, 0.05
     p = O.DEFAULTS
-    c = p["density"] * p["gravity"] / (3.0 * p["viscosity"])
-    dth, dph = math.pi / (nt - 1), 2.0 * math.pi / nphi
-    theta = np.arange(nt) * dth
-    phi = np.arange(nphi) * dph
-    h = a + eps * theta[:, None] * np.cos(m * phi)[None, :]
+    h, inc, top, bot = cpu_mode(nt, nphi, m, 500e-9, 40e-9, dt, p["density"], p["gravity"], p["viscosity"], p["diffusion"],
+                                p["radius_m"])
     s = O.OracleDrainage(nt, nphi)
     s.data[:] = h
     s.step(dt)
-    lam = (2.0 * math.cos(m * dph) - 2.0) / (dph * dph)
-    th = theta[1:-1, None]
-    lap = eps * np.cos(m * phi)[None, :] * (np.cos(th) / np.sin(th) + th * lam / np.sin(th) ** 2) / p["radius_m"] ** 2
-    inc = dt * (-c * h[1:-1] ** 3 * np.sin(th) + p["diffusion"] * lap)
     got = s.data[1:-1] - h[1:-1]
     # increments: diffusion up to 9e-12 m, gravity up to 3e-14 m, on a 5e-7 m field whose ulp is 1e-22 m -- the
     # agreement (5e-23 m measured) is at the rounding of the stored field, 2e-9 of the smaller of the two terms
-    grav = dt * c * h[1:-1] ** 3 * np.sin(th)
-    assert np.abs(inc).max() > 5e-12 and grav.max() > 1e-14
+    assert np.abs(inc).max() > 5e-12
     assert np.abs(got - inc).max() <= 2e-22
-    new = h[1:-1] + inc
-    assert abs(s.data[0, 0] - new[0].mean()) <= 1e-21 and np.all(s.data[0] == s.data[0, 0])
-    assert abs(s.data[-1, 5] - new[-1].mean()) <= 1e-21 and np.all(s.data[-1] == s.data[-1, 0])
+    assert abs(s.data[0, 0] - top) <= 1e-21 and np.all(s.data[0] == s.data[0, 0])
+    assert abs(s.data[-1, 5] - bot) <= 1e-21 and np.all(s.data[-1] == s.data[-1, 0])
 
 
 def test_kat_wgsl_discrete_mode_closed_form():
@@ -266,33 +257,20 @@ def test_kat_wgsl_discrete_mode_closed_form():
     concentration update with its thickness coupling (:180-197), poles copied (:84-88).  The shader is f32, so the
     closed form (f64) is met to a few ulps of the stored f32 values: 1e-13 m on increments up to 1.8e-8 m, 1e-7 on
     concentration increments up to 0.023 (the 0.001 coupling term, 6e-8 at most here, is below that and not checked)."""
-    H, W, m = 33, 48, 3
-    a, eps, c0, delta = 500e-9, 40e-9, 0.4, 0.05
+    from closed_form import wgsl_mode
+
+    H, W = 33, 48
     p = O.wgsl_params(grid_width=W, grid_height=H, marangoni_enabled=1, dt=1.0, diffusion_coeff=1e-7,
                       surfactant_diffusion=1e-7, marangoni_coeff=2e3)
-    dth, dph = math.pi / (H - 1), 2.0 * math.pi / W
-    theta, phi = np.arange(H) * dth, np.arange(W) * dph
-    mode = theta[:, None] * np.cos(m * phi)[None, :]
-    h, c = (a + eps * mode).astype(np.float32), (c0 + delta * mode).astype(np.float32)
+    h, c, inc_h, inc_c, grav, mar = wgsl_mode(H, W, 3, 500e-9, 40e-9, 0.4, 0.05, p)
     ho, co = O.wgsl_step(p, h, c)
     ho, co = ho.reshape(H, W).astype(np.float64), co.reshape(H, W).astype(np.float64)
     assert np.array_equal(ho[[0, -1]], h[[0, -1]]) and np.array_equal(co[[0, -1]], c[[0, -1]])  # poles: copied
-
-    R, dt = float(p.bubble_radius), float(p.dt)
-    th, cm, sm = theta[1:-1, None], np.cos(m * phi)[None, :], np.sin(m * phi)[None, :]
-    lam = (2.0 * math.cos(m * dph) - 2.0) / (dph * dph)
-    shape = cm * (np.cos(th) / np.sin(th) + th * lam / np.sin(th) ** 2)  # R^2 x Laplacian of theta cos(m phi)
-    hh, cc = h[1:-1].astype(np.float64), c[1:-1].astype(np.float64)
-    grav = -(float(p.density) * float(p.gravity) / (3.0 * float(p.viscosity))) * hh ** 3 * np.sin(th)
-    grad = np.sqrt((delta * cm / R) ** 2 + (-delta * th * sm * math.sin(m * dph) / dph / (R * np.sin(th))) ** 2)
-    mar = float(p.marangoni_coeff) * float(p.gamma_reduction) * grad * hh * hh
-    inc_h = dt * (grav + float(p.diffusion_coeff) * eps * shape / (R * R) + mar)
-    inc_c = dt * (float(p.surfactant_diffusion) * delta * shape / (R * R) + 0.001 * (eps * shape) * cc)
-    got_h, got_c = ho[1:-1] - hh, co[1:-1] - cc
+    got_h, got_c = ho[1:-1] - h[1:-1].astype(np.float64), co[1:-1] - c[1:-1].astype(np.float64)
     # tolerances: ~4 ulp of h (5.7e-14 m) and of c (6e-8).  Leaving out the Marangoni term (4.5e-9 m), the diffusion term
     # (1.8e-8 m) or the gravity term (6e-13 m) would each miss by more than that.
     tol_h, tol_c = 2.5e-13, 2.5e-7
-    assert np.abs(dt * mar).max() > 1000 * tol_h and np.abs(inc_h - dt * mar).max() > 1000 * tol_h and np.abs(dt * grav).max() > 2 * tol_h
+    assert np.abs(mar).max() > 1000 * tol_h and np.abs(inc_h - mar).max() > 1000 * tol_h and np.abs(grav).max() > 2 * tol_h
     assert np.abs(inc_c).max() > 1000 * tol_c
     assert np.abs(got_h - inc_h).max() <= tol_h
     assert np.abs(got_c - inc_c).max() <= tol_c
